@@ -1,0 +1,170 @@
+/* yolob200.h — C ABI of libyolob200.so: the B200-native (sm_100a) replacement for the
+ * TensorFlow ops that wizyoung/YOLOv3_TensorFlow's hot path builds its graph from.
+ *
+ * The reference has no FFI layer of its own (it is pure Python over TensorFlow), so
+ * each entry point below names the reference *call site* (file:line, relative to the
+ * reference repo) whose TF ops it replaces.  The Python package
+ * `yolov3_tensorflow_b200` binds these with ctypes and re-exposes the reference's
+ * Python API (model.yolov3, utils.nms_utils.gpu_nms, utils.misc_utils.load_weights).
+ *
+ * Conventions
+ *   - every function returns YB_OK (0) or a negative yb_status; text via
+ *     yb_last_error_string() (thread-local).
+ *   - the CALLER owns every buffer (inputs, outputs, workspaces, arenas); nothing is
+ *     allocated or freed on the device behind the caller's back.
+ *   - all work is enqueued on the cudaStream_t passed as `stream` (void*); no entry
+ *     point synchronises the device unless its comment says so.
+ *   - device pointers unless marked "host".  Activations are NHWC.
+ */
+#ifndef YOLOB200_H_
+#define YOLOB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum yb_status {
+  YB_OK = 0,
+  YB_ERR_INVALID_ARGUMENT = -1,
+  YB_ERR_CUDA = -2,
+  YB_ERR_UNSUPPORTED = -3,
+  YB_ERR_WORKSPACE = -4
+} yb_status;
+
+typedef enum yb_dtype { YB_F16 = 0, YB_BF16 = 1, YB_F32 = 2 } yb_dtype;
+
+/* layout of a conv weight tensor handed to the packer */
+typedef enum yb_wlayout {
+  YB_W_HWIO = 0, /* TensorFlow variable layout [kh,kw,Cin,Cout] (utils/misc_utils.py:120)   */
+  YB_W_OIHW = 1, /* darknet .weights stream layout (Cout,Cin,kh,kw) (utils/misc_utils.py:117) */
+  YB_W_OHWI = 2  /* engine layout [Cout,kh,kw,Cin] (K-major for the implicit GEMM)           */
+} yb_wlayout;
+
+int yb_version(void);
+const char* yb_last_error_string(void);
+/* device 0..: SM count and compute capability of the current device. */
+int yb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------
+ * Convolution  (replaces slim.conv2d + slim.batch_norm + leaky_relu + tf.add +
+ * tf.pad + resize_nearest_neighbor + tf.concat: utils/layer_utils.py:9-22,30,82-87,
+ * model.py:43-49,55-57,62,72)
+ * --------------------------------------------------------------------------------- */
+typedef struct yb_conv_desc {
+  int n, h, w;      /* input batch / height / width                                         */
+  int cin, cout;    /* real channel counts (cout = 255 for the detection heads)             */
+  int ksize;        /* 1 or 3                                                               */
+  int stride;       /* 1 (SAME) or 2 (pad 1 each side then VALID — darknet rule)            */
+  int in_ld;        /* elements between consecutive input pixels  (>= cin; concat slices)   */
+  int out_ld;       /* elements between consecutive output pixels (>= cout)                 */
+  int res_ld;       /* same for the residual input (ignored when res == NULL)               */
+  int dtype;        /* yb_dtype of x / w / res (and of out unless out_fp32)                 */
+  int out_fp32;     /* 1: write float32 (detection heads), 0: write `dtype`                 */
+  int leaky;        /* 1: leaky_relu(0.1) after scale/shift                                 */
+  int upsample2x;   /* 1: nearest-neighbour 2x: every output pixel is stored to its 4 places
+                          in an [n, 2*ho, 2*wo, out_ld] buffer (model.py:61,71)             */
+} yb_conv_desc;
+
+/* out[p, co] = act( scale[co] * sum_{r,s,ci} x[p*stride + (r,s) - pad, ci] * w[co,r,s,ci] + shift[co] ) (+ res[p, co])
+ *   x        [n,h,w,in_ld]   dtype
+ *   w_packed [cout_pad, ksize, ksize, cin] dtype, cout_pad = yb_conv_cout_pad(cout) (zero rows beyond cout)
+ *   scale, shift  float32 [cout_pad]   (BN folded: gamma/sqrt(var+eps), beta-mean*scale; heads: 1, bias)
+ *   res      nullable, [n,ho,wo,res_ld] dtype — added AFTER the activation (utils/layer_utils.py:30)
+ *   out      [n,ho,wo,out_ld] (or the 2x-upsampled buffer)
+ *   stat_sum/stat_sqsum nullable float32 [cout_pad]: when given, the per-channel sum and sum of squares of
+ *            the raw convolution result (before scale/shift) are atomically accumulated (BN batch statistics).
+ * Requires cin % 32 == 0 (the 3-channel stem has its own entry point).  tcgen05 implicit GEMM. */
+int yb_conv2d_fwd(const yb_conv_desc* d, const void* x, const void* w_packed, const float* scale,
+                  const float* shift, const void* res, void* out, float* stat_sum, float* stat_sqsum,
+                  void* stream);
+int yb_conv_cout_pad(int cout);
+
+/* First layer (darknet53_body/Conv, 3->32, 3x3 s1; utils/layer_utils.py:35): float32 NHWC image in,
+ * `dtype` NHWC out.  w is OHWI float32 [32,3,3,3]. */
+int yb_stem_conv_fwd(const float* x, const float* w_ohwi, const float* scale, const float* shift, int n, int h,
+                     int w, int cout, int dtype, int leaky, void* out, void* stream);
+
+/* Weight repack (utils/misc_utils.py:114-123 does (Cout,Cin,kh,kw) -> HWIO on the host):
+ * src float32 in `layout` -> dst `dtype` (or float32) OHWI [cout_pad,k,k,cin], rows >= cout zeroed. */
+int yb_pack_conv_weights(const float* src, int layout, int cout, int cin, int ksize, int cout_pad, int dtype,
+                         void* dst, void* stream);
+/* BN inference fold (model.py:35-41, eps=1e-5): scale = gamma/sqrt(var+eps), shift = beta - mean*scale. */
+int yb_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, int c, float eps,
+               float* scale, float* shift, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Decode  (replaces the ~40 elementwise TF ops of model.py:82-190 and the caller's
+ * pred_scores = pred_confs * pred_probs, test_single_image.py:55)
+ * --------------------------------------------------------------------------------- */
+/* reorg_layer (model.py:82-137) for one scale.  anchors3x2: host float[6] (w,h) pixels.
+ * xy_offset [gh,gw,1,2], boxes [n,gh,gw,3,4] (cx,cy,w,h px), conf_logits [n,gh,gw,3,1],
+ * prob_logits [n,gh,gw,3,C]; any output may be NULL. */
+int yb_reorg_layer(const float* feature_map, int n, int gh, int gw, int img_h, int img_w, int class_num,
+                   const float* anchors3x2, float* xy_offset, float* boxes, float* conf_logits,
+                   float* prob_logits, void* stream);
+/* predict (model.py:140-190) over the three scales (/32,/16,/8).  anchors9x2: host float[18].
+ * boxes [n,B,4] xyxy, confs [n,B,1], probs [n,B,C], scores [n,B,C] = conf*prob (nullable),
+ * B = 3*(h/32*w/32 + h/16*w/16 + h/8*w/8). */
+int yb_predict(const float* fm1, const float* fm2, const float* fm3, int n, int img_h, int img_w, int class_num,
+               const float* anchors9x2, float* boxes, float* confs, float* probs, float* scores, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * NMS  (replaces utils/nms_utils.py:8-48: greater_equal + boolean_mask x2 +
+ * tf.image.non_max_suppression + gather x3 per class + concat x3)
+ * --------------------------------------------------------------------------------- */
+int yb_nms_workspace_bytes(int n_images, int num_boxes, int num_classes, int max_boxes, size_t* bytes);
+/* Per image and class: keep score >= score_thresh, greedy NMS (IoU > iou_thresh suppresses; TF CPU-kernel
+ * arithmetic), at most max_boxes per class; classes concatenated ascending, descending score inside a class.
+ *   boxes [n,B,4] xyxy, scores [n,B,C]
+ *   out_boxes [n, C*max_boxes, 4], out_scores / out_labels / out_indices [n, C*max_boxes]
+ *   out_indices = index of the kept box in the ORIGINAL [B] axis (not exposed by the reference)
+ *   out_counts [n] (device int32) = K of each image. */
+int yb_nms(const float* boxes, const float* scores, int n_images, int num_boxes, int num_classes, int max_boxes,
+           float score_thresh, float iou_thresh, void* workspace, size_t workspace_bytes, float* out_boxes,
+           float* out_scores, int32_t* out_labels, int32_t* out_indices, int32_t* out_counts, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Network plan: the 75-conv Darknet-53 + YOLOv3 head of model.py:30-80 for a fixed
+ * (batch, H, W, dtype).  Holds tensor maps and the layer schedule; buffers are the
+ * caller's: one activation arena and one parameter arena.
+ * --------------------------------------------------------------------------------- */
+typedef struct yb_net yb_net;
+
+typedef struct yb_layer_info {
+  int index;          /* creation order == TF variable order == darknet .weights order  */
+  int cin, cout, ksize, stride;
+  int has_bn;         /* 0 for the three detection convs (bias, linear)                  */
+  int in_h, in_w, out_h, out_w;
+  int is_head;        /* 1: under yolov3_head, 0: darknet53_body                        */
+  int scope_index;    /* k of "Conv_k" inside its variable scope                        */
+  int upsample2x;     /* 1: output is stored 2x nearest-neighbour upsampled (model.py:61,71) */
+} yb_layer_info;
+
+int yb_net_create(yb_net** net, int class_num, int n, int h, int w, int dtype, int training);
+int yb_net_destroy(yb_net* net);
+int yb_net_num_layers(const yb_net* net);
+int yb_net_layer_info(const yb_net* net, int layer, yb_layer_info* info);
+int yb_net_arena_bytes(const yb_net* net, size_t* activation_bytes, size_t* param_bytes);
+/* Bind caller-owned arenas (256-byte aligned).  Must be called before set_params/forward. */
+int yb_net_bind(yb_net* net, void* activation_arena, size_t activation_bytes, void* param_arena,
+                size_t param_bytes);
+/* Upload one conv's parameters (device float32 pointers).  BN layers: gamma,beta,mean,var (bias NULL);
+ * detection convs: bias (others NULL).  Repacks/folds on `stream`. */
+int yb_net_set_conv_params(yb_net* net, int layer, const float* w, int layout, const float* gamma,
+                           const float* beta, const float* mean, const float* var, const float* bias,
+                           void* stream);
+/* forward (model.py:30-80), inference mode: images float32 [n,h,w,3] -> fm1 [n,h/32,w/32,D],
+ * fm2 [n,h/16,w/16,D], fm3 [n,h/8,w/8,D] float32, D = 3*(5+class_num). */
+int yb_net_forward(yb_net* net, const float* images, float* fm1, float* fm2, float* fm3, void* stream);
+/* device pointer + geometry of one layer's output activation (tests / debugging). */
+int yb_net_layer_output(const yb_net* net, int layer, void** ptr, int* ld, int* dtype);
+/* number of kernels one yb_net_forward enqueues (for bench.py's gpu_launches). */
+int yb_net_forward_launches(const yb_net* net);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YOLOB200_H_ */

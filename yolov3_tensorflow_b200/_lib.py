@@ -1,0 +1,96 @@
+"""ctypes binding of libyolob200.so (the C ABI declared in include/yolob200.h).
+
+The library is the product: there is no Python/PyTorch fallback.  Importing this
+module when the shared object is missing raises immediately.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libyolob200.so")
+
+YB_F16, YB_BF16, YB_F32 = 0, 1, 2
+YB_W_HWIO, YB_W_OIHW, YB_W_OHWI = 0, 1, 2
+
+
+class YoloB200Error(RuntimeError):
+    pass
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} not found: build it with ./build.sh (or python -c 'import __graft_entry__ as g; g.build()'). "
+        "yolov3_tensorflow_b200 has no CPU/PyTorch fallback.")
+
+lib = C.CDLL(LIB_PATH)
+
+vp, i32, f32, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [(n, i32) for n in ("n", "h", "w", "cin", "cout", "ksize", "stride", "in_ld", "out_ld", "res_ld",
+                                   "dtype", "out_fp32", "leaky", "upsample2x")]
+
+
+class LayerInfo(C.Structure):
+    _fields_ = [(n, i32) for n in ("index", "cin", "cout", "ksize", "stride", "has_bn", "in_h", "in_w", "out_h",
+                                   "out_w", "is_head", "scope_index", "upsample2x")]
+
+
+_SIGS = {
+    "yb_version": ([], i32),
+    "yb_last_error_string": ([], C.c_char_p),
+    "yb_device_info": ([C.POINTER(i32)] * 3, i32),
+    "yb_conv2d_fwd": ([C.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp], i32),
+    "yb_conv_cout_pad": ([i32], i32),
+    "yb_stem_conv_fwd": ([vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp], i32),
+    "yb_pack_conv_weights": ([vp, i32, i32, i32, i32, i32, i32, vp, vp], i32),
+    "yb_bn_fold": ([vp, vp, vp, vp, i32, f32, vp, vp, vp], i32),
+    "yb_reorg_layer": ([vp, i32, i32, i32, i32, i32, i32, C.POINTER(f32), vp, vp, vp, vp, vp], i32),
+    "yb_predict": ([vp, vp, vp, i32, i32, i32, i32, C.POINTER(f32), vp, vp, vp, vp, vp], i32),
+    "yb_nms_workspace_bytes": ([i32, i32, i32, i32, C.POINTER(sz)], i32),
+    "yb_nms": ([vp, vp, i32, i32, i32, i32, f32, f32, vp, sz, vp, vp, vp, vp, vp, vp], i32),
+    "yb_net_create": ([C.POINTER(vp), i32, i32, i32, i32, i32, i32], i32),
+    "yb_net_destroy": ([vp], i32),
+    "yb_net_num_layers": ([vp], i32),
+    "yb_net_layer_info": ([vp, i32, C.POINTER(LayerInfo)], i32),
+    "yb_net_arena_bytes": ([vp, C.POINTER(sz), C.POINTER(sz)], i32),
+    "yb_net_bind": ([vp, vp, sz, vp, sz], i32),
+    "yb_net_set_conv_params": ([vp, i32, vp, i32, vp, vp, vp, vp, vp, vp], i32),
+    "yb_net_forward": ([vp, vp, vp, vp, vp, vp], i32),
+    "yb_net_layer_output": ([vp, i32, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32)], i32),
+    "yb_net_forward_launches": ([vp], i32),
+}
+for _name, (_args, _ret) in _SIGS.items():
+    _fn = getattr(lib, _name)          # AttributeError here == header/library mismatch: fail loudly
+    _fn.argtypes = _args
+    _fn.restype = _ret
+
+EXPORTED = tuple(_SIGS)
+
+
+def check(rc: int, what: str = ""):
+    """Translate a yb_status into the Python exceptions the reference API raises."""
+    if rc == 0:
+        return
+    msg = lib.yb_last_error_string().decode("utf-8", "replace")
+    if rc == -1:
+        raise ValueError(f"{what}: {msg}")
+    raise YoloB200Error(f"{what}: status {rc}: {msg}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_handle():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def fptr(values):
+    arr = (f32 * len(values))(*[float(v) for v in values])
+    return arr

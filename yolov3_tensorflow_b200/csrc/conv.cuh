@@ -1,0 +1,31 @@
+// Shared between conv_igemm.cu (kernel + launcher) and net.cu (network plan).
+#pragma once
+#include "common.cuh"
+
+namespace yb {
+
+struct ConvParams {
+  int M, P, Q;            // output pixels (n*P*Q), output height, width
+  int cout;               // valid output channels
+  int cin;                // input channels (K per filter tap)
+  int ksize, stride, pad;
+  int im2col;             // 1: A via im2col TMA, 0: A via 2D tiled TMA
+  int num_m_tiles, num_n_tiles;
+  const float* scale;     // [cout_pad]
+  const float* shift;     // [cout_pad]
+  void* out;
+  long out_ld;
+  const void* res;
+  long res_ld;
+  int out_fp32, leaky, upsample;
+  float* stat_sum;        // nullable: BN batch statistics of the raw conv result
+  float* stat_sqsum;
+};
+
+int conv_prepare(const yb_conv_desc* d, const void* x, const void* w_packed, const float* scale, const float* shift,
+                 const void* res, void* out, float* stat_sum, float* stat_sqsum, CUtensorMap* tmA, CUtensorMap* tmB,
+                 ConvParams* p, int* cout_pad_out);
+int conv_launch(int dtype, int cout_pad, const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p,
+                cudaStream_t st);
+
+}  // namespace yb

@@ -1,0 +1,446 @@
+// Fused conv (+BN scale/shift +leaky +residual +2x-upsample +concat-slice store) as an
+// im2col-free implicit GEMM on the 5th-gen tensor cores:
+//
+//   D[M = n*ho*wo pixels, N = cout] = A[M, K = k*k*cin] * B[N, K]^T
+//
+//   A  : NHWC activations.  3x3 convs: TMA *im2col mode* (cuTensorMapEncodeIm2col) gathers
+//        128 consecutive output pixels x 64 channels of one filter tap per request — image
+//        borders (the darknet pad-1 rule, utils/layer_utils.py:10-21) and the batch tail
+//        come back zero-filled, so no padded copy of the input ever exists (K4 in SURVEY §2.3).
+//        1x1 convs: plain 2D tiled TMA over the [M, in_ld] matrix.
+//   B  : weights packed OHWI = [cout_pad, k*k*cin] K-major, 2D tiled TMA.
+//   D  : fp32 accumulators in TMEM (2 stages x BLOCK_N columns), tcgen05.mma issued by
+//        one thread, operands straight from 128B-swizzled shared memory.
+//
+// Warp roles (192 threads, persistent over tiles): warp0 = TMA producer, warp1 = TMEM
+// allocator + MMA issuer, warps 2..5 = epilogue (TMEM -> registers -> global), so the
+// epilogue of tile i overlaps the mainloop of tile i+1.
+//
+// Replaces: slim.conv2d/batch_norm/leaky_relu (utils/layer_utils.py:20, model.py:43-49),
+// tf.add (utils/layer_utils.py:30), tf.pad (:15-16), resize_nearest_neighbor (:86),
+// tf.concat (model.py:62,72).
+#include <cudaTypedefs.h>
+
+#include <type_traits>
+
+#include "common.cuh"
+#include "conv.cuh"
+
+namespace yb {
+
+static constexpr int BLOCK_M = 128;
+static constexpr int UMMA_K = 16;
+static constexpr int NUM_THREADS = 192;
+static constexpr int SMEM_BUDGET = 200 * 1024;  // operand ring; barriers + alignment slack on top
+
+template <int BN, int BK>
+struct Cfg {
+  static constexpr int A_BYTES = BLOCK_M * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
+  static constexpr int TMEM_COLS = 2 * BN;  // power of two >= 32 for BN in {64,128,256}
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr uint32_t SWIZZLE = (BK == 64) ? 2u : 4u;   // UMMA layout_type: 128B / 64B
+  static constexpr uint32_t SBO = 8 * BK * 2;                  // bytes between 8-row groups
+};
+
+template <typename T, int BN, int BK>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const ConvParams p) {
+  using C = Cfg<BN, BK>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + C::STAGES * C::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;                       // [STAGES] TMA -> MMA
+  uint64_t* empty_bar = bars + C::STAGES;          // [STAGES] MMA -> TMA
+  uint64_t* tfull_bar = bars + 2 * C::STAGES;      // [2] MMA -> epilogue
+  uint64_t* tempty_bar = bars + 2 * C::STAGES + 2; // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int kb_per_tap = p.cin / BK;
+  const int num_kb = p.ksize * p.ksize * kb_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / p.num_n_tiles) * BLOCK_M;
+      const int n0 = (tile % p.num_n_tiles) * BN;
+      // first output pixel of the tile -> (image, row, col); base input pixel of the 3x3 window
+      const int q = m0 % p.Q;
+      const int pp = (m0 / p.Q) % p.P;
+      const int img = m0 / (p.Q * p.P);
+      const int w_base = q * p.stride - p.pad;
+      const int h_base = pp * p.stride - p.pad;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int tap = kb / kb_per_tap;
+        const int c0 = (kb - tap * kb_per_tap) * BK;
+        if (lane == 0) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          if (p.im2col) {
+            tma_load_im2col_4d(sA + stage * C::A_BYTES, &tmA, &full_bar[stage], c0, w_base, h_base, img,
+                               (uint16_t)(tap % p.ksize), (uint16_t)(tap / p.ksize));
+          } else {
+            tma_load_2d(sA + stage * C::A_BYTES, &tmA, &full_bar[stage], c0, m0);
+          }
+          tma_load_2d(sB + stage * C::B_BYTES, &tmB, &full_bar[stage], tap * p.cin + c0, n0);
+        }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc_f16(BLOCK_M, BN, sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      if (lane == 0) mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue drained this accumulator
+      __syncwarp();
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        if (lane == 0) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * C::A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * C::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adesc = make_kmajor_desc(a_addr + k * UMMA_K * 2, C::SBO, C::SWIZZLE);
+            const uint64_t bdesc = make_kmajor_desc(b_addr + k * UMMA_K * 2, C::SBO, C::SWIZZLE);
+            umma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);                       // smem slot reusable once these MMAs retire
+          if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are this warp's
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m0 = (tile / p.num_n_tiles) * BLOCK_M;
+      const int n0 = (tile % p.num_n_tiles) * BN;
+      const int row = m0 + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      // output row(s)
+      long orow[4];
+      int nrep = 1;
+      if (p.upsample) {
+        const int q = row % p.Q;
+        const int pp = (row / p.Q) % p.P;
+        const int img = row / (p.Q * p.P);
+        const long W2 = 2L * p.Q;
+        const long base = ((long)img * 2 * p.P + 2 * pp) * W2 + 2 * q;
+        orow[0] = base; orow[1] = base + 1; orow[2] = base + W2; orow[3] = base + W2 + 1;
+        nrep = 4;
+      } else {
+        orow[0] = row;
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + ch * 32, r);
+        tmem_ld_wait();
+        const int col0 = n0 + ch * 32;
+        if (p.stat_sum != nullptr) {
+          // BN batch statistics of the raw conv output: reduce the warp's 32 rows per column
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float v = row_ok ? __uint_as_float(r[j]) : 0.f;
+            float s = v, s2 = v * v;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              s += __shfl_xor_sync(0xffffffffu, s, o);
+              s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            }
+            if (lane == j && col0 + j < p.cout) {
+              atomicAdd(p.stat_sum + col0 + j, s);
+              atomicAdd(p.stat_sqsum + col0 + j, s2);
+            }
+          }
+        }
+        if (row_ok) {
+          float v[32];
+          const float4* sc4 = reinterpret_cast<const float4*>(p.scale + col0);
+          const float4* sh4 = reinterpret_cast<const float4*>(p.shift + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 sc = __ldg(sc4 + j);
+            const float4 sh = __ldg(sh4 + j);
+            v[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), sc.x, sh.x);
+            v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), sc.y, sh.y);
+            v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), sc.z, sh.z);
+            v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), sc.w, sh.w);
+          }
+          if (p.leaky) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = leaky01(v[j]);
+          }
+          if (p.res != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const T*>(p.res) + (long)row * p.res_ld + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 u = __ldg(rp + j);
+              float2 f;
+              f = Pack2<T>::unpack(u.x); v[8 * j + 0] += f.x; v[8 * j + 1] += f.y;
+              f = Pack2<T>::unpack(u.y); v[8 * j + 2] += f.x; v[8 * j + 3] += f.y;
+              f = Pack2<T>::unpack(u.z); v[8 * j + 4] += f.x; v[8 * j + 5] += f.y;
+              f = Pack2<T>::unpack(u.w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
+            }
+          }
+          if (p.out_fp32) {
+            for (int rep = 0; rep < nrep; ++rep) {
+              float* op = static_cast<float*>(p.out) + orow[rep] * p.out_ld + col0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.cout) op[j] = v[j];
+            }
+          } else {
+            uint4 pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              pk[j].x = Pack2<T>::pack(v[8 * j + 0], v[8 * j + 1]);
+              pk[j].y = Pack2<T>::pack(v[8 * j + 2], v[8 * j + 3]);
+              pk[j].z = Pack2<T>::pack(v[8 * j + 4], v[8 * j + 5]);
+              pk[j].w = Pack2<T>::pack(v[8 * j + 6], v[8 * j + 7]);
+            }
+            for (int rep = 0; rep < nrep; ++rep) {
+              uint4* op = reinterpret_cast<uint4*>(static_cast<T*>(p.out) + orow[rep] * p.out_ld + col0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) op[j] = pk[j];
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ----------------------------------------------------------------------------------
+// host: tensor maps (driver entry points fetched at run time: no link-time libcuda)
+// ----------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode_tiled = nullptr;
+static PFN_cuTensorMapEncodeIm2col_v12000 g_encode_im2col = nullptr;
+
+static int load_driver_entry_points() {
+  if (g_encode_tiled && g_encode_im2col) return YB_OK;
+  cudaDriverEntryPointQueryResult qr;
+  void* fn = nullptr;
+  YB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+  if (qr != cudaDriverEntryPointSuccess || !fn) { set_error("cuTensorMapEncodeTiled not available"); return YB_ERR_CUDA; }
+  g_encode_tiled = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  YB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qr));
+  if (qr != cudaDriverEntryPointSuccess || !fn) { set_error("cuTensorMapEncodeIm2col not available"); return YB_ERR_CUDA; }
+  g_encode_im2col = reinterpret_cast<PFN_cuTensorMapEncodeIm2col_v12000>(fn);
+  return YB_OK;
+}
+
+static CUtensorMapDataType tm_dtype(int dtype) {
+  return dtype == YB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+}
+
+// 2D row-major [rows, cols] 16-bit matrix, row pitch `ld` elements; box = [box_rows, box_cols]
+int make_tmap_2d(CUtensorMap* tm, const void* base, int dtype, long rows, long cols, long ld, int box_rows,
+                 int box_cols, int weights) {
+  int rc = load_driver_entry_points();
+  if (rc) return rc;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapSwizzle sw = box_cols * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = g_encode_tiled(tm, tm_dtype(dtype), 2, const_cast<void*>(base), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                              weights ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): rows=%ld cols=%ld ld=%ld box=%dx%d", (int)r, rows, cols, ld,
+              box_rows, box_cols);
+    return YB_ERR_CUDA;
+  }
+  return YB_OK;
+}
+
+// NHWC activation seen as {C, W, H, N}; im2col traversal for a ksize x ksize window with
+// symmetric padding `pad` and traversal stride `stride`; one request = 128 pixels x bk channels.
+int make_tmap_im2col(CUtensorMap* tm, const void* base, int dtype, int n, int h, int w, int c, long ld, int ksize,
+                     int stride, int pad, int bk) {
+  int rc = load_driver_entry_points();
+  if (rc) return rc;
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)w * ld * 2, (cuuint64_t)h * w * ld * 2};
+  // base-pixel bounding box: [-pad, dim-1 + pad-(k-1)]  (cutlass conv/collective/detail.hpp fprop rule)
+  int lower[2] = {-pad, -pad};
+  int upper[2] = {pad - (ksize - 1), pad - (ksize - 1)};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUtensorMapSwizzle sw = bk * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = g_encode_im2col(tm, tm_dtype(dtype), 4, const_cast<void*>(base), dims, strides, lower, upper,
+                               (cuuint32_t)bk, (cuuint32_t)BLOCK_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeIm2col failed (%d): n=%d h=%d w=%d c=%d ld=%ld k=%d s=%d", (int)r, n, h, w, c, ld,
+              ksize, stride);
+    return YB_ERR_CUDA;
+  }
+  // Driver workaround used by CUTLASS (copy_traits_sm90_im2col.hpp): for tensors < 128 KiB
+  // drivers <= 13.1 set a descriptor bit that makes the im2col traversal fault.
+  int drv = 0;
+  cudaDriverGetVersion(&drv);
+  if (drv <= 13010 && (size_t)n * h * w * ld * 2 < 131072) {
+    reinterpret_cast<uint64_t*>(tm)[1] &= ~(1ull << 21);
+  }
+  return YB_OK;
+}
+
+template <typename T, int BN, int BK>
+static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t st) {
+  using C = Cfg<BN, BK>;
+  static bool attr_done = false;
+  auto kern = conv_igemm_kernel<T, BN, BK>;
+  if (!attr_done) {
+    YB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmA, tmB, p);
+  YB_CUDA(cudaGetLastError());
+  return YB_OK;
+}
+
+int conv_block_n(int cout_pad) { return (cout_pad % 128 == 0) ? 128 : 64; }
+int conv_block_k(int cin) { return (cin % 64 == 0) ? 64 : 32; }
+
+// Launch with prebuilt tensor maps (used by the network plan).
+int conv_launch(int dtype, int cout_pad, const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p,
+                cudaStream_t st) {
+  const int bn = conv_block_n(cout_pad);
+  const int bk = conv_block_k(p.cin);
+#define YB_DISPATCH(T)                                                         \
+  if (bn == 128 && bk == 64) return launch_cfg<T, 128, 64>(tmA, tmB, p, st); \
+  if (bn == 128 && bk == 32) return launch_cfg<T, 128, 32>(tmA, tmB, p, st); \
+  if (bn == 64 && bk == 64) return launch_cfg<T, 64, 64>(tmA, tmB, p, st);   \
+  if (bn == 64 && bk == 32) return launch_cfg<T, 64, 32>(tmA, tmB, p, st);
+  if (dtype == YB_F16) { YB_DISPATCH(__half) }
+  else if (dtype == YB_BF16) { YB_DISPATCH(__nv_bfloat16) }
+#undef YB_DISPATCH
+  set_error("conv_launch: unsupported dtype %d", dtype);
+  return YB_ERR_UNSUPPORTED;
+}
+
+// Build maps + params for one conv.  x/w/out pointers are baked into maps/params.
+int conv_prepare(const yb_conv_desc* d, const void* x, const void* w_packed, const float* scale, const float* shift,
+                 const void* res, void* out, float* stat_sum, float* stat_sqsum, CUtensorMap* tmA, CUtensorMap* tmB,
+                 ConvParams* p, int* cout_pad_out) {
+  YB_REQUIRE(d->ksize == 1 || d->ksize == 3, "conv: ksize must be 1 or 3 (got %d)", d->ksize);
+  YB_REQUIRE(d->stride == 1 || d->stride == 2, "conv: stride must be 1 or 2 (got %d)", d->stride);
+  YB_REQUIRE(!(d->ksize == 1 && d->stride != 1), "conv: 1x1 stride-2 is not on the YOLOv3 path");
+  YB_REQUIRE(d->cin % 32 == 0 && d->cin >= 32, "conv: cin must be a multiple of 32 (got %d); use yb_stem_conv_fwd", d->cin);
+  YB_REQUIRE(d->dtype == YB_F16 || d->dtype == YB_BF16, "conv: dtype must be f16 or bf16");
+  YB_REQUIRE(d->h % d->stride == 0 && d->w % d->stride == 0, "conv: h,w must be divisible by stride");
+  YB_REQUIRE(d->in_ld >= d->cin && d->in_ld % 8 == 0, "conv: in_ld %d invalid for cin %d", d->in_ld, d->cin);
+  YB_REQUIRE(x && w_packed && scale && shift && out, "conv: null pointer");
+  YB_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)out & 15) == 0 &&
+                 ((uintptr_t)res & 15) == 0,
+             "conv: pointers must be 16-byte aligned");
+  const int cout_pad = yb_conv_cout_pad(d->cout);
+  if (!d->out_fp32) {
+    YB_REQUIRE(d->cout % 32 == 0, "conv: 16-bit output needs cout %% 32 == 0 (got %d)", d->cout);
+    YB_REQUIRE(d->out_ld >= d->cout && d->out_ld % 8 == 0, "conv: out_ld %d invalid", d->out_ld);
+  } else {
+    YB_REQUIRE(d->out_ld >= d->cout, "conv: out_ld %d invalid", d->out_ld);
+  }
+  if (res) YB_REQUIRE(d->res_ld >= d->cout && d->res_ld % 8 == 0 && !d->out_fp32, "conv: res_ld %d invalid", d->res_ld);
+  YB_REQUIRE((stat_sum == nullptr) == (stat_sqsum == nullptr), "conv: stat_sum/stat_sqsum must both be given");
+  const int P = d->h / d->stride, Q = d->w / d->stride;
+  const int bn = conv_block_n(cout_pad), bk = conv_block_k(d->cin);
+  const int pad = d->ksize / 2;
+  p->M = d->n * P * Q; p->P = P; p->Q = Q;
+  p->cout = d->cout; p->cin = d->cin; p->ksize = d->ksize; p->stride = d->stride; p->pad = pad;
+  p->im2col = d->ksize == 3;
+  p->num_m_tiles = ceil_div(p->M, BLOCK_M);
+  p->num_n_tiles = cout_pad / bn;
+  p->scale = scale; p->shift = shift;
+  p->out = out; p->out_ld = d->out_ld; p->res = res; p->res_ld = d->res_ld;
+  p->out_fp32 = d->out_fp32; p->leaky = d->leaky; p->upsample = d->upsample2x;
+  p->stat_sum = stat_sum; p->stat_sqsum = stat_sqsum;
+  int rc;
+  if (p->im2col) {
+    rc = make_tmap_im2col(tmA, x, d->dtype, d->n, d->h, d->w, d->cin, d->in_ld, d->ksize, d->stride, pad, bk);
+  } else {
+    rc = make_tmap_2d(tmA, x, d->dtype, (long)d->n * d->h * d->w, d->cin, d->in_ld, BLOCK_M, bk, 0);
+  }
+  if (rc) return rc;
+  rc = make_tmap_2d(tmB, w_packed, d->dtype, cout_pad, (long)d->ksize * d->ksize * d->cin,
+                    (long)d->ksize * d->ksize * d->cin, bn, bk, 1);
+  if (rc) return rc;
+  *cout_pad_out = cout_pad;
+  return YB_OK;
+}
+
+}  // namespace yb
+
+extern "C" int yb_conv_cout_pad(int cout) { return (cout + 63) / 64 * 64; }
+
+extern "C" int yb_conv2d_fwd(const yb_conv_desc* d, const void* x, const void* w_packed, const float* scale,
+                             const float* shift, const void* res, void* out, float* stat_sum, float* stat_sqsum,
+                             void* stream) {
+  if (!d) { yb::set_error("conv: null descriptor"); return YB_ERR_INVALID_ARGUMENT; }
+  CUtensorMap tmA, tmB;
+  yb::ConvParams p;
+  int cout_pad = 0;
+  int rc = yb::conv_prepare(d, x, w_packed, scale, shift, res, out, stat_sum, stat_sqsum, &tmA, &tmB, &p, &cout_pad);
+  if (rc) return rc;
+  return yb::conv_launch(d->dtype, cout_pad, tmA, tmB, p, static_cast<cudaStream_t>(stream));
+}

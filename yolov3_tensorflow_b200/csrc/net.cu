@@ -1,0 +1,322 @@
+// Network plan: Darknet-53 + 3-scale YOLOv3 head (model.py:30-80, utils/layer_utils.py:24-79)
+// for a fixed (batch, H, W, dtype): layer schedule, activation/parameter arena layout,
+// TMA tensor maps.  concat (model.py:62,72) and NN-upsample (utils/layer_utils.py:82-87)
+// never run as ops: producers store straight into channel slices of the concat buffers.
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "conv.cuh"
+
+namespace yb {
+
+struct Ten {          // a view of an activation: buffer id + channel slice
+  int buf = -1;       // -1: network input image
+  int off = 0;        // first channel inside the buffer
+  int c = 0, h = 0, w = 0;
+};
+
+struct Buf {
+  int h, w, ld;       // [n, h, w, ld]
+  int fp32;           // detection outputs are float32
+  size_t offset = 0, bytes = 0;
+};
+
+struct Layer {
+  yb_layer_info info;
+  Ten in, out, res;   // res.buf == -2: none
+  bool upsample = false, out_fp32 = false;
+  int cout_pad = 0;
+  // parameter arena offsets (bytes)
+  size_t w_master = 0, w_packed = 0, gamma = 0, beta = 0, mean = 0, var = 0, bias = 0, scale = 0, shift = 0;
+  // prepared launch state
+  CUtensorMap tmA, tmB;
+  ConvParams params;
+  bool prepared = false;
+};
+
+}  // namespace yb
+
+struct yb_net {
+  int class_num, n, h, w, dtype, training;
+  std::vector<yb::Layer> layers;
+  std::vector<yb::Buf> bufs;
+  int fm_buf[3];
+  size_t act_bytes = 0, param_bytes = 0;
+  uint8_t* act = nullptr;
+  uint8_t* par = nullptr;
+};
+
+namespace yb {
+
+static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
+struct Builder {
+  yb_net* net;
+  int body_k = 0, head_k = 0;
+
+  int new_buf(int h, int w, int ld, int fp32) {
+    Buf b; b.h = h; b.w = w; b.ld = ld; b.fp32 = fp32;
+    net->bufs.push_back(b);
+    return (int)net->bufs.size() - 1;
+  }
+  // conv2d of utils/layer_utils.py:9-22.  dst: optional pre-allocated destination view.
+  Ten conv(const Ten& x, int cout, int k, int s, bool head, bool bn = true, const Ten* shortcut = nullptr,
+           const Ten* dst = nullptr, bool upsample = false) {
+    Layer L;
+    memset(&L.info, 0, sizeof(L.info));
+    L.info.index = (int)net->layers.size();
+    L.info.cin = x.c; L.info.cout = cout; L.info.ksize = k; L.info.stride = s; L.info.has_bn = bn ? 1 : 0;
+    L.info.in_h = x.h; L.info.in_w = x.w; L.info.out_h = x.h / s; L.info.out_w = x.w / s;
+    L.info.is_head = head ? 1 : 0;
+    L.info.scope_index = head ? head_k++ : body_k++;
+    L.in = x;
+    L.upsample = upsample;
+    L.info.upsample2x = upsample ? 1 : 0;
+    L.out_fp32 = !bn;
+    L.cout_pad = yb_conv_cout_pad(cout);
+    if (shortcut) L.res = *shortcut; else L.res.buf = -2;
+    Ten y;
+    if (dst) {
+      y = *dst;
+    } else {
+      y.buf = new_buf(x.h / s, x.w / s, cout, !bn);
+      y.off = 0;
+    }
+    y.c = cout;
+    y.h = (x.h / s) * (upsample ? 2 : 1);
+    y.w = (x.w / s) * (upsample ? 2 : 1);
+    L.out = y;
+    net->layers.push_back(L);
+    return y;
+  }
+  Ten res_block(const Ten& x, int f, const Ten* dst = nullptr) {   // utils/layer_utils.py:25-32
+    Ten a = conv(x, f, 1, 1, false);
+    return conv(a, 2 * f, 3, 1, false, true, &x, dst);
+  }
+  void yolo_block(const Ten& x, int f, Ten* route, Ten* net_out) {  // utils/layer_utils.py:71-79
+    Ten t = conv(x, f, 1, 1, true);
+    t = conv(t, 2 * f, 3, 1, true);
+    t = conv(t, f, 1, 1, true);
+    t = conv(t, 2 * f, 3, 1, true);
+    t = conv(t, f, 1, 1, true);
+    *route = t;
+    *net_out = conv(t, 2 * f, 3, 1, true);
+  }
+
+  void build() {
+    const int H = net->h, W = net->w, D = 3 * (5 + net->class_num);
+    // concat buffers (model.py:62,72): [upsampled | route]
+    const int cat1 = new_buf(H / 16, W / 16, 256 + 512, 0);
+    const int cat2 = new_buf(H / 8, W / 8, 128 + 256, 0);
+    Ten x; x.buf = -1; x.c = 3; x.h = H; x.w = W;
+    // ---- darknet53_body (utils/layer_utils.py:35-66) ----
+    Ten t = conv(x, 32, 3, 1, false);
+    t = conv(t, 64, 3, 2, false);
+    t = res_block(t, 32);
+    t = conv(t, 128, 3, 2, false);
+    for (int i = 0; i < 2; ++i) t = res_block(t, 64);
+    t = conv(t, 256, 3, 2, false);
+    Ten r1dst; r1dst.buf = cat2; r1dst.off = 128;
+    for (int i = 0; i < 8; ++i) t = res_block(t, 128, i == 7 ? &r1dst : nullptr);
+    const Ten route1 = t;
+    t = conv(t, 512, 3, 2, false);
+    Ten r2dst; r2dst.buf = cat1; r2dst.off = 256;
+    for (int i = 0; i < 8; ++i) t = res_block(t, 256, i == 7 ? &r2dst : nullptr);
+    const Ten route2 = t;
+    t = conv(t, 1024, 3, 2, false);
+    for (int i = 0; i < 4; ++i) t = res_block(t, 512);
+    const Ten route3 = t;
+    (void)route1; (void)route2;
+    // ---- yolov3_head (model.py:53-78) ----
+    Ten inter, nt;
+    yolo_block(route3, 512, &inter, &nt);
+    Ten fm1 = conv(nt, D, 1, 1, true, false);
+    Ten up1; up1.buf = cat1; up1.off = 0;
+    conv(inter, 256, 1, 1, true, true, nullptr, &up1, true);
+    Ten c1; c1.buf = cat1; c1.off = 0; c1.c = 768; c1.h = H / 16; c1.w = W / 16;
+    yolo_block(c1, 256, &inter, &nt);
+    Ten fm2 = conv(nt, D, 1, 1, true, false);
+    Ten up2; up2.buf = cat2; up2.off = 0;
+    conv(inter, 128, 1, 1, true, true, nullptr, &up2, true);
+    Ten c2; c2.buf = cat2; c2.off = 0; c2.c = 384; c2.h = H / 8; c2.w = W / 8;
+    yolo_block(c2, 128, &inter, &nt);
+    Ten fm3 = conv(nt, D, 1, 1, true, false);
+    net->fm_buf[0] = fm1.buf; net->fm_buf[1] = fm2.buf; net->fm_buf[2] = fm3.buf;
+
+    // ---- arenas ----
+    const size_t esz = 2;
+    size_t o = 0;
+    for (auto& b : net->bufs) {
+      b.bytes = (size_t)net->n * b.h * b.w * b.ld * (b.fp32 ? 4 : esz);
+      b.offset = o;
+      o = align256(o + b.bytes);
+    }
+    net->act_bytes = o;
+    o = 0;
+    for (auto& L : net->layers) {
+      const size_t kk = (size_t)L.info.ksize * L.info.ksize * L.info.cin;
+      L.w_master = o; o = align256(o + (size_t)L.info.cout * kk * 4);
+      L.w_packed = o; o = align256(o + (size_t)L.cout_pad * kk * esz);
+      const size_t cb = (size_t)L.cout_pad * 4;
+      if (L.info.has_bn) {
+        L.gamma = o; o = align256(o + cb);
+        L.beta = o;  o = align256(o + cb);
+        L.mean = o;  o = align256(o + cb);
+        L.var = o;   o = align256(o + cb);
+      } else {
+        L.bias = o;  o = align256(o + cb);
+      }
+      L.scale = o; o = align256(o + cb);
+      L.shift = o; o = align256(o + cb);
+    }
+    net->param_bytes = o;
+  }
+};
+
+static void* ten_ptr(const yb_net* net, const Ten& t) {
+  const Buf& b = net->bufs[t.buf];
+  return net->act + b.offset + (size_t)t.off * (b.fp32 ? 4 : 2);
+}
+
+__global__ void fill_kernel(float* p, int n, float v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+}  // namespace yb
+
+using namespace yb;
+
+extern "C" int yb_net_create(yb_net** out, int class_num, int n, int h, int w, int dtype, int training) {
+  YB_REQUIRE(out, "net_create: null out pointer");
+  YB_REQUIRE(class_num > 0 && n > 0, "net_create: bad class_num/batch");
+  YB_REQUIRE(h > 0 && w > 0 && h % 32 == 0 && w % 32 == 0, "net_create: H,W must be multiples of 32 (got %dx%d)", h, w);
+  YB_REQUIRE(dtype == YB_F16 || dtype == YB_BF16, "net_create: dtype must be f16 or bf16");
+  if (training) { set_error("net_create: training plans are not implemented in this build"); return YB_ERR_UNSUPPORTED; }
+  yb_net* net = new yb_net();
+  net->class_num = class_num; net->n = n; net->h = h; net->w = w; net->dtype = dtype; net->training = training;
+  Builder b{net};
+  b.build();
+  *out = net;
+  return YB_OK;
+}
+
+extern "C" int yb_net_destroy(yb_net* net) { delete net; return YB_OK; }
+
+extern "C" int yb_net_num_layers(const yb_net* net) { return net ? (int)net->layers.size() : YB_ERR_INVALID_ARGUMENT; }
+
+extern "C" int yb_net_layer_info(const yb_net* net, int layer, yb_layer_info* info) {
+  YB_REQUIRE(net && info && layer >= 0 && layer < (int)net->layers.size(), "layer_info: bad argument");
+  *info = net->layers[layer].info;
+  return YB_OK;
+}
+
+extern "C" int yb_net_arena_bytes(const yb_net* net, size_t* activation_bytes, size_t* param_bytes) {
+  YB_REQUIRE(net && activation_bytes && param_bytes, "arena_bytes: bad argument");
+  *activation_bytes = net->act_bytes;
+  *param_bytes = net->param_bytes;
+  return YB_OK;
+}
+
+extern "C" int yb_net_bind(yb_net* net, void* activation_arena, size_t activation_bytes, void* param_arena,
+                           size_t param_bytes) {
+  YB_REQUIRE(net && activation_arena && param_arena, "bind: null pointer");
+  YB_REQUIRE(activation_bytes >= net->act_bytes && param_bytes >= net->param_bytes, "bind: arena too small");
+  YB_REQUIRE(((uintptr_t)activation_arena & 255) == 0 && ((uintptr_t)param_arena & 255) == 0,
+             "bind: arenas must be 256-byte aligned");
+  net->act = static_cast<uint8_t*>(activation_arena);
+  net->par = static_cast<uint8_t*>(param_arena);
+  // prepare every tensor-core conv (layer 0 is the CUDA-core stem)
+  for (size_t i = 1; i < net->layers.size(); ++i) {
+    Layer& L = net->layers[i];
+    yb_conv_desc d;
+    memset(&d, 0, sizeof(d));
+    d.n = net->n; d.h = L.info.in_h; d.w = L.info.in_w; d.cin = L.info.cin; d.cout = L.info.cout;
+    d.ksize = L.info.ksize; d.stride = L.info.stride;
+    d.in_ld = net->bufs[L.in.buf].ld; d.out_ld = net->bufs[L.out.buf].ld;
+    d.res_ld = L.res.buf >= 0 ? net->bufs[L.res.buf].ld : 0;
+    d.dtype = net->dtype; d.out_fp32 = L.out_fp32; d.leaky = L.info.has_bn; d.upsample2x = L.upsample;
+    int cp = 0;
+    int rc = conv_prepare(&d, ten_ptr(net, L.in), net->par + L.w_packed,
+                          reinterpret_cast<const float*>(net->par + L.scale),
+                          reinterpret_cast<const float*>(net->par + L.shift),
+                          L.res.buf >= 0 ? ten_ptr(net, L.res) : nullptr, ten_ptr(net, L.out), nullptr, nullptr, &L.tmA,
+                          &L.tmB, &L.params, &cp);
+    if (rc) return rc;
+    L.prepared = true;
+  }
+  return YB_OK;
+}
+
+extern "C" int yb_net_set_conv_params(yb_net* net, int layer, const float* w, int layout, const float* gamma,
+                                      const float* beta, const float* mean, const float* var, const float* bias,
+                                      void* stream) {
+  YB_REQUIRE(net && net->par, "set_conv_params: net not bound");
+  YB_REQUIRE(layer >= 0 && layer < (int)net->layers.size() && w, "set_conv_params: bad argument");
+  Layer& L = net->layers[layer];
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int c = L.info.cout;
+  int rc = yb_pack_conv_weights(w, layout, c, L.info.cin, L.info.ksize, c, YB_F32, net->par + L.w_master, stream);
+  if (rc) return rc;
+  rc = yb_pack_conv_weights(w, layout, c, L.info.cin, L.info.ksize, L.cout_pad, net->dtype, net->par + L.w_packed, stream);
+  if (rc) return rc;
+  float* scale = reinterpret_cast<float*>(net->par + L.scale);
+  float* shift = reinterpret_cast<float*>(net->par + L.shift);
+  if (L.info.has_bn) {
+    YB_REQUIRE(gamma && beta && mean && var, "set_conv_params: layer %d needs gamma/beta/mean/var", layer);
+    YB_CUDA(cudaMemcpyAsync(net->par + L.gamma, gamma, c * 4, cudaMemcpyDeviceToDevice, st));
+    YB_CUDA(cudaMemcpyAsync(net->par + L.beta, beta, c * 4, cudaMemcpyDeviceToDevice, st));
+    YB_CUDA(cudaMemcpyAsync(net->par + L.mean, mean, c * 4, cudaMemcpyDeviceToDevice, st));
+    YB_CUDA(cudaMemcpyAsync(net->par + L.var, var, c * 4, cudaMemcpyDeviceToDevice, st));
+    rc = yb_bn_fold(gamma, beta, mean, var, c, 1e-5f, scale, shift, stream);   // model.py:37 epsilon
+    if (rc) return rc;
+  } else {
+    YB_REQUIRE(bias, "set_conv_params: layer %d needs a bias", layer);
+    YB_CUDA(cudaMemcpyAsync(net->par + L.bias, bias, c * 4, cudaMemcpyDeviceToDevice, st));
+    YB_CUDA(cudaMemsetAsync(shift, 0, L.cout_pad * 4, st));
+    YB_CUDA(cudaMemcpyAsync(shift, bias, c * 4, cudaMemcpyDeviceToDevice, st));
+    fill_kernel<<<ceil_div(L.cout_pad, 128), 128, 0, st>>>(scale, L.cout_pad, 1.0f);
+    YB_CUDA(cudaGetLastError());
+  }
+  return YB_OK;
+}
+
+extern "C" int yb_net_forward(yb_net* net, const float* images, float* fm1, float* fm2, float* fm3, void* stream) {
+  YB_REQUIRE(net && net->act && net->par, "forward: net not bound");
+  YB_REQUIRE(images, "forward: null images");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* user_fm[3] = {fm1, fm2, fm3};
+  {
+    Layer& L = net->layers[0];
+    int rc = yb_stem_conv_fwd(images, reinterpret_cast<const float*>(net->par + L.w_master),
+                              reinterpret_cast<const float*>(net->par + L.scale),
+                              reinterpret_cast<const float*>(net->par + L.shift), net->n, net->h, net->w, L.info.cout,
+                              net->dtype, 1, ten_ptr(net, L.out), stream);
+    if (rc) return rc;
+  }
+  for (size_t i = 1; i < net->layers.size(); ++i) {
+    Layer& L = net->layers[i];
+    ConvParams* p = &L.params;
+    if (!L.info.has_bn) {
+      int which = L.out.buf == net->fm_buf[0] ? 0 : (L.out.buf == net->fm_buf[1] ? 1 : 2);
+      p->out = user_fm[which] ? (void*)user_fm[which] : ten_ptr(net, L.out);
+    }
+    int rc = conv_launch(net->dtype, L.cout_pad, L.tmA, L.tmB, *p, st);
+    if (rc) return rc;
+  }
+  return YB_OK;
+}
+
+extern "C" int yb_net_layer_output(const yb_net* net, int layer, void** ptr, int* ld, int* dtype) {
+  YB_REQUIRE(net && net->act && layer >= 0 && layer < (int)net->layers.size() && ptr && ld && dtype,
+             "layer_output: bad argument");
+  const Layer& L = net->layers[layer];
+  *ptr = ten_ptr(net, L.out);
+  *ld = net->bufs[L.out.buf].ld;
+  *dtype = L.out_fp32 ? YB_F32 : net->dtype;
+  return YB_OK;
+}
+
+extern "C" int yb_net_forward_launches(const yb_net* net) { return net ? (int)net->layers.size() : 0; }

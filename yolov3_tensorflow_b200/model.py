@@ -1,0 +1,262 @@
+"""`yolov3` — the reference's model class (model.py:12-365 of wizyoung/YOLOv3_TensorFlow)
+re-hosted on the B200 engine.
+
+Same constructor and method names/arguments as the reference.  The reference methods
+build TF1 graph nodes; these run eagerly: they take/return CUDA `torch.Tensor`s (used
+purely as device-buffer containers, NHWC, float32 at the API surface) and enqueue
+hand-written sm_100a kernels from libyolob200.so on the current CUDA stream.
+There is no torch op on the compute path and no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check, ptr, stream_handle
+
+
+def _dtype_code(dtype):
+    if dtype in ("fp16", "float16", torch.float16, _lib.YB_F16):
+        return _lib.YB_F16, torch.float16
+    if dtype in ("bf16", "bfloat16", torch.bfloat16, _lib.YB_BF16):
+        return _lib.YB_BF16, torch.bfloat16
+    raise ValueError(f"unsupported compute dtype {dtype!r} (fp16 or bf16)")
+
+
+def _as_cuda_f32(x, device):
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+    if not isinstance(x, torch.Tensor):
+        raise TypeError(f"expected a torch.Tensor or numpy array, got {type(x)}")
+    if x.dtype != torch.float32:
+        raise TypeError(f"expected float32, got {x.dtype}")
+    if not x.is_cuda:
+        x = x.to(device, non_blocking=True)
+    return x.contiguous()
+
+
+class _Plan:
+    """One yb_net (fixed batch/H/W) plus the arenas it is bound to."""
+
+    def __init__(self, model, n, h, w):
+        self.n, self.h, self.w = n, h, w
+        self.handle = C.c_void_p()
+        check(lib.yb_net_create(C.byref(self.handle), model.class_num, n, h, w, model._dtype_code, 0), "yb_net_create")
+        a, p = C.c_size_t(), C.c_size_t()
+        check(lib.yb_net_arena_bytes(self.handle, C.byref(a), C.byref(p)), "yb_net_arena_bytes")
+        dev = model.device
+        self.act = torch.zeros(max(a.value, 256), dtype=torch.uint8, device=dev)
+        self.par = torch.zeros(max(p.value, 256), dtype=torch.uint8, device=dev)
+        check(lib.yb_net_bind(self.handle, ptr(self.act), self.act.numel(), ptr(self.par), self.par.numel()), "yb_net_bind")
+        self.param_version = -1
+        self.num_layers = lib.yb_net_num_layers(self.handle)
+
+    def layer_info(self, i):
+        info = _lib.LayerInfo()
+        check(lib.yb_net_layer_info(self.handle, i, C.byref(info)), "yb_net_layer_info")
+        return info
+
+    def layer_output(self, i):
+        """Arena view of one layer's output activation ([n,h,w,ld-strided] -> [n,h,w,cout])."""
+        p, ld, dt = C.c_void_p(), C.c_int(), C.c_int()
+        check(lib.yb_net_layer_output(self.handle, i, C.byref(p), C.byref(ld), C.byref(dt)), "yb_net_layer_output")
+        info = self.layer_info(i)
+        tdt = {0: torch.float16, 1: torch.bfloat16, 2: torch.float32}[dt.value]
+        esz = 4 if dt.value == 2 else 2
+        off = p.value - self.act.data_ptr()
+        up = 2 if info.upsample2x else 1
+        oh, ow = info.out_h * up, info.out_w * up
+        nelem = ((self.n * oh * ow - 1) * ld.value + info.cout)
+        flat = self.act[off: off + nelem * esz].view(tdt)
+        return flat.as_strided((self.n, oh, ow, info.cout), (oh * ow * ld.value, ow * ld.value, ld.value, 1))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                lib.yb_net_destroy(self.handle)
+        except Exception:
+            pass
+
+
+class yolov3(object):
+
+    def __init__(self, class_num, anchors, use_label_smooth=False, use_focal_loss=False, batch_norm_decay=0.999,
+                 weight_decay=5e-4, use_static_shape=True, dtype="fp16", device=None):
+        # model.py:14-28 (same meaning); `dtype`/`device` are engine additions.
+        self.class_num = int(class_num)
+        self.anchors = np.asarray(anchors, dtype=np.float32).reshape(-1, 2)
+        if self.anchors.shape != (9, 2):
+            raise ValueError(f"anchors must be [9,2] (w,h) pixels, got {self.anchors.shape}")
+        self.batch_norm_decay = batch_norm_decay
+        self.use_label_smooth = use_label_smooth
+        self.use_focal_loss = use_focal_loss
+        self.weight_decay = weight_decay
+        self.use_static_shape = use_static_shape
+        self._dtype_code, self._torch_dtype = _dtype_code(dtype)
+        if not torch.cuda.is_available():
+            raise _lib.YoloB200Error("yolov3_tensorflow_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.img_size = None
+        self._plans = {}
+        self._params = None          # list of 75 dicts of CUDA float32 tensors
+        self._param_layout = _lib.YB_W_HWIO
+        self._param_version = 0
+
+    # ------------------------------------------------------------------ parameters
+    @staticmethod
+    def conv_table(class_num=80):
+        """(cin, cout, ksize, stride, has_bn) of the 75 convs in creation order
+        (== TF variable order == darknet .weights order)."""
+        t = []
+        c = 3
+
+        def conv(co, k, s=1, bn=True):
+            nonlocal c
+            t.append((c, co, k, s, bn))
+            c = co
+
+        conv(32, 3); conv(64, 3, 2)
+        for reps, f in ((1, 32), (2, 64), (8, 128), (8, 256), (4, 512)):
+            for _ in range(reps):
+                conv(f, 1); conv(2 * f, 3)
+            if f != 512:
+                conv(4 * f, 3, 2)
+        D = 3 * (5 + class_num)
+        for cin, f in ((1024, 512), (768, 256), (384, 128)):
+            c = cin
+            for _ in range(3):
+                conv(f, 1); conv(2 * f, 3)
+            conv(D, 1, 1, False)
+            if f != 128:
+                c = f
+                conv(f // 2, 1)
+        return t
+
+    def set_params(self, params, layout="HWIO"):
+        """params: 75 dicts in creation order with 'w' (+ 'gamma','beta','mean','var' | 'b'),
+        numpy or torch float32.  layout of 'w': 'HWIO' (TF variables) or 'OIHW' (darknet)."""
+        table = self.conv_table(self.class_num)
+        if len(params) != len(table):
+            raise ValueError(f"expected {len(table)} conv parameter sets, got {len(params)}")
+        out = []
+        for i, (p, (cin, cout, k, s, bn)) in enumerate(zip(params, table)):
+            q = {}
+            want = (k, k, cin, cout) if layout == "HWIO" else (cout, cin, k, k)
+            for name, v in p.items():
+                tv = torch.as_tensor(np.ascontiguousarray(v) if isinstance(v, np.ndarray) else v, dtype=torch.float32)
+                q[name] = tv.to(self.device).contiguous()
+            if tuple(q["w"].shape) != want:
+                raise ValueError(f"conv {i}: weight shape {tuple(q['w'].shape)} != {want}")   # tf.assign validate_shape
+            need = ("gamma", "beta", "mean", "var") if bn else ("b",)
+            for name in need:
+                if name not in q or q[name].numel() != cout:
+                    raise ValueError(f"conv {i}: missing/ill-shaped '{name}'")
+            out.append(q)
+        self._params = out
+        self._param_layout = _lib.YB_W_HWIO if layout == "HWIO" else _lib.YB_W_OIHW
+        self._param_version += 1
+
+    def init_params(self, seed=0):
+        """Random init as the reference graph would: Glorot-uniform conv weights,
+        gamma=1, beta=0, moving mean 0 / variance 1, zero detection biases (model.py:55-57)."""
+        rng = np.random.default_rng(seed)
+        ps = []
+        for cin, cout, k, s, bn in self.conv_table(self.class_num):
+            lim = math.sqrt(6.0 / (k * k * (cin + cout)))
+            p = {"w": rng.uniform(-lim, lim, (k, k, cin, cout)).astype(np.float32)}
+            if bn:
+                p.update(gamma=np.ones(cout, np.float32), beta=np.zeros(cout, np.float32),
+                         mean=np.zeros(cout, np.float32), var=np.ones(cout, np.float32))
+            else:
+                p["b"] = np.zeros(cout, np.float32)
+            ps.append(p)
+        self.set_params(ps, "HWIO")
+
+    def _plan(self, n, h, w):
+        key = (n, h, w)
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = _Plan(self, n, h, w)
+            self._plans[key] = plan
+        if plan.param_version != self._param_version:
+            if self._params is None:
+                raise _lib.YoloB200Error("no parameters: call load_weights(model, file), set_params() or init_params()")
+            st = stream_handle()
+            for i, q in enumerate(self._params):
+                check(lib.yb_net_set_conv_params(plan.handle, i, ptr(q["w"]), self._param_layout, ptr(q.get("gamma")),
+                                                 ptr(q.get("beta")), ptr(q.get("mean")), ptr(q.get("var")),
+                                                 ptr(q.get("b")), st), f"yb_net_set_conv_params[{i}]")
+            plan.param_version = self._param_version
+        return plan
+
+    # ------------------------------------------------------------------ model.py:30-80
+    def forward(self, inputs, is_training=False, reuse=False):
+        """inputs float32 [N,H,W,3] in [0,1] (RGB) -> (feature_map_1, feature_map_2, feature_map_3),
+        float32 NHWC [N,H/32,W/32,3*(5+C)], [N,H/16,...], [N,H/8,...].  Sets self.img_size (model.py:33)."""
+        x = _as_cuda_f32(inputs, self.device)
+        if x.dim() != 4 or x.shape[3] != 3:
+            raise ValueError(f"inputs must be [N,H,W,3], got {tuple(x.shape)}")
+        if is_training:
+            raise _lib.YoloB200Error("is_training=True is not available in this build of the engine")
+        n, h, w = int(x.shape[0]), int(x.shape[1]), int(x.shape[2])
+        if h % 32 or w % 32:
+            raise ValueError(f"H and W must be multiples of 32, got {h}x{w}")
+        self.img_size = (h, w)
+        plan = self._plan(n, h, w)
+        D = 3 * (5 + self.class_num)
+        fms = [torch.empty((n, h // s, w // s, D), dtype=torch.float32, device=self.device) for s in (32, 16, 8)]
+        check(lib.yb_net_forward(plan.handle, ptr(x), ptr(fms[0]), ptr(fms[1]), ptr(fms[2]), stream_handle()),
+              "yb_net_forward")
+        self._last_plan = plan
+        return fms[0], fms[1], fms[2]
+
+    # ------------------------------------------------------------------ model.py:82-137
+    def reorg_layer(self, feature_map, anchors):
+        if self.img_size is None:
+            raise _lib.YoloB200Error("reorg_layer: call forward() first (it records img_size, model.py:33)")
+        fm = _as_cuda_f32(feature_map, self.device)
+        anchors = np.asarray(anchors, np.float32).reshape(3, 2)
+        n, gh, gw, d = fm.shape
+        C_ = self.class_num
+        if d != 3 * (5 + C_):
+            raise ValueError(f"feature_map last dim {d} != 3*(5+{C_})")
+        dev = self.device
+        xy = torch.empty((gh, gw, 1, 2), dtype=torch.float32, device=dev)
+        boxes = torch.empty((n, gh, gw, 3, 4), dtype=torch.float32, device=dev)
+        conf = torch.empty((n, gh, gw, 3, 1), dtype=torch.float32, device=dev)
+        prob = torch.empty((n, gh, gw, 3, C_), dtype=torch.float32, device=dev)
+        check(lib.yb_reorg_layer(ptr(fm), n, gh, gw, self.img_size[0], self.img_size[1], C_,
+                                 _lib.fptr(anchors.reshape(-1)), ptr(xy), ptr(boxes), ptr(conf), ptr(prob),
+                                 stream_handle()), "yb_reorg_layer")
+        return xy, boxes, conf, prob
+
+    # ------------------------------------------------------------------ model.py:140-190
+    def predict(self, feature_maps, return_scores=False):
+        """-> boxes [N,B,4] (xmin,ymin,xmax,ymax), confs [N,B,1], probs [N,B,C]
+        (+ scores = confs*probs, the caller-side op of test_single_image.py:55, if return_scores)."""
+        if self.img_size is None:
+            raise _lib.YoloB200Error("predict: call forward() first (it records img_size, model.py:33)")
+        fms = [_as_cuda_f32(f, self.device) for f in feature_maps]
+        if len(fms) != 3:
+            raise ValueError("predict expects 3 feature maps")
+        n = fms[0].shape[0]
+        h, w = self.img_size
+        C_ = self.class_num
+        for f, s in zip(fms, (32, 16, 8)):
+            if tuple(f.shape) != (n, h // s, w // s, 3 * (5 + C_)):
+                raise ValueError(f"feature map shape {tuple(f.shape)} does not match img_size {self.img_size}")
+        B = 3 * sum((h // s) * (w // s) for s in (32, 16, 8))
+        dev = self.device
+        boxes = torch.empty((n, B, 4), dtype=torch.float32, device=dev)
+        confs = torch.empty((n, B, 1), dtype=torch.float32, device=dev)
+        probs = torch.empty((n, B, C_), dtype=torch.float32, device=dev)
+        scores = torch.empty((n, B, C_), dtype=torch.float32, device=dev) if return_scores else None
+        check(lib.yb_predict(ptr(fms[0]), ptr(fms[1]), ptr(fms[2]), n, h, w, C_, _lib.fptr(self.anchors.reshape(-1)),
+                             ptr(boxes), ptr(confs), ptr(probs), ptr(scores), stream_handle()), "yb_predict")
+        if return_scores:
+            return boxes, confs, probs, scores
+        return boxes, confs, probs
