@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the YOLOv3 hot path on B200 (contract: see task ④).
+
+Workload (BASELINE.json configs[1]): batch=64 416x416 inference, 80 classes, one step =
+forward (75 convs) -> decode (+ score = conf*prob) -> per-image gpu_nms(max_boxes=200,
+score_thresh=0.3, nms_thresh=0.45) over one batch of synthetic images.  Weights are random
+(no checkpoint is shipped): SURVEY.md §8d cfg 2 — Glorot init, detection-head weights x8
+and conf bias -2 so that scores straddle the 0.3 threshold.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--size S]
+
+`value`  : images/s with the batch already resident in HBM, CUDA-event timed, max over ranks.
+`e2e`    : images/s through the public API from pinned HOST float32 images (H2D inside the
+           timed region) to host-side detections (D2H inside the timed region).
+`roofline`: the tensor-core conv kernel (74 launches/step): algorithmic conv FLOPs / event-timed
+           duration of those launches, against MEASURED_PEAKS.json's sustained bf16 peak.
+`cpu_baseline` / `--impl reference`: the CPU oracle port (TensorFlow 1.x cannot be installed in
+           this image) timed on the host cores on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+NMS_ARGS = dict(max_boxes=200, score_thresh=0.3, nms_thresh=0.45)   # test_single_image.py:57
+CLASS_NUM = 80
+FWD_GFLOP_416 = 65.864075264       # SURVEY.md Appendix A (2*MAC, 75 convs, per image @416^2)
+STEM_GFLOP_416 = 2 * 416 * 416 * 32 * 27 / 1e9
+
+
+def make_bench_params(seed=2):
+    """SURVEY.md §8d cfg 2 parameters (numpy, HWIO): Glorot-uniform, identity BN, head x8, conf bias -2."""
+    from yolov3_tensorflow_b200.model import yolov3
+    rng = np.random.default_rng(seed)
+    ps = []
+    for cin, cout, k, s, bn in yolov3.conv_table(CLASS_NUM):
+        lim = np.sqrt(6.0 / (k * k * (cin + cout)))
+        w = rng.uniform(-lim, lim, (k, k, cin, cout)).astype(np.float32)
+        if bn:
+            ps.append(dict(w=w, gamma=np.ones(cout, np.float32), beta=np.zeros(cout, np.float32),
+                           mean=np.zeros(cout, np.float32), var=np.ones(cout, np.float32)))
+        else:
+            b = np.zeros(cout, np.float32)
+            b.reshape(3, -1)[:, 4] = -2.0
+            ps.append(dict(w=(w * 8.0).astype(np.float32), b=b))
+    return ps
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self._stop = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                f = [v.strip() for v in out.split(",")]
+                self.samples.append((float(f[0]), float(f[1])))
+                for n, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(s[0] for s in self.samples)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": sorted(self.reasons),
+                "samples": len(sm)}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(tflops=p.get("bf16_tflops_sustained", p.get("bf16_tflops")), hbm=p.get("hbm_gbs"), src="measured (MEASURED_PEAKS.json, sustained bf16)")
+    return dict(tflops=1400.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+# --------------------------------------------------------------------------------------
+# CPU reference arm (oracle port; TensorFlow is not installable here)
+# --------------------------------------------------------------------------------------
+def cpu_step(O, x, params, anchors):
+    """One reference-path pass on the host: forward -> predict -> score -> per-image gpu_nms."""
+    fms = O.forward(x, params)
+    boxes, confs, probs = O.predict(fms, anchors, x.shape[1:3], CLASS_NUM)
+    scores = confs * probs
+    k = 0
+    for i in range(x.shape[0]):
+        r = O.gpu_nms(boxes[i:i + 1], scores[i:i + 1], CLASS_NUM, NMS_ARGS["max_boxes"], NMS_ARGS["score_thresh"],
+                      NMS_ARGS["nms_thresh"], nms_fn=O.nms_fast if hasattr(O, "nms_fast") else None)
+        k += len(r[1])
+    return k
+
+
+def run_cpu(size, steps, warmup, sample_images):
+    import torch
+    from oracle import yolov3_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    params = make_bench_params()
+    x = np.random.default_rng(2).random((sample_images, size, size, 3), dtype=np.float32)
+    for _ in range(warmup):
+        cpu_step(O, x, params, O.COCO_ANCHORS)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_step(O, x, params, O.COCO_ANCHORS)
+    dt = time.perf_counter() - t0
+    model = ""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    return dict(value=sample_images * steps / dt, unit="images/s", cores=cores, kind="port", cpu_model=model,
+                sample=f"{steps} passes over {sample_images} image(s) {size}x{size} (forward+decode+NMS, fp32, torch-CPU conv2d "
+                       f"restatement of the TF1 graph; TensorFlow not installable in this image)"), dt / steps
+
+
+# --------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--size", type=int, default=416)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = (f"batch={args.batch} {args.size}x{args.size} inference: forward + decode + per-image gpu_nms(200, 0.3, 0.45), "
+                f"COCO 80-class, random-init cfg-2 weights (BASELINE.json configs[1])")
+    config = {"workload": workload, "batch_per_gpu": args.batch, "image": [args.size, args.size], "classes": CLASS_NUM,
+              "parallelism": f"replicas x{world} (independent images, no data-path collective)",
+              "l2": "per-step inputs (133 MB) + activations (~6 GB) exceed the 126 MB L2; no explicit flush"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 3))
+        cb, spp = run_cpu(args.size, steps, min(args.warmup, 1), sample_images=2)
+        line = {"impl": "reference", "metric": "images/sec", "value": cb["value"], "unit": "images/s", "n_gpus": args.gpus,
+                "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": spp * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    import yolov3_tensorflow_b200 as pkg
+    from yolov3_tensorflow_b200 import _lib
+    from yolov3_tensorflow_b200.utils.nms_utils import batched_nms_raw
+
+    B, S = args.batch, args.size
+    anchors = pkg.parse_anchors(os.path.join(ROOT, "yolov3_tensorflow_b200", "data", "yolo_anchors.txt"))
+    model = pkg.yolov3(CLASS_NUM, anchors, dtype="fp16")
+    model.set_params(make_bench_params(), "HWIO")
+    x_host = torch.from_numpy(np.random.default_rng(2 + rank).random((B, S, S, 3), dtype=np.float32)).pin_memory()
+    x_dev = x_host.cuda()
+
+    def step_device():
+        fms = model.forward(x_dev)
+        boxes, confs, probs, scores = model.predict(fms, return_scores=True)
+        return batched_nms_raw(boxes, scores, CLASS_NUM, **NMS_ARGS)
+
+    def step_e2e():
+        xd = x_host.to("cuda", non_blocking=True)                              # H2D, every step
+        fms = model.forward(xd)
+        boxes, confs, probs, scores = model.predict(fms, return_scores=True)
+        ob, os_, ol, oi, cnt = batched_nms_raw(boxes, scores, CLASS_NUM, **NMS_ARGS)
+        counts = cnt.cpu()                                                     # D2H (sync): K per image
+        kmax = max(int(counts.max()), 1)
+        res = (ob[:, :kmax].cpu(), os_[:, :kmax].cpu(), ol[:, :kmax].cpu())    # D2H: detections
+        return counts, res, kmax
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- warm-up ----------------
+    for _ in range(max(args.warmup, 3)):
+        out = step_device()
+    torch.cuda.synchronize()
+    n_det = int(out[4].sum())
+
+    # ---------------- timed: device-resident ----------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---------------- timed: end to end (host -> host) ----------------
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    d2h = 0
+    for _ in range(args.steps):
+        counts, res, kmax = step_e2e()
+        d2h = counts.numel() * 4 + sum(r.numel() * r.element_size() for r in res)
+    t1.record()
+    barrier()
+    ms2 = torch.tensor([t0.elapsed_time(t1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_ms = float(ms2)
+
+    # ---------------- roofline: the tensor-core conv kernel, event-timed inside the step ----------------
+    plan = model._last_plan
+    D = 3 * (5 + CLASS_NUM)
+    fm = [torch.empty((B, S // s, S // s, D), dtype=torch.float32, device="cuda") for s in (32, 16, 8)]
+    st = _lib.stream_handle()
+    conv_ms, stem_ms = [], []
+    for i in range(args.steps + 2):
+        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a.record()
+        _lib.check(_lib.lib.yb_net_forward_layers(plan.handle, _lib.ptr(x_dev), _lib.ptr(fm[0]), _lib.ptr(fm[1]), _lib.ptr(fm[2]), 0, 0, st), "stem")
+        b.record()
+        _lib.check(_lib.lib.yb_net_forward_layers(plan.handle, _lib.ptr(x_dev), _lib.ptr(fm[0]), _lib.ptr(fm[1]), _lib.ptr(fm[2]), 1, 74, st), "convs")
+        c.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            stem_ms.append(a.elapsed_time(b)); conv_ms.append(b.elapsed_time(c))
+    conv_t = float(np.mean(conv_ms)) * 1e-3
+    scale = (S / 416.0) ** 2
+    conv_flop = (FWD_GFLOP_416 - STEM_GFLOP_416) * scale * 1e9 * B
+    pk = peaks()
+    achieved = conv_flop / conv_t / 1e12
+    roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel (74 launches/step, layers 1..74)", "achieved": achieved,
+                "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None,
+                "peak_source": pk["src"], "ms_per_step_conv": conv_t * 1e3, "ms_per_step_stem": float(np.mean(stem_ms)),
+                "algorithmic_flop_per_step": conv_flop}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    imgs = B * world * args.steps
+    value = imgs / (ms_total * 1e-3)
+    line = {"metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": config,
+            "e2e": {"value": imgs / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4,
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": args.steps * (1 + 74 + 1 + 3),
+            "launches_per_step": {"stem_conv": 1, "conv_igemm(tcgen05)": 74, "predict": 1, "nms": 3},
+            "detections_per_step": n_det, "clocks": clocks, "roofline": roofline,
+            "fraction_of_conv_flop_roofline": (value / world) * FWD_GFLOP_416 * scale * 1e9 / (pk["tflops"] * 1e12)}
+    if world == 1 and not args.no_cpu_baseline:
+        cb, _ = run_cpu(S, 2, 1, sample_images=2)
+        line["cpu_baseline"] = cb
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -159,6 +159,10 @@ int yb_net_set_conv_params(yb_net* net, int layer, const float* w, int layout, c
 /* forward (model.py:30-80), inference mode: images float32 [n,h,w,3] -> fm1 [n,h/32,w/32,D],
  * fm2 [n,h/16,w/16,D], fm3 [n,h/8,w/8,D] float32, D = 3*(5+class_num). */
 int yb_net_forward(yb_net* net, const float* images, float* fm1, float* fm2, float* fm3, void* stream);
+/* Same, restricted to layers [first, last] (creation order) — lets a benchmark bracket the CUDA-core stem
+ * (layer 0) and the tensor-core convs (1..74) with its own events. */
+int yb_net_forward_layers(yb_net* net, const float* images, float* fm1, float* fm2, float* fm3, int first,
+                          int last, void* stream);
 /* device pointer + geometry of one layer's output activation (tests / debugging). */
 int yb_net_layer_output(const yb_net* net, int layer, void** ptr, int* ld, int* dtype);
 /* number of kernels one yb_net_forward enqueues (for bench.py's gpu_launches). */

@@ -60,6 +60,7 @@ _SIGS = {
     "yb_net_bind": ([vp, vp, sz, vp, sz], i32),
     "yb_net_set_conv_params": ([vp, i32, vp, i32, vp, vp, vp, vp, vp, vp], i32),
     "yb_net_forward": ([vp, vp, vp, vp, vp, vp], i32),
+    "yb_net_forward_layers": ([vp, vp, vp, vp, vp, i32, i32, vp], i32),
     "yb_net_layer_output": ([vp, i32, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32)], i32),
     "yb_net_forward_launches": ([vp], i32),
 }

@@ -179,6 +179,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
+        if (n0 + ch * 32 >= p.cout) break;   // zero-padded weight rows (cout_pad > cout): nothing to store
         uint32_t r[32];
         tmem_ld_32x32(t_row + ch * 32, r);
         tmem_ld_wait();

@@ -284,11 +284,17 @@ extern "C" int yb_net_set_conv_params(yb_net* net, int layer, const float* w, in
 }
 
 extern "C" int yb_net_forward(yb_net* net, const float* images, float* fm1, float* fm2, float* fm3, void* stream) {
+  return yb_net_forward_layers(net, images, fm1, fm2, fm3, 0, 1 << 30, stream);
+}
+
+extern "C" int yb_net_forward_layers(yb_net* net, const float* images, float* fm1, float* fm2, float* fm3, int first,
+                                     int last, void* stream) {
   YB_REQUIRE(net && net->act && net->par, "forward: net not bound");
   YB_REQUIRE(images, "forward: null images");
+  YB_REQUIRE(first >= 0 && first <= last, "forward: bad layer range");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* user_fm[3] = {fm1, fm2, fm3};
-  {
+  if (first == 0) {
     Layer& L = net->layers[0];
     int rc = yb_stem_conv_fwd(images, reinterpret_cast<const float*>(net->par + L.w_master),
                               reinterpret_cast<const float*>(net->par + L.scale),
@@ -296,7 +302,7 @@ extern "C" int yb_net_forward(yb_net* net, const float* images, float* fm1, floa
                               net->dtype, 1, ten_ptr(net, L.out), stream);
     if (rc) return rc;
   }
-  for (size_t i = 1; i < net->layers.size(); ++i) {
+  for (size_t i = first > 1 ? first : 1; i < net->layers.size() && (int)i <= last; ++i) {
     Layer& L = net->layers[i];
     ConvParams* p = &L.params;
     if (!L.info.has_bn) {

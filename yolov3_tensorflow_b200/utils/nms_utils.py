@@ -57,7 +57,11 @@ def gpu_nms(boxes, scores, num_classes, max_boxes=50, score_thresh=0.5, nms_thre
     on the device, classes ascending, descending score inside a class, at most max_boxes PER CLASS.
     return_indices=True appends the original box index of every kept box (not available in the reference).
     Reading K back is the one host synchronisation of this call."""
-    b = boxes.reshape(1, -1, 4)
+    if not (isinstance(boxes, torch.Tensor) and isinstance(scores, torch.Tensor)):
+        raise TypeError("gpu_nms expects torch CUDA tensors")
+    if boxes.numel() % 4 or scores.numel() % num_classes or boxes.numel() // 4 != scores.numel() // num_classes:
+        raise ValueError(f"gpu_nms: shapes {tuple(boxes.shape)} / {tuple(scores.shape)} do not match num_classes={num_classes}")
+    b = boxes.reshape(1, -1, 4)                    # utils/nms_utils.py:26-27
     s = scores.reshape(1, -1, num_classes)
     ob, os_, ol, oi, cnt = batched_nms_raw(b, s, num_classes, max_boxes, score_thresh, nms_thresh)
     k = int(cnt.item())
