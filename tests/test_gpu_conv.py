@@ -12,6 +12,14 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["1cta", "2cta"], autouse=True)
+def conv_mode(request, monkeypatch):
+    """Every conv test runs against both tcgen05 kernels: cta_group::1 (128-row tiles) and
+    cta_group::2 (a CTA pair per 256-row tile).  YB_CONV_MODE overrides the size heuristic."""
+    monkeypatch.setenv("YB_CONV_MODE", request.param)
+    return request.param
+
+
 def _lib():
     from yolov3_tensorflow_b200 import _lib
     return _lib

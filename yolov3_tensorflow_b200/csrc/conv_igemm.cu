@@ -20,6 +20,8 @@
 // tf.add (utils/layer_utils.py:30), tf.pad (:15-16), resize_nearest_neighbor (:86),
 // tf.concat (model.py:62,72).
 #include <cudaTypedefs.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <type_traits>
 
@@ -32,6 +34,7 @@ static constexpr int BLOCK_M = 128;
 static constexpr int UMMA_K = 16;
 static constexpr int NUM_THREADS = 192;
 static constexpr int SMEM_BUDGET = 200 * 1024;  // operand ring; barriers + alignment slack on top
+static constexpr int STAGE_FLOATS = 32 * 33;    // per-epilogue-warp fp32 transpose tile (detection-head stores)
 
 template <int BN, int BK>
 struct Cfg {
@@ -40,10 +43,130 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BN;  // power of two >= 32 for BN in {64,128,256}
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4 * STAGE_FLOATS * 4;
   static constexpr uint32_t SWIZZLE = (BK == 64) ? 2u : 4u;   // UMMA layout_type: 128B / 64B
   static constexpr uint32_t SBO = 8 * BK * 2;                  // bytes between 8-row groups
 };
+
+// One epilogue pass of a warp over its 32 accumulator rows x BN columns:
+// TMEM -> registers -> scale/shift (+leaky) (+residual) -> 16-bit / fp32 global stores
+// (channel-slice and 2x-upsample aware), optional BN batch statistics.
+template <typename T, int BN>
+__device__ __forceinline__ void epilogue_tile(const ConvParams& p, const int row, const int n0, const uint32_t t_row,
+                                              const int lane, float* stage) {
+  const bool row_ok = row < p.M;
+  // output row(s)
+  long orow[4];
+  int nrep = 1;
+  if (p.upsample) {
+    const int q = row % p.Q;
+    const int pp = (row / p.Q) % p.P;
+    const int img = row / (p.Q * p.P);
+    const long W2 = 2L * p.Q;
+    const long base = ((long)img * 2 * p.P + 2 * pp) * W2 + 2 * q;
+    orow[0] = base; orow[1] = base + 1; orow[2] = base + W2; orow[3] = base + W2 + 1;
+    nrep = 4;
+  } else {
+    orow[0] = row;
+  }
+#pragma unroll 1
+  for (int ch = 0; ch < BN / 32; ++ch) {
+    if (n0 + ch * 32 >= p.cout) break;   // zero-padded weight rows (cout_pad > cout): nothing to store
+    uint32_t r[32];
+    tmem_ld_32x32(t_row + ch * 32, r);
+    tmem_ld_wait();
+    const int col0 = n0 + ch * 32;
+    if (p.stat_sum != nullptr) {
+      // BN batch statistics of the raw conv output: reduce the warp's 32 rows per column
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float v = row_ok ? __uint_as_float(r[j]) : 0.f;
+        float s = v, s2 = v * v;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          s += __shfl_xor_sync(0xffffffffu, s, o);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (lane == j && col0 + j < p.cout) {
+          atomicAdd(p.stat_sum + col0 + j, s);
+          atomicAdd(p.stat_sqsum + col0 + j, s2);
+        }
+      }
+    }
+    if (row_ok) {
+      float v[32];
+      const float4* sc4 = reinterpret_cast<const float4*>(p.scale + col0);
+      const float4* sh4 = reinterpret_cast<const float4*>(p.shift + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 sc = __ldg(sc4 + j);
+        const float4 sh = __ldg(sh4 + j);
+        v[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), sc.x, sh.x);
+        v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), sc.y, sh.y);
+        v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), sc.z, sh.z);
+        v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), sc.w, sh.w);
+      }
+      if (p.leaky) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = leaky01(v[j]);
+      }
+      if (p.res != nullptr) {
+        const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const T*>(p.res) + (long)row * p.res_ld + col0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 u = __ldg(rp + j);
+          float2 f;
+          f = Pack2<T>::unpack(u.x); v[8 * j + 0] += f.x; v[8 * j + 1] += f.y;
+          f = Pack2<T>::unpack(u.y); v[8 * j + 2] += f.x; v[8 * j + 3] += f.y;
+          f = Pack2<T>::unpack(u.z); v[8 * j + 4] += f.x; v[8 * j + 5] += f.y;
+          f = Pack2<T>::unpack(u.w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
+        }
+      }
+      if (p.out_fp32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = v[j];
+      } else {
+        uint4 pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          pk[j].x = Pack2<T>::pack(v[8 * j + 0], v[8 * j + 1]);
+          pk[j].y = Pack2<T>::pack(v[8 * j + 2], v[8 * j + 3]);
+          pk[j].z = Pack2<T>::pack(v[8 * j + 4], v[8 * j + 5]);
+          pk[j].w = Pack2<T>::pack(v[8 * j + 6], v[8 * j + 7]);
+        }
+        for (int rep = 0; rep < nrep; ++rep) {
+          uint4* op = reinterpret_cast<uint4*>(static_cast<T*>(p.out) + orow[rep] * p.out_ld + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) op[j] = pk[j];
+        }
+      }
+    }
+    if (p.out_fp32) {
+      // detection heads (cout = 255, fp32): transpose through shared memory so that each store
+      // instruction writes one 128-byte row segment instead of 32 scattered words
+      __syncwarp();
+      const int row_base = row - lane;
+      for (int rr = 0; rr < 32; ++rr) {
+        const int r2 = row_base + rr;
+        if (r2 >= p.M) break;
+        if (col0 + lane < p.cout) {
+          const float val = stage[rr * 33 + lane];
+          if (!p.upsample) {
+            static_cast<float*>(p.out)[(long)r2 * p.out_ld + col0 + lane] = val;
+          } else {
+            const int q = r2 % p.Q, pp = (r2 / p.Q) % p.P, img = r2 / (p.Q * p.P);
+            const long W2 = 2L * p.Q;
+            const long base = ((long)img * 2 * p.P + 2 * pp) * W2 + 2 * q;
+            float* o = static_cast<float*>(p.out) + col0 + lane;
+            o[base * p.out_ld] = val; o[(base + 1) * p.out_ld] = val;
+            o[(base + W2) * p.out_ld] = val; o[(base + W2 + 1) * p.out_ld] = val;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
 
 template <typename T, int BN, int BK>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -60,6 +183,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tfull_bar = bars + 2 * C::STAGES;      // [2] MMA -> epilogue
   uint64_t* tempty_bar = bars + 2 * C::STAGES + 2; // [2] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+  float* stage_base = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -158,102 +282,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m0 = (tile / p.num_n_tiles) * BLOCK_M;
       const int n0 = (tile % p.num_n_tiles) * BN;
-      const int row = m0 + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
-      // output row(s)
-      long orow[4];
-      int nrep = 1;
-      if (p.upsample) {
-        const int q = row % p.Q;
-        const int pp = (row / p.Q) % p.P;
-        const int img = row / (p.Q * p.P);
-        const long W2 = 2L * p.Q;
-        const long base = ((long)img * 2 * p.P + 2 * pp) * W2 + 2 * q;
-        orow[0] = base; orow[1] = base + 1; orow[2] = base + W2; orow[3] = base + W2 + 1;
-        nrep = 4;
-      } else {
-        orow[0] = row;
-      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        if (n0 + ch * 32 >= p.cout) break;   // zero-padded weight rows (cout_pad > cout): nothing to store
-        uint32_t r[32];
-        tmem_ld_32x32(t_row + ch * 32, r);
-        tmem_ld_wait();
-        const int col0 = n0 + ch * 32;
-        if (p.stat_sum != nullptr) {
-          // BN batch statistics of the raw conv output: reduce the warp's 32 rows per column
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float v = row_ok ? __uint_as_float(r[j]) : 0.f;
-            float s = v, s2 = v * v;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              s += __shfl_xor_sync(0xffffffffu, s, o);
-              s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-            }
-            if (lane == j && col0 + j < p.cout) {
-              atomicAdd(p.stat_sum + col0 + j, s);
-              atomicAdd(p.stat_sqsum + col0 + j, s2);
-            }
-          }
-        }
-        if (row_ok) {
-          float v[32];
-          const float4* sc4 = reinterpret_cast<const float4*>(p.scale + col0);
-          const float4* sh4 = reinterpret_cast<const float4*>(p.shift + col0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 sc = __ldg(sc4 + j);
-            const float4 sh = __ldg(sh4 + j);
-            v[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), sc.x, sh.x);
-            v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), sc.y, sh.y);
-            v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), sc.z, sh.z);
-            v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), sc.w, sh.w);
-          }
-          if (p.leaky) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = leaky01(v[j]);
-          }
-          if (p.res != nullptr) {
-            const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const T*>(p.res) + (long)row * p.res_ld + col0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 u = __ldg(rp + j);
-              float2 f;
-              f = Pack2<T>::unpack(u.x); v[8 * j + 0] += f.x; v[8 * j + 1] += f.y;
-              f = Pack2<T>::unpack(u.y); v[8 * j + 2] += f.x; v[8 * j + 3] += f.y;
-              f = Pack2<T>::unpack(u.z); v[8 * j + 4] += f.x; v[8 * j + 5] += f.y;
-              f = Pack2<T>::unpack(u.w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
-            }
-          }
-          if (p.out_fp32) {
-            for (int rep = 0; rep < nrep; ++rep) {
-              float* op = static_cast<float*>(p.out) + orow[rep] * p.out_ld + col0;
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.cout) op[j] = v[j];
-            }
-          } else {
-            uint4 pk[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              pk[j].x = Pack2<T>::pack(v[8 * j + 0], v[8 * j + 1]);
-              pk[j].y = Pack2<T>::pack(v[8 * j + 2], v[8 * j + 3]);
-              pk[j].z = Pack2<T>::pack(v[8 * j + 4], v[8 * j + 5]);
-              pk[j].w = Pack2<T>::pack(v[8 * j + 6], v[8 * j + 7]);
-            }
-            for (int rep = 0; rep < nrep; ++rep) {
-              uint4* op = reinterpret_cast<uint4*>(static_cast<T*>(p.out) + orow[rep] * p.out_ld + col0);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) op[j] = pk[j];
-            }
-          }
-        }
-      }
+      epilogue_tile<T, BN>(p, m0 + quarter * 32 + lane, n0, tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN, lane,
+                           stage_base + (warp - 2) * STAGE_FLOATS);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -265,6 +297,164 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 1) {
     tcgen05_fence_after();
     tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ----------------------------------------------------------------------------------
+// 2-CTA variant: a cluster of two CTAs (one SM pair) computes a 256 x BN tile with
+// tcgen05.mma.cta_group::2 (UMMA M = 256).  Each CTA loads only ITS 128 rows of A and
+// ITS half of the B tile, so the L2 -> shared fill per FLOP is half that of the 1-CTA
+// kernel (profiles/r01_a: the 1-CTA kernel is fill-bound at ~8 TB/s).  The leader CTA
+// (cluster rank 0) issues the MMAs; tcgen05.commit multicasts barrier arrivals to both
+// CTAs; each CTA drains its own 128 TMEM lanes in its own epilogue warps.
+// ----------------------------------------------------------------------------------
+template <int BN, int BK>
+struct Cfg2 {
+  static constexpr int A_BYTES = BLOCK_M * BK * 2;         // this CTA's 128 rows
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;        // this CTA's half of the BN weight rows
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 4 * STAGE_FLOATS * 4;
+  static constexpr uint32_t SWIZZLE = (BK == 64) ? 2u : 4u;
+  static constexpr uint32_t SBO = 8 * BK * 2;
+};
+
+template <typename T, int BN, int BK>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const ConvParams p) {
+  using C = Cfg2<BN, BK>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + C::STAGES * C::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;                        // [STAGES] used in the leader only
+  uint64_t* empty_bar = bars + C::STAGES;           // [STAGES] one per CTA (multicast commit)
+  uint64_t* tfull_bar = bars + 2 * C::STAGES;       // [2] one per CTA (multicast commit)
+  uint64_t* tempty_bar = bars + 2 * C::STAGES + 2;  // [2] used in the leader only (8 arrivals: 4 warps x 2 CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+  float* stage_base = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();          // 0 = leader
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;   // m tiles are 256 rows here
+  const int kb_per_tap = p.cin / BK;
+  const int num_kb = p.ksize * p.ksize * kb_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm<C::TMEM_COLS>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();                               // peer barriers are initialised before any remote arrive / TMA
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m0 = (tile / p.num_n_tiles) * (2 * BLOCK_M) + (int)rank * BLOCK_M;   // this CTA's 128 rows
+      const int n0 = (tile % p.num_n_tiles) * BN + (int)rank * (BN / 2);             // this CTA's half of B
+      const int q = m0 % p.Q;
+      const int pp = (m0 / p.Q) % p.P;
+      const int img = m0 / (p.Q * p.P);
+      const int w_base = q * p.stride - p.pad;
+      const int h_base = pp * p.stride - p.pad;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int tap = kb / kb_per_tap;
+        const int c0 = (kb - tap * kb_per_tap) * BK;
+        if (lane == 0) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);   // both CTAs' bytes
+          if (p.im2col) {
+            tma_load_im2col_4d_2sm(sA + stage * C::A_BYTES, &tmA, &full_bar[stage], c0, w_base, h_base, img,
+                                   (uint16_t)(tap % p.ksize), (uint16_t)(tap / p.ksize));
+          } else {
+            tma_load_2d_2sm(sA + stage * C::A_BYTES, &tmA, &full_bar[stage], c0, m0);
+          }
+          tma_load_2d_2sm(sB + stage * C::B_BYTES, &tmB, &full_bar[stage], tap * p.cin + c0, n0);
+        }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(2 * BLOCK_M, BN, std::is_same<T, __nv_bfloat16>::value);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        if (lane == 0) mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        __syncwarp();
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          if (lane == 0) {
+            mbar_wait(&full_bar[stage], phase);
+            tcgen05_fence_after();
+            const uint32_t a_addr = smem_u32(sA + stage * C::A_BYTES);
+            const uint32_t b_addr = smem_u32(sB + stage * C::B_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t adesc = make_kmajor_desc(a_addr + k * UMMA_K * 2, C::SBO, C::SWIZZLE);
+              const uint64_t bdesc = make_kmajor_desc(b_addr + k * UMMA_K * 2, C::SBO, C::SWIZZLE);
+              umma_f16_2sm(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+            }
+            umma_commit_2sm(&empty_bar[stage]);                       // frees the slot in BOTH CTAs
+            if (kb == num_kb - 1) umma_commit_2sm(&tfull_bar[acc]);   // accumulator ready in BOTH CTAs
+          }
+          __syncwarp();
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5, both CTAs) =====================
+    const int quarter = warp & 3;
+    int it = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m0 = (tile / p.num_n_tiles) * (2 * BLOCK_M) + (int)rank * BLOCK_M;
+      const int n0 = (tile % p.num_n_tiles) * BN;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      epilogue_tile<T, BN>(p, m0 + quarter * 32 + lane, n0, tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN, lane,
+                           stage_base + (warp - 2) * STAGE_FLOATS);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);    // the leader's MMA warp waits for both CTAs
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();                               // nobody exits while the peer may still signal / read its smem
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc_2sm<C::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -360,22 +550,66 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv
   return YB_OK;
 }
 
-int conv_block_n(int cout_pad) { return (cout_pad % 128 == 0) ? 128 : 64; }
-int conv_block_k(int cin) { return (cin % 64 == 0) ? 64 : 32; }
+template <typename T, int BN, int BK>
+static int launch_cfg2(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t st) {
+  using C = Cfg2<BN, BK>;
+  static bool attr_done = false;
+  auto kern = conv_igemm_2cta_kernel<T, BN, BK>;
+  if (!attr_done) {
+    YB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int max_clusters = num_sms() / 2;
+  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  YB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+  return YB_OK;
+}
 
-// Launch with prebuilt tensor maps (used by the network plan).
+int conv_block_k(int cin) { return (cin % 64 == 0) ? 64 : 32; }
+// 1-CTA tile width
+int conv_block_n(int cout_pad) { return (cout_pad % 128 == 0) ? 128 : 64; }
+// 2-CTA (pair) tile width
+int conv_block_n2(int cout_pad) { return (cout_pad % 256 == 0) ? 256 : ((cout_pad % 128 == 0) ? 128 : 64); }
+
+// Launch with prebuilt tensor maps (used by the network plan).  p.two_cta selects the kernel.
 int conv_launch(int dtype, int cout_pad, const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p,
                 cudaStream_t st) {
-  const int bn = conv_block_n(cout_pad);
   const int bk = conv_block_k(p.cin);
+  if (p.two_cta) {
+    const int bn = conv_block_n2(cout_pad);
+#define YB_DISPATCH2(T)                                                         \
+  if (bn == 256 && bk == 64) return launch_cfg2<T, 256, 64>(tmA, tmB, p, st); \
+  if (bn == 256 && bk == 32) return launch_cfg2<T, 256, 32>(tmA, tmB, p, st); \
+  if (bn == 128 && bk == 64) return launch_cfg2<T, 128, 64>(tmA, tmB, p, st); \
+  if (bn == 128 && bk == 32) return launch_cfg2<T, 128, 32>(tmA, tmB, p, st); \
+  if (bn == 64 && bk == 64) return launch_cfg2<T, 64, 64>(tmA, tmB, p, st);   \
+  if (bn == 64 && bk == 32) return launch_cfg2<T, 64, 32>(tmA, tmB, p, st);
+    if (dtype == YB_F16) { YB_DISPATCH2(__half) }
+    else if (dtype == YB_BF16) { YB_DISPATCH2(__nv_bfloat16) }
+#undef YB_DISPATCH2
+  } else {
+    const int bn = conv_block_n(cout_pad);
 #define YB_DISPATCH(T)                                                         \
   if (bn == 128 && bk == 64) return launch_cfg<T, 128, 64>(tmA, tmB, p, st); \
   if (bn == 128 && bk == 32) return launch_cfg<T, 128, 32>(tmA, tmB, p, st); \
   if (bn == 64 && bk == 64) return launch_cfg<T, 64, 64>(tmA, tmB, p, st);   \
   if (bn == 64 && bk == 32) return launch_cfg<T, 64, 32>(tmA, tmB, p, st);
-  if (dtype == YB_F16) { YB_DISPATCH(__half) }
-  else if (dtype == YB_BF16) { YB_DISPATCH(__nv_bfloat16) }
+    if (dtype == YB_F16) { YB_DISPATCH(__half) }
+    else if (dtype == YB_BF16) { YB_DISPATCH(__nv_bfloat16) }
 #undef YB_DISPATCH
+  }
   set_error("conv_launch: unsupported dtype %d", dtype);
   return YB_ERR_UNSUPPORTED;
 }
@@ -405,12 +639,19 @@ int conv_prepare(const yb_conv_desc* d, const void* x, const void* w_packed, con
   if (res) YB_REQUIRE(d->res_ld >= d->cout && d->res_ld % 8 == 0 && !d->out_fp32, "conv: res_ld %d invalid", d->res_ld);
   YB_REQUIRE((stat_sum == nullptr) == (stat_sqsum == nullptr), "conv: stat_sum/stat_sqsum must both be given");
   const int P = d->h / d->stride, Q = d->w / d->stride;
-  const int bn = conv_block_n(cout_pad), bk = conv_block_k(d->cin);
+  const int bk = conv_block_k(d->cin);
   const int pad = d->ksize / 2;
   p->M = d->n * P * Q; p->P = P; p->Q = Q;
+  // a CTA pair per 256-row tile once there are enough tiles to occupy the 74 SM pairs
+  const char* force = getenv("YB_CONV_MODE");   // "1cta" / "2cta": testing override
+  bool two = (long)ceil_div(p->M, 2 * BLOCK_M) * (cout_pad / conv_block_n2(cout_pad)) >= 32;
+  if (force && force[0] == '1') two = false;
+  if (force && force[0] == '2') two = true;
+  p->two_cta = two ? 1 : 0;
+  const int bn = two ? conv_block_n2(cout_pad) : conv_block_n(cout_pad);
   p->cout = d->cout; p->cin = d->cin; p->ksize = d->ksize; p->stride = d->stride; p->pad = pad;
   p->im2col = d->ksize == 3;
-  p->num_m_tiles = ceil_div(p->M, BLOCK_M);
+  p->num_m_tiles = ceil_div(p->M, two ? 2 * BLOCK_M : BLOCK_M);
   p->num_n_tiles = cout_pad / bn;
   p->scale = scale; p->shift = shift;
   p->out = out; p->out_ld = d->out_ld; p->res = res; p->res_ld = d->res_ld;
@@ -424,7 +665,7 @@ int conv_prepare(const yb_conv_desc* d, const void* x, const void* w_packed, con
   }
   if (rc) return rc;
   rc = make_tmap_2d(tmB, w_packed, d->dtype, cout_pad, (long)d->ksize * d->ksize * d->cin,
-                    (long)d->ksize * d->ksize * d->cin, bn, bk, 1);
+                    (long)d->ksize * d->ksize * d->cin, two ? bn / 2 : bn, bk, 1);
   if (rc) return rc;
   *cout_pad_out = cout_pad;
   return YB_OK;
