@@ -644,7 +644,9 @@ int conv_prepare(const yb_conv_desc* d, const void* x, const void* w_packed, con
   p->M = d->n * P * Q; p->P = P; p->Q = Q;
   // a CTA pair per 256-row tile once there are enough tiles to occupy the 74 SM pairs
   const char* force = getenv("YB_CONV_MODE");   // "1cta" / "2cta": testing override
-  bool two = (long)ceil_div(p->M, 2 * BLOCK_M) * (cout_pad / conv_block_n2(cout_pad)) >= 32;
+  // (measured, profiles/r01_b: pairs win 1.4-1.6x on 256-wide tiles — half the L2->smem fill per FLOP — but lose on
+  //  64/128-wide tiles, whose short per-tile pipelines are dominated by the cross-CTA barrier latency)
+  bool two = cout_pad % 256 == 0 && (long)ceil_div(p->M, 2 * BLOCK_M) * (cout_pad / 256) >= 32;
   if (force && force[0] == '1') two = false;
   if (force && force[0] == '2') two = true;
   p->two_cta = two ? 1 : 0;
