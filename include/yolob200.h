@@ -96,6 +96,44 @@ int yb_bn_fold(const float* gamma, const float* beta, const float* mean, const f
                float* scale, float* shift, void* stream);
 
 /* ---------------------------------------------------------------------------------
+ * Training-mode pieces around the conv (replace slim.batch_norm(is_training=True) and TF autodiff of
+ * slim.conv2d / batch_norm / leaky_relu: model.py:35-49, train.py:108-112)
+ * --------------------------------------------------------------------------------- */
+/* dw[cout, k*k*cin] (fp32, OHWI, ACCUMULATED) += sum over output pixels of dz[p,co] * im2col(x)[p,(r,s,ci)].
+ * d describes the FORWARD conv (n,h,w,cin,cout,ksize,stride,in_ld,dtype); x is its input activation,
+ * dz [n*ho*wo, dz_ld] the gradient w.r.t. its raw output; dz_dilated=1: dz is stored zero-inserted in an
+ * [n, 2ho, 2wo, dz_ld] buffer (what the stride-2 dgrad consumes).  tcgen05, MN-major operands, split over pixels. */
+int yb_conv2d_wgrad(const yb_conv_desc* d, const void* x, const void* dz, int dz_ld, int dz_dilated, float* dw,
+                    void* stream);
+/* wgrad of the 3-channel stem: x float32 [n,h,w,3], dz [n*h*w, 32] 16-bit -> dw [32,3,3,3] accumulated. */
+int yb_stem_conv_wgrad(const float* x, const void* dz, int dtype, int n, int h, int w, float* dw, void* stream);
+/* dgrad weights: dst[ci][r][s][co] = w_ohwi[co][k-1-r][k-1-s][ci] (k_cout >= cout, cin_pad >= cin zero-padded):
+ * the data gradient of a stride-1 conv is yb_conv2d_fwd(dz, dst) (stride-2: on the zero-inserted dz). */
+int yb_pack_dgrad_weights(const float* w_ohwi, int cout, int cin, int ksize, int k_cout, int cin_pad, int dtype,
+                          void* dst, void* stream);
+/* BN batch statistics -> scale/shift for bn_act_apply, saved mean/invstd for the backward, moving-stat update
+ * (biased variance normalises, unbiased variance feeds the moving average; moving_* nullable). */
+int yb_bn_finalize(const float* sum, const float* sqsum, long count, int c, const float* gamma, const float* beta,
+                   float eps, float decay, float* moving_mean, float* moving_var, float* scale, float* shift,
+                   float* save_mean, float* save_invstd, void* stream);
+/* out = leaky(z*scale+shift) (+res); z/res/out 16-bit [n*h*w, ld]; upsample2x stores every row to its 4 places. */
+int yb_bn_act_apply(const void* z, long z_ld, const float* scale, const float* shift, const void* res, long res_ld,
+                    void* out, long out_ld, int n, int h, int w, int c, int dtype, int leaky, int upsample2x,
+                    void* stream);
+/* dgamma/dbeta (fp32 [c], overwritten) from dA (gradient w.r.t. the layer output; upsample2x: summed over the
+ * 4 copies) and the saved z. */
+int yb_bn_bwd_reduce(const void* dA, long dA_ld, const void* z, long z_ld, const float* scale, const float* shift,
+                     const float* save_mean, const float* save_invstd, int n, int h, int w, int c, int dtype,
+                     int leaky, int upsample2x, float* dgamma, float* dbeta, void* stream);
+/* dz = gamma*invstd*(dact - dbeta/M - zhat*dgamma/M); dilate2x stores row (p,q) at (2p,2q) of [n,2h,2w,dz_ld]. */
+int yb_bn_bwd_apply(const void* dA, long dA_ld, const void* z, long z_ld, const float* gamma, const float* scale,
+                    const float* shift, const float* save_mean, const float* save_invstd, const float* dgamma,
+                    const float* dbeta, int n, int h, int w, int c, int dtype, int leaky, int upsample2x,
+                    int dilate2x, void* dz, long dz_ld, void* stream);
+/* out[c] (fp32, overwritten) = column sums of x [rows, ld] (bias gradient of the detection convs). */
+int yb_col_sum(const void* x, long ld, long rows, int c, int dtype, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------
  * Decode  (replaces the ~40 elementwise TF ops of model.py:82-190 and the caller's
  * pred_scores = pred_confs * pred_probs, test_single_image.py:55)
  * --------------------------------------------------------------------------------- */
@@ -125,6 +163,27 @@ int yb_nms_workspace_bytes(int n_images, int num_boxes, int num_classes, int max
 int yb_nms(const float* boxes, const float* scores, int n_images, int num_boxes, int num_classes, int max_boxes,
            float score_thresh, float iou_thresh, void* workspace, size_t workspace_bytes, float* out_boxes,
            float* out_scores, int32_t* out_labels, int32_t* out_indices, int32_t* out_counts, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Loss  (replaces model.py:192-304 loss_layer, :307-345 box_iou, :348-365 compute_loss and
+ * the part of TF autodiff (train.py:112) that differentiates them)
+ * --------------------------------------------------------------------------------- */
+int yb_loss_workspace_bytes(int n, int gh, int gw, size_t* bytes);
+/* One scale.  feature_map [n,gh,gw,3*(5+C)] f32 logits, y_true [n,gh,gw,3,5+C+1] f32 (utils/data_utils.py:51-115
+ * format: cx,cy,w,h px | obj | one-hot | mix-up weight), anchors3x2 host float[6].
+ * loss4 (device double[4]: xy, wh, conf, class) is ACCUMULATED into (zero it first; every term already
+ * carries the 1/N of model.py:276-302, N = 1/inv_batch).
+ * dfm (nullable) receives d(total)/d(feature_map): dfm_dtype YB_F32 -> same layout as feature_map;
+ * YB_F16/YB_BF16 -> [n*gh*gw, dfm_ld] rows (dfm_ld >= 3*(5+C), padding columns zeroed) for the backward GEMMs. */
+int yb_loss_layer(const float* feature_map, const float* y_true, int n, int gh, int gw, int img_h, int img_w,
+                  int class_num, const float* anchors3x2, int use_label_smooth, int use_focal_loss,
+                  float inv_batch, void* workspace, size_t workspace_bytes, double* loss4, void* dfm,
+                  int dfm_dtype, int dfm_ld, void* stream);
+/* out5 (device float[5]) = [total, xy, wh, conf, class] (model.py:364-365). */
+int yb_loss_finalize(const double* loss4, float* out5, void* stream);
+/* box_iou (model.py:307-345): pred_boxes [P,4], true_boxes [V,4] (cx,cy,w,h) -> iou [P,V]. */
+int yb_box_iou(const float* pred_boxes, const float* true_boxes, long num_pred, int num_true, float* iou,
+               void* stream);
 
 /* ---------------------------------------------------------------------------------
  * Network plan: the 75-conv Darknet-53 + YOLOv3 head of model.py:30-80 for a fixed

@@ -48,10 +48,22 @@ _SIGS = {
     "yb_stem_conv_fwd": ([vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp], i32),
     "yb_pack_conv_weights": ([vp, i32, i32, i32, i32, i32, i32, vp, vp], i32),
     "yb_bn_fold": ([vp, vp, vp, vp, i32, f32, vp, vp, vp], i32),
+    "yb_conv2d_wgrad": ([C.POINTER(ConvDesc), vp, vp, i32, i32, vp, vp], i32),
+    "yb_stem_conv_wgrad": ([vp, vp, i32, i32, i32, i32, vp, vp], i32),
+    "yb_pack_dgrad_weights": ([vp, i32, i32, i32, i32, i32, i32, vp, vp], i32),
+    "yb_bn_finalize": ([vp, vp, C.c_long, i32, vp, vp, f32, f32, vp, vp, vp, vp, vp, vp, vp], i32),
+    "yb_bn_act_apply": ([vp, C.c_long, vp, vp, vp, C.c_long, vp, C.c_long, i32, i32, i32, i32, i32, i32, i32, vp], i32),
+    "yb_bn_bwd_reduce": ([vp, C.c_long, vp, C.c_long, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp], i32),
+    "yb_bn_bwd_apply": ([vp, C.c_long, vp, C.c_long, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, C.c_long, vp], i32),
+    "yb_col_sum": ([vp, C.c_long, C.c_long, i32, i32, vp, vp], i32),
     "yb_reorg_layer": ([vp, i32, i32, i32, i32, i32, i32, C.POINTER(f32), vp, vp, vp, vp, vp], i32),
     "yb_predict": ([vp, vp, vp, i32, i32, i32, i32, C.POINTER(f32), vp, vp, vp, vp, vp], i32),
     "yb_nms_workspace_bytes": ([i32, i32, i32, i32, C.POINTER(sz)], i32),
     "yb_nms": ([vp, vp, i32, i32, i32, i32, f32, f32, vp, sz, vp, vp, vp, vp, vp, vp], i32),
+    "yb_loss_workspace_bytes": ([i32, i32, i32, C.POINTER(sz)], i32),
+    "yb_loss_layer": ([vp, vp, i32, i32, i32, i32, i32, i32, C.POINTER(f32), i32, i32, f32, vp, sz, vp, vp, i32, i32, vp], i32),
+    "yb_loss_finalize": ([vp, vp, vp], i32),
+    "yb_box_iou": ([vp, vp, C.c_long, i32, vp, vp], i32),
     "yb_net_create": ([C.POINTER(vp), i32, i32, i32, i32, i32, i32], i32),
     "yb_net_destroy": ([vp], i32),
     "yb_net_num_layers": ([vp], i32),

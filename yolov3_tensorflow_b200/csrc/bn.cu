@@ -1,0 +1,335 @@
+// Batch-norm (training mode) + leaky-ReLU forward/backward around the tensor-core convs.
+// TF semantics (slim.batch_norm fused, model.py:35-41): batch mean and
+// *biased* variance normalise; moving stats are updated with the *unbiased* variance
+// (train.py:108-109 UPDATE_OPS).  The conv epilogue already produced the per-channel
+// sum / sum of squares of the raw conv output z (yb_conv2d_fwd stat_sum/stat_sqsum).
+//
+//   bn_finalize      : sums -> mean/var -> scale/shift (+ saved mean/invstd, moving update)
+//   bn_act_apply     : a = leaky(z*scale+shift) (+ residual), optional 2x-upsample store
+//   bn_bwd_reduce    : dbeta = sum(dact), dgamma = sum(dact * zhat), dact = dA * leaky'(y)
+//   bn_bwd_apply     : dz = gamma*invstd*(dact - dbeta/M - zhat*dgamma/M), optional
+//                      zero-insertion (dilated) store for the dgrad of stride-2 convs
+//   col_sum          : bias gradient of the detection convs
+// All are HBM-bound streaming kernels over [rows, C] NHWC 16-bit tensors (C % 8 == 0):
+// a thread owns 8 consecutive channels (one 16-byte load), a block a slab of rows.
+#include "common.cuh"
+
+namespace yb {
+
+__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sqsum, float count, int c,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float decay, float* moving_mean, float* moving_var, float* scale, float* shift,
+                                   float* save_mean, float* save_invstd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  const float mean = sum[i] / count;
+  float var = sqsum[i] / count - mean * mean;   // biased
+  var = fmaxf(var, 0.f);
+  const float invstd = rsqrtf(var + eps);
+  const float sc = gamma[i] * invstd;
+  scale[i] = sc;
+  shift[i] = beta[i] - mean * sc;
+  save_mean[i] = mean;
+  save_invstd[i] = invstd;
+  if (moving_mean) {
+    const float unb = count > 1.f ? var * count / (count - 1.f) : var;
+    moving_mean[i] = moving_mean[i] * decay + (1.f - decay) * mean;
+    moving_var[i] = moving_var[i] * decay + (1.f - decay) * unb;
+  }
+}
+
+struct RowGeom {
+  long rows;        // n*h*w
+  int h, w;         // spatial (for the upsample / dilate address maps)
+  int c;
+};
+
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 f;
+  f = Pack2<T>::unpack(u.x); v[0] = f.x; v[1] = f.y;
+  f = Pack2<T>::unpack(u.y); v[2] = f.x; v[3] = f.y;
+  f = Pack2<T>::unpack(u.z); v[4] = f.x; v[5] = f.y;
+  f = Pack2<T>::unpack(u.w); v[6] = f.x; v[7] = f.y;
+}
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const float (&v)[8]) {
+  uint4 u;
+  u.x = Pack2<T>::pack(v[0], v[1]); u.y = Pack2<T>::pack(v[2], v[3]);
+  u.z = Pack2<T>::pack(v[4], v[5]); u.w = Pack2<T>::pack(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+// row index in the 2x-upsampled [n, 2h, 2w] grid of the top-left copy of row r of [n, h, w]
+__device__ __forceinline__ long up_row(long r, int h, int w) {
+  const long q = r % w, pp = (r / w) % h, img = r / ((long)w * h);
+  return ((img * 2 * h + 2 * pp) * (2L * w)) + 2 * q;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_act_apply_kernel(const T* __restrict__ z, long z_ld, const float* __restrict__ scale, const float* __restrict__ shift,
+                    const T* __restrict__ res, long res_ld, T* __restrict__ out, long out_ld, RowGeom g, int leaky,
+                    int upsample) {
+  const int cv = g.c / 8;
+  const long total = g.rows * cv;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / cv;
+    const int c0 = (int)(i % cv) * 8;
+    float v[8];
+    load8(z + r * z_ld + c0, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[j] = fmaf(v[j], __ldg(scale + c0 + j), __ldg(shift + c0 + j));
+      if (leaky) v[j] = leaky01(v[j]);
+    }
+    if (res) {
+      float rv[8];
+      load8(res + r * res_ld + c0, rv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += rv[j];
+    }
+    if (!upsample) {
+      store8(out + r * out_ld + c0, v);
+    } else {
+      const long b = up_row(r, g.h, g.w);
+      const long W2 = 2L * g.w;
+      store8(out + b * out_ld + c0, v); store8(out + (b + 1) * out_ld + c0, v);
+      store8(out + (b + W2) * out_ld + c0, v); store8(out + (b + W2 + 1) * out_ld + c0, v);
+    }
+  }
+}
+
+// dA of row r (summing the 4 upsampled copies when the forward stored 2x-upsampled)
+template <typename T>
+__device__ __forceinline__ void load_dA(const T* dA, long dA_ld, long r, int c0, const RowGeom& g, int upsample,
+                                        float (&v)[8]) {
+  if (!upsample) {
+    load8(dA + r * dA_ld + c0, v);
+  } else {
+    const long b = up_row(r, g.h, g.w);
+    const long W2 = 2L * g.w;
+    float t[8];
+    load8(dA + b * dA_ld + c0, v);
+    load8(dA + (b + 1) * dA_ld + c0, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += t[j];
+    load8(dA + (b + W2) * dA_ld + c0, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += t[j];
+    load8(dA + (b + W2 + 1) * dA_ld + c0, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += t[j];
+  }
+}
+
+// grid: (row slabs, channel groups of blockDim.x*8); block (CX, RY): CX threads over channels, RY over rows
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const T* __restrict__ dA, long dA_ld, const T* __restrict__ z, long z_ld,
+                     const float* __restrict__ scale, const float* __restrict__ shift,
+                     const float* __restrict__ save_mean, const float* __restrict__ save_invstd, RowGeom g, int leaky,
+                     int upsample, long rows_per_block, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float s_g[256][8 + 1], s_b[256][8 + 1];
+  const int c0 = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
+  const bool active = c0 < g.c;
+  float ag[8], ab[8], sc[8], sh[8], mu[8], is[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    ag[j] = ab[j] = 0.f;
+    sc[j] = active ? scale[c0 + j] : 0.f; sh[j] = active ? shift[c0 + j] : 0.f;
+    mu[j] = active ? save_mean[c0 + j] : 0.f; is[j] = active ? save_invstd[c0 + j] : 0.f;
+  }
+  const long r0 = blockIdx.x * rows_per_block;
+  const long r1 = min(r0 + rows_per_block, g.rows);
+  if (active) {
+    for (long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+      float zv[8], dv[8];
+      load8(z + r * z_ld + c0, zv);
+      load_dA(dA, dA_ld, r, c0, g, upsample, dv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float y = fmaf(zv[j], sc[j], sh[j]);
+        const float da = (leaky && y <= 0.f) ? 0.1f * dv[j] : dv[j];
+        ab[j] += da;
+        ag[j] += da * (zv[j] - mu[j]) * is[j];
+      }
+    }
+  }
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s_g[tid][j] = ag[j]; s_b[tid][j] = ab[j]; }
+  __syncthreads();
+  if (threadIdx.y == 0 && active) {
+    for (int y = 1; y < blockDim.y; ++y) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { ag[j] += s_g[y * blockDim.x + threadIdx.x][j]; ab[j] += s_b[y * blockDim.x + threadIdx.x][j]; }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { atomicAdd(dgamma + c0 + j, ag[j]); atomicAdd(dbeta + c0 + j, ab[j]); }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const T* __restrict__ dA, long dA_ld, const T* __restrict__ z, long z_ld,
+                    const float* __restrict__ gamma, const float* __restrict__ scale, const float* __restrict__ shift,
+                    const float* __restrict__ save_mean, const float* __restrict__ save_invstd,
+                    const float* __restrict__ dgamma, const float* __restrict__ dbeta, RowGeom g, int leaky, int upsample,
+                    int dilate, T* __restrict__ dz, long dz_ld) {
+  const int cv = g.c / 8;
+  const long total = g.rows * cv;
+  const float inv_m = 1.f / (float)g.rows;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / cv;
+    const int c0 = (int)(i % cv) * 8;
+    float zv[8], dv[8], o[8];
+    load8(z + r * z_ld + c0, zv);
+    load_dA(dA, dA_ld, r, c0, g, upsample, dv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      const float y = fmaf(zv[j], __ldg(scale + c), __ldg(shift + c));
+      const float da = (leaky && y <= 0.f) ? 0.1f * dv[j] : dv[j];
+      const float is = __ldg(save_invstd + c);
+      const float zh = (zv[j] - __ldg(save_mean + c)) * is;
+      o[j] = __ldg(gamma + c) * is * (da - __ldg(dbeta + c) * inv_m - zh * __ldg(dgamma + c) * inv_m);
+    }
+    const long orow = dilate ? up_row(r, g.h, g.w) : r;   // (2p, 2q) of a zero-initialised [n,2h,2w] buffer
+    store8(dz + orow * dz_ld + c0, o);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+col_sum_kernel(const T* __restrict__ x, long ld, long rows, int c, long rows_per_block, float* __restrict__ out) {
+  // block (32, 8): 32 channels x 8 row lanes
+  __shared__ float s[8][33];
+  const int ch = blockIdx.y * 32 + threadIdx.x;
+  float a = 0.f;
+  const long r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, rows);
+  if (ch < c)
+    for (long r = r0 + threadIdx.y; r < r1; r += 8) a += static_cast<float>(x[r * ld + ch]);
+  s[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && ch < c) {
+    for (int y = 1; y < 8; ++y) a += s[y][threadIdx.x];
+    atomicAdd(out + ch, a);
+  }
+}
+
+static int grid1d(long total) {
+  long g = (total + 255) / 256;
+  const long cap = (long)num_sms() * 16;
+  return (int)(g < cap ? g : cap);
+}
+
+}  // namespace yb
+
+using namespace yb;
+
+#define YB_BN_COMMON_CHECK(name)                                                                         \
+  YB_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, name ": bad shape (c must be a multiple of 8)"); \
+  YB_REQUIRE(dtype == YB_F16 || dtype == YB_BF16, name ": dtype must be f16 or bf16");
+
+extern "C" int yb_bn_finalize(const float* sum, const float* sqsum, long count, int c, const float* gamma,
+                              const float* beta, float eps, float decay, float* moving_mean, float* moving_var,
+                              float* scale, float* shift, float* save_mean, float* save_invstd, void* stream) {
+  YB_REQUIRE(sum && sqsum && gamma && beta && scale && shift && save_mean && save_invstd && c > 0 && count > 0,
+             "bn_finalize: bad argument");
+  YB_REQUIRE((moving_mean == nullptr) == (moving_var == nullptr), "bn_finalize: moving_mean/var must both be given");
+  bn_finalize_kernel<<<ceil_div(c, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      sum, sqsum, (float)count, c, gamma, beta, eps, decay, moving_mean, moving_var, scale, shift, save_mean, save_invstd);
+  YB_CUDA(cudaGetLastError());
+  return YB_OK;
+}
+
+extern "C" int yb_bn_act_apply(const void* z, long z_ld, const float* scale, const float* shift, const void* res,
+                               long res_ld, void* out, long out_ld, int n, int h, int w, int c, int dtype, int leaky,
+                               int upsample2x, void* stream) {
+  YB_BN_COMMON_CHECK("bn_act_apply");
+  YB_REQUIRE(z && scale && shift && out, "bn_act_apply: null pointer");
+  RowGeom g{(long)n * h * w, h, w, c};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = grid1d(g.rows * (c / 8));
+  if (dtype == YB_F16)
+    bn_act_apply_kernel<__half><<<grid, 256, 0, st>>>((const __half*)z, z_ld, scale, shift, (const __half*)res, res_ld,
+                                                     (__half*)out, out_ld, g, leaky, upsample2x);
+  else
+    bn_act_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)z, z_ld, scale, shift,
+                                                            (const __nv_bfloat16*)res, res_ld, (__nv_bfloat16*)out,
+                                                            out_ld, g, leaky, upsample2x);
+  YB_CUDA(cudaGetLastError());
+  return YB_OK;
+}
+
+extern "C" int yb_bn_bwd_reduce(const void* dA, long dA_ld, const void* z, long z_ld, const float* scale,
+                                const float* shift, const float* save_mean, const float* save_invstd, int n, int h,
+                                int w, int c, int dtype, int leaky, int upsample2x, float* dgamma, float* dbeta,
+                                void* stream) {
+  YB_BN_COMMON_CHECK("bn_bwd_reduce");
+  YB_REQUIRE(dA && z && scale && shift && save_mean && save_invstd && dgamma && dbeta, "bn_bwd_reduce: null pointer");
+  RowGeom g{(long)n * h * w, h, w, c};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int cx = c / 8 < 32 ? c / 8 : 32;
+  dim3 block(cx, 256 / cx);
+  const int gy = ceil_div(c / 8, cx);
+  long slabs = (long)num_sms() * 8 / gy;
+  if (slabs < 1) slabs = 1;
+  long rpb = (g.rows + slabs - 1) / slabs;
+  if (rpb < (long)block.y * 4) rpb = (long)block.y * 4;
+  dim3 grid(ceil_div(g.rows, rpb), gy);
+  YB_CUDA(cudaMemsetAsync(dgamma, 0, c * 4, st));
+  YB_CUDA(cudaMemsetAsync(dbeta, 0, c * 4, st));
+  if (dtype == YB_F16)
+    bn_bwd_reduce_kernel<__half><<<grid, block, 0, st>>>((const __half*)dA, dA_ld, (const __half*)z, z_ld, scale, shift,
+                                                        save_mean, save_invstd, g, leaky, upsample2x, rpb, dgamma, dbeta);
+  else
+    bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)dA, dA_ld, (const __nv_bfloat16*)z,
+                                                               z_ld, scale, shift, save_mean, save_invstd, g, leaky,
+                                                               upsample2x, rpb, dgamma, dbeta);
+  YB_CUDA(cudaGetLastError());
+  return YB_OK;
+}
+
+extern "C" int yb_bn_bwd_apply(const void* dA, long dA_ld, const void* z, long z_ld, const float* gamma,
+                               const float* scale, const float* shift, const float* save_mean,
+                               const float* save_invstd, const float* dgamma, const float* dbeta, int n, int h, int w,
+                               int c, int dtype, int leaky, int upsample2x, int dilate2x, void* dz, long dz_ld,
+                               void* stream) {
+  YB_BN_COMMON_CHECK("bn_bwd_apply");
+  YB_REQUIRE(dA && z && gamma && scale && shift && save_mean && save_invstd && dgamma && dbeta && dz,
+             "bn_bwd_apply: null pointer");
+  RowGeom g{(long)n * h * w, h, w, c};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = grid1d(g.rows * (c / 8));
+  if (dtype == YB_F16)
+    bn_bwd_apply_kernel<__half><<<grid, 256, 0, st>>>((const __half*)dA, dA_ld, (const __half*)z, z_ld, gamma, scale,
+                                                     shift, save_mean, save_invstd, dgamma, dbeta, g, leaky,
+                                                     upsample2x, dilate2x, (__half*)dz, dz_ld);
+  else
+    bn_bwd_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dA, dA_ld, (const __nv_bfloat16*)z,
+                                                            z_ld, gamma, scale, shift, save_mean, save_invstd, dgamma,
+                                                            dbeta, g, leaky, upsample2x, dilate2x, (__nv_bfloat16*)dz,
+                                                            dz_ld);
+  YB_CUDA(cudaGetLastError());
+  return YB_OK;
+}
+
+extern "C" int yb_col_sum(const void* x, long ld, long rows, int c, int dtype, float* out, void* stream) {
+  YB_REQUIRE(x && out && rows > 0 && c > 0, "col_sum: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  YB_CUDA(cudaMemsetAsync(out, 0, c * 4, st));
+  const int gy = ceil_div(c, 32);
+  long slabs = (long)num_sms() * 8 / gy;
+  if (slabs < 1) slabs = 1;
+  long rpb = (rows + slabs - 1) / slabs;
+  if (rpb < 32) rpb = 32;
+  dim3 grid(ceil_div(rows, rpb), gy), block(32, 8);
+  if (dtype == YB_F16) col_sum_kernel<__half><<<grid, block, 0, st>>>((const __half*)x, ld, rows, c, rpb, out);
+  else if (dtype == YB_BF16) col_sum_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, ld, rows, c, rpb, out);
+  else if (dtype == YB_F32) col_sum_kernel<float><<<grid, block, 0, st>>>((const float*)x, ld, rows, c, rpb, out);
+  else { set_error("col_sum: bad dtype"); return YB_ERR_UNSUPPORTED; }
+  YB_CUDA(cudaGetLastError());
+  return YB_OK;
+}

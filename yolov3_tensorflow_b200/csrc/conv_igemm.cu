@@ -505,8 +505,15 @@ int make_tmap_2d(CUtensorMap* tm, const void* base, int dtype, long rows, long c
 
 // NHWC activation seen as {C, W, H, N}; im2col traversal for a ksize x ksize window with
 // symmetric padding `pad` and traversal stride `stride`; one request = 128 pixels x bk channels.
+int make_tmap_im2col_px(CUtensorMap* tm, const void* base, int dtype, int n, int h, int w, int c, long ld, int ksize,
+                        int stride, int pad, int bk, int pixels);
 int make_tmap_im2col(CUtensorMap* tm, const void* base, int dtype, int n, int h, int w, int c, long ld, int ksize,
                      int stride, int pad, int bk) {
+  return make_tmap_im2col_px(tm, base, dtype, n, h, w, c, ld, ksize, stride, pad, bk, BLOCK_M);
+}
+// `pixels` = output pixels gathered per request (rows of the shared-memory box)
+int make_tmap_im2col_px(CUtensorMap* tm, const void* base, int dtype, int n, int h, int w, int c, long ld, int ksize,
+                        int stride, int pad, int bk, int pixels) {
   int rc = load_driver_entry_points();
   if (rc) return rc;
   cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
@@ -517,7 +524,7 @@ int make_tmap_im2col(CUtensorMap* tm, const void* base, int dtype, int n, int h,
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUtensorMapSwizzle sw = bk * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUresult r = g_encode_im2col(tm, tm_dtype(dtype), 4, const_cast<void*>(base), dims, strides, lower, upper,
-                               (cuuint32_t)bk, (cuuint32_t)BLOCK_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                               (cuuint32_t)bk, (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeIm2col failed (%d): n=%d h=%d w=%d c=%d ld=%ld k=%d s=%d", (int)r, n, h, w, c, ld,

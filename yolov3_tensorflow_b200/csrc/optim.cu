@@ -1,0 +1,109 @@
+// Training-step tail (train.py:78,113-115; utils/misc_utils.py:151-153): L2 regulariser on the
+// conv weights (slim.l2_regularizer: grad += wd*w), per-tensor tf.clip_by_norm(g, clip), Momentum
+// (v = m*v + g ; w -= lr*v), plus the refresh of the 16-bit compute copy of every conv weight —
+// all 222 trainable tensors in two multi-tensor launches driven by a device-side chunk table.
+#include "common.cuh"
+#include "optim.cuh"
+
+namespace yb {
+
+__global__ void __launch_bounds__(256)
+opt_norm_kernel(const OptTensor* __restrict__ tensors, const OptChunk* __restrict__ chunks, int num_chunks,
+                float grad_scale, float weight_decay, float* __restrict__ sqnorm) {
+  __shared__ float s_red[8];
+  for (int ci = blockIdx.x; ci < num_chunks; ci += gridDim.x) {
+    const OptChunk ch = chunks[ci];
+    const OptTensor t = tensors[ch.tensor];
+    const float wd = t.l2 ? weight_decay : 0.f;
+    float acc = 0.f;
+    for (long i = ch.begin + threadIdx.x; i < ch.end; i += 256) {
+      const float g = t.g[i] * grad_scale + wd * t.w[i];
+      acc += g * g;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int w = 0; w < 8; ++w) s += s_red[w];
+      atomicAdd(sqnorm + ch.tensor, s);
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+opt_update_kernel(const OptTensor* __restrict__ tensors, const OptChunk* __restrict__ chunks, int num_chunks,
+                  float grad_scale, float weight_decay, float clip, float momentum, float lr,
+                  const float* __restrict__ sqnorm) {
+  for (int ci = blockIdx.x; ci < num_chunks; ci += gridDim.x) {
+    const OptChunk ch = chunks[ci];
+    const OptTensor t = tensors[ch.tensor];
+    const float wd = t.l2 ? weight_decay : 0.f;
+    const float nrm = sqrtf(sqnorm[ch.tensor]);
+    const float cs = clip > 0.f ? clip / fmaxf(nrm, clip) : 1.f;        // tf.clip_by_norm
+    T* w16 = static_cast<T*>(t.w16);
+    for (long i = ch.begin + threadIdx.x; i < ch.end; i += 256) {
+      const float w = t.w[i];
+      const float g = (t.g[i] * grad_scale + wd * w) * cs;
+      const float v = momentum * t.v[i] + g;                              // [TF] MomentumOptimizer, no Nesterov
+      const float nw = w - lr * v;
+      t.v[i] = v;
+      t.w[i] = nw;
+      if (w16) w16[i] = static_cast<T>(nw);
+    }
+  }
+}
+
+int opt_step(const OptTensor* tensors, const OptChunk* chunks, int num_tensors, int num_chunks, float* sqnorm,
+             int dtype, float lr, float grad_scale, float momentum, float weight_decay, float clip, cudaStream_t st) {
+  YB_CUDA(cudaMemsetAsync(sqnorm, 0, sizeof(float) * num_tensors, st));
+  const int grid = num_chunks < num_sms() * 8 ? num_chunks : num_sms() * 8;
+  opt_norm_kernel<<<grid, 256, 0, st>>>(tensors, chunks, num_chunks, grad_scale, weight_decay, sqnorm);
+  YB_CUDA(cudaGetLastError());
+  if (dtype == YB_BF16)
+    opt_update_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(tensors, chunks, num_chunks, grad_scale, weight_decay, clip,
+                                                          momentum, lr, sqnorm);
+  else
+    opt_update_kernel<__half><<<grid, 256, 0, st>>>(tensors, chunks, num_chunks, grad_scale, weight_decay, clip,
+                                                   momentum, lr, sqnorm);
+  YB_CUDA(cudaGetLastError());
+  return YB_OK;
+}
+
+// dgrad weights: Wd[ci][r'][s'][co] = W[co][k-1-r'][k-1-s'][ci]  (flip + transpose), K padded to kco
+template <typename T>
+__global__ void pack_dgrad_weights_kernel(const float* __restrict__ w, int cout, int cin, int ks, int kco, int cin_pad,
+                                          T* __restrict__ dst) {
+  const long total = (long)cin_pad * ks * ks * kco;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int co = i % kco;
+    const int s = (i / kco) % ks;
+    const int r = (i / ((long)kco * ks)) % ks;
+    const int ci = i / ((long)kco * ks * ks);
+    float v = 0.f;
+    if (co < cout && ci < cin) v = w[(((long)co * ks + (ks - 1 - r)) * ks + (ks - 1 - s)) * cin + ci];
+    dst[i] = static_cast<T>(v);
+  }
+}
+
+}  // namespace yb
+
+using namespace yb;
+
+extern "C" int yb_pack_dgrad_weights(const float* w_ohwi, int cout, int cin, int ksize, int k_cout, int cin_pad,
+                                     int dtype, void* dst, void* stream) {
+  YB_REQUIRE(w_ohwi && dst && cout > 0 && cin > 0 && k_cout >= cout && cin_pad >= cin, "pack_dgrad: bad argument");
+  const long total = (long)cin_pad * ksize * ksize * k_cout;
+  const int grid = (int)((total + 255) / 256 < 148L * 16 ? (total + 255) / 256 : 148L * 16);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == YB_F16)
+    pack_dgrad_weights_kernel<__half><<<grid, 256, 0, st>>>(w_ohwi, cout, cin, ksize, k_cout, cin_pad, (__half*)dst);
+  else if (dtype == YB_BF16)
+    pack_dgrad_weights_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(w_ohwi, cout, cin, ksize, k_cout, cin_pad, (__nv_bfloat16*)dst);
+  else { set_error("pack_dgrad: bad dtype"); return YB_ERR_UNSUPPORTED; }
+  YB_CUDA(cudaGetLastError());
+  return YB_OK;
+}

@@ -260,3 +260,60 @@ class yolov3(object):
         if return_scores:
             return boxes, confs, probs, scores
         return boxes, confs, probs
+
+    # ------------------------------------------------------------------ model.py:192-304
+    def _loss_scale(self, feature_map_i, y_true, anchors, loss4, want_grad=False, grad_out=None):
+        fm = _as_cuda_f32(feature_map_i, self.device)
+        yt = _as_cuda_f32(y_true, self.device)
+        n, gh, gw, d = fm.shape
+        C_ = self.class_num
+        if d != 3 * (5 + C_):
+            raise ValueError(f"feature_map last dim {d} != 3*(5+{C_})")
+        if tuple(yt.shape) != (n, gh, gw, 3, 6 + C_):
+            raise ValueError(f"y_true shape {tuple(yt.shape)} != {(n, gh, gw, 3, 6 + C_)}")
+        if self.img_size is None:
+            raise _lib.YoloB200Error("loss_layer: call forward() first (it records img_size, model.py:33)")
+        need = C.c_size_t()
+        check(lib.yb_loss_workspace_bytes(n, gh, gw, C.byref(need)), "yb_loss_workspace_bytes")
+        ws = torch.empty(need.value, dtype=torch.uint8, device=self.device)
+        grad = None
+        if want_grad:
+            grad = grad_out if grad_out is not None else torch.empty_like(fm)
+        anchors = np.asarray(anchors, np.float32).reshape(3, 2)
+        check(lib.yb_loss_layer(ptr(fm), ptr(yt), n, gh, gw, self.img_size[0], self.img_size[1], C_,
+                                _lib.fptr(anchors.reshape(-1)), int(self.use_label_smooth), int(self.use_focal_loss),
+                                1.0 / n, ptr(ws), ws.numel(), ptr(loss4), ptr(grad), _lib.YB_F32, 0, stream_handle()),
+              "yb_loss_layer")
+        return grad
+
+    def loss_layer(self, feature_map_i, y_true, anchors):
+        """model.py:192-304 -> (xy_loss, wh_loss, conf_loss, class_loss), 0-dim float32 CUDA tensors."""
+        l4 = torch.zeros(4, dtype=torch.float64, device=self.device)
+        self._loss_scale(feature_map_i, y_true, anchors, l4)
+        out = torch.empty(5, dtype=torch.float32, device=self.device)
+        check(lib.yb_loss_finalize(ptr(l4), ptr(out), stream_handle()), "yb_loss_finalize")
+        return out[1], out[2], out[3], out[4]
+
+    def box_iou(self, pred_boxes, valid_true_boxes):
+        """model.py:307-345: pred_boxes [g,g,3,4], valid_true_boxes [V,4] (cx,cy,w,h) -> [g,g,3,V]."""
+        pb = _as_cuda_f32(pred_boxes, self.device)
+        tb = _as_cuda_f32(valid_true_boxes, self.device).reshape(-1, 4)
+        lead = tuple(pb.shape[:-1])
+        P, V = int(np.prod(lead)), tb.shape[0]
+        out = torch.empty(lead + (V,), dtype=torch.float32, device=self.device)
+        check(lib.yb_box_iou(ptr(pb), ptr(tb), P, V, ptr(out), stream_handle()), "yb_box_iou")
+        return out
+
+    def compute_loss(self, y_pred, y_true, return_grads=False):
+        """model.py:348-365 -> [total_loss, loss_xy, loss_wh, loss_conf, loss_class] (0-dim float32 CUDA
+        tensors).  return_grads=True additionally returns d(total)/d(feature_map_i) for the three scales
+        (what train.py:112's compute_gradients back-propagates into the network)."""
+        if len(y_pred) != 3 or len(y_true) != 3:
+            raise ValueError("compute_loss expects 3 feature maps and 3 y_true tensors")
+        groups = [self.anchors[6:9], self.anchors[3:6], self.anchors[0:3]]
+        l4 = torch.zeros(4, dtype=torch.float64, device=self.device)
+        grads = [self._loss_scale(y_pred[i], y_true[i], groups[i], l4, want_grad=return_grads) for i in range(3)]
+        out = torch.empty(5, dtype=torch.float32, device=self.device)
+        check(lib.yb_loss_finalize(ptr(l4), ptr(out), stream_handle()), "yb_loss_finalize")
+        losses = [out[0], out[1], out[2], out[3], out[4]]
+        return (losses, grads) if return_grads else losses
