@@ -132,6 +132,8 @@ int yb_bn_bwd_apply(const void* dA, long dA_ld, const void* z, long z_ld, const 
                     int dilate2x, void* dz, long dz_ld, void* stream);
 /* out[c] (fp32, overwritten) = column sums of x [rows, ld] (bias gradient of the detection convs). */
 int yb_col_sum(const void* x, long ld, long rows, int c, int dtype, float* out, void* stream);
+/* column sums and sums of squares (BN batch statistics of the stem's raw output). */
+int yb_col_stats(const void* x, long ld, long rows, int c, int dtype, float* sum, float* sqsum, void* stream);
 
 /* ---------------------------------------------------------------------------------
  * Decode  (replaces the ~40 elementwise TF ops of model.py:82-190 and the caller's
@@ -222,6 +224,28 @@ int yb_net_forward(yb_net* net, const float* images, float* fm1, float* fm2, flo
  * (layer 0) and the tensor-core convs (1..74) with its own events. */
 int yb_net_forward_layers(yb_net* net, const float* images, float* fm1, float* fm2, float* fm3, int first,
                           int last, void* stream);
+/* ---- training plan (yb_net_create(..., training=1)); one reference training step (train.py:105-115) is
+ *      yb_net_train_fwd_bwd -> [all-reduce of yb_net_grad_buffer across ranks] -> yb_net_train_update ---- */
+/* forward with BN batch statistics (updating the moving statistics with `bn_decay`, train.py:108-109) ->
+ * compute_loss (model.py:348-365; loss4 = device double[4] xy,wh,conf,class, overwritten) -> backward into the
+ * flat gradient buffer (data term only).  forward_only=1 stops after the forward (y_true*, loss4 may be NULL).
+ * y_true_k: [n, g_k, g_k, 3, 5+C+1] float32 for the /32, /16, /8 maps; anchors9x2 host float[18].
+ * fm1..3 nullable (then the arena-owned float32 outputs are used). */
+int yb_net_train_fwd_bwd(yb_net* net, const float* images, const float* y_true_1, const float* y_true_2,
+                         const float* y_true_3, const float* anchors9x2, int use_label_smooth, int use_focal_loss,
+                         float bn_decay, float* fm1, float* fm2, float* fm3, double* loss4, int forward_only,
+                         void* stream);
+/* the flat float32 gradient of all 222 trainable tensors (creation order: per conv w [OHWI], then gamma, beta
+ * | bias; each padded to 4 floats) — the buffer a data-parallel wrapper all-reduces. */
+int yb_net_grad_buffer(yb_net* net, float** ptr, size_t* count);
+/* g = grad_scale*grad + weight_decay*w (conv weights only); per-tensor clip_by_norm(g, clip_norm) (<=0: off);
+ * v = momentum*v + g; w -= lr*v; refresh the 16-bit compute copies (train.py:78,113-115, misc_utils.py:151-153). */
+int yb_net_train_update(yb_net* net, float lr, float grad_scale, float momentum, float weight_decay,
+                        float clip_norm, void* stream);
+/* device pointers of one conv's float32 master parameters (w is OHWI [cout,k,k,cin]) / of its gradients. */
+int yb_net_get_conv_params(yb_net* net, int layer, float** w_ohwi, float** gamma, float** beta, float** mean,
+                           float** var, float** bias);
+int yb_net_layer_grad(yb_net* net, int layer, float** dw, float** dgamma, float** dbeta, float** dbias);
 /* device pointer + geometry of one layer's output activation (tests / debugging). */
 int yb_net_layer_output(const yb_net* net, int layer, void** ptr, int* ld, int* dtype);
 /* number of kernels one yb_net_forward enqueues (for bench.py's gpu_launches). */

@@ -273,3 +273,85 @@ def test_compute_loss_full_size_cfg3():
     ref = O.compute_loss([torch.from_numpy(a) for a in f], y_true, O.COCO_ANCHORS, (h, w), cn, True, True)
     np.testing.assert_allclose([float(v) for v in losses], [float(v) for v in ref], rtol=5e-5)
     assert all(torch.isfinite(gr).all() for gr in grads)
+
+
+# ------------------------------------------------------------------------- training step (A11, A12)
+def _train_case(seed=31, n=2, h=64, w=96, cn=80):
+    rng = np.random.default_rng(seed)
+    params = O.make_params(cn, seed=seed, random_bn=True, det_scale=2.0)
+    x = gen_inputs(seed + 1, n, h, w)
+    ys = [[], [], []]
+    for i in range(n):
+        boxes, labels = O.synth_gt(rng, w, h, cn, 8)
+        boxes[:, 2] = np.minimum(boxes[:, 2], w); boxes[:, 3] = np.minimum(boxes[:, 3], h)
+        y = O.process_box(boxes, labels, [w, h], cn, O.COCO_ANCHORS)
+        for j in range(3):
+            ys[j].append(y[j])
+    return params, x, [np.stack(y) for y in ys]
+
+
+def test_train_forward_batchnorm_statistics(golden_dir):
+    """forward(is_training=True): BN batch statistics + moving-stat update vs the reference-generated golden."""
+    g = np.load(os.path.join(golden_dir, "forward_train.npz"))
+    n, h, w = (int(v) for v in g["shape"])
+    params = O.make_params(80, seed=int(g["seed_params"]), random_bn=True)
+    x = gen_inputs(int(g["seed_x"]), n, h, w)
+    m = _pkg().yolov3(80, O.COCO_ANCHORS, batch_norm_decay=float(g["decay"]), dtype="bf16")
+    m.set_params(params, "HWIO")
+    fms = m.forward(torch.from_numpy(x).cuda(), is_training=True)
+    for a, name in zip(fms, ("fm1", "fm2", "fm3")):
+        assert _rel_err(a.cpu().numpy(), g[name]) < 6e-2, (name, _rel_err(a.cpu().numpy(), g[name]))   # bf16 storage, 75 layers
+    ps = m.get_params()
+    np.testing.assert_allclose(ps[0]["mean"], g["mean_first"], rtol=2e-2, atol=2e-4)
+    np.testing.assert_allclose(ps[0]["var"], g["var_first"], rtol=2e-2, atol=2e-4)
+    np.testing.assert_allclose(ps[73]["mean"], g["mean_last"], rtol=0.1, atol=3e-3)
+    np.testing.assert_allclose(ps[73]["var"], g["var_last"], rtol=0.1, atol=3e-3)
+
+
+@pytest.mark.parametrize("flags", [(False, False), (True, True)])
+def test_train_step_matches_oracle(flags):
+    ls, fo = flags
+    params, x, y_true = _train_case()
+    n, h, w = x.shape[:3]
+    lr = 1e-3
+    m = _pkg().yolov3(80, O.COCO_ANCHORS, use_label_smooth=ls, use_focal_loss=fo, batch_norm_decay=0.99, dtype="bf16")
+    m.set_params(params, "HWIO")
+    losses = m.train_step(torch.from_numpy(x).cuda(), [torch.from_numpy(y).cuda() for y in y_true], lr)
+    plan = m._last_plan
+    vel0 = [{k: np.zeros_like(v) for k, v in p.items() if k in ("w", "gamma", "beta", "b")} for p in params]
+    olosses, ograds, oparams, ovel = O.train_step(x, y_true, params, vel0, lr, O.COCO_ANCHORS, 80, ls, fo, bn_decay=0.99,
+                                                  emulate="bf16")
+    got = np.array([float(v) for v in losses])
+    np.testing.assert_allclose(got, olosses[:5], rtol=3e-2, atol=1e-3)
+    # gradients (data term) layer by layer: relative L2 error
+    worst = 0.0
+    for i in range(75):
+        gr = plan.layer_grads(i)
+        gw = np.transpose(gr["w"].cpu().numpy(), (1, 2, 3, 0))            # OHWI -> HWIO
+        ow = ograds[i]["w"] - 5e-4 * params[i]["w"]                       # oracle grads include the L2 term
+        e = float(np.linalg.norm(gw - ow) / max(np.linalg.norm(ow), 1e-12))
+        worst = max(worst, e)
+        assert e < 0.15, f"layer {i}: dW rel L2 err {e:.3g}"
+        for k in ("gamma", "beta", "b"):
+            if k in gr:
+                a, b = gr[k].cpu().numpy(), ograds[i][k]
+                e2 = float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-12))
+                assert e2 < 0.15, f"layer {i}: d{k} rel L2 err {e2:.3g}"
+    print(f"worst dW rel err {worst:.3g}")
+    # updated parameters and moving statistics
+    new = m.get_params()
+    for i in (0, 1, 30, 57, 58, 73, 74):
+        for k, v in oparams[i].items():
+            np.testing.assert_allclose(new[i][k], v, rtol=2e-2, atol=2e-4, err_msg=f"layer {i} {k}")
+    # the trained parameters drive the next inference forward (BN refold)
+    fms = m.forward(torch.from_numpy(x).cuda())
+    ref = O.forward(x, oparams_full(params, oparams), emulate="bf16")
+    for a, r in zip(fms, ref):
+        assert _rel_err(a.cpu().numpy(), r) < 6e-2
+
+
+def oparams_full(params, newp):
+    out = []
+    for p, q in zip(params, newp):
+        d = dict(p); d.update(q); out.append(d)
+    return out

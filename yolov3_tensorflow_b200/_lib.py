@@ -56,6 +56,7 @@ _SIGS = {
     "yb_bn_bwd_reduce": ([vp, C.c_long, vp, C.c_long, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp], i32),
     "yb_bn_bwd_apply": ([vp, C.c_long, vp, C.c_long, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, C.c_long, vp], i32),
     "yb_col_sum": ([vp, C.c_long, C.c_long, i32, i32, vp, vp], i32),
+    "yb_col_stats": ([vp, C.c_long, C.c_long, i32, i32, vp, vp, vp], i32),
     "yb_reorg_layer": ([vp, i32, i32, i32, i32, i32, i32, C.POINTER(f32), vp, vp, vp, vp, vp], i32),
     "yb_predict": ([vp, vp, vp, i32, i32, i32, i32, C.POINTER(f32), vp, vp, vp, vp, vp], i32),
     "yb_nms_workspace_bytes": ([i32, i32, i32, i32, C.POINTER(sz)], i32),
@@ -73,6 +74,11 @@ _SIGS = {
     "yb_net_set_conv_params": ([vp, i32, vp, i32, vp, vp, vp, vp, vp, vp], i32),
     "yb_net_forward": ([vp, vp, vp, vp, vp, vp], i32),
     "yb_net_forward_layers": ([vp, vp, vp, vp, vp, i32, i32, vp], i32),
+    "yb_net_train_fwd_bwd": ([vp, vp, vp, vp, vp, C.POINTER(f32), i32, i32, f32, vp, vp, vp, vp, i32, vp], i32),
+    "yb_net_grad_buffer": ([vp, C.POINTER(vp), C.POINTER(sz)], i32),
+    "yb_net_train_update": ([vp, f32, f32, f32, f32, f32, vp], i32),
+    "yb_net_get_conv_params": ([vp, i32] + [C.POINTER(vp)] * 6, i32),
+    "yb_net_layer_grad": ([vp, i32] + [C.POINTER(vp)] * 4, i32),
     "yb_net_layer_output": ([vp, i32, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32)], i32),
     "yb_net_forward_launches": ([vp], i32),
 }

@@ -202,19 +202,24 @@ bn_bwd_apply_kernel(const T* __restrict__ dA, long dA_ld, const T* __restrict__ 
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-col_sum_kernel(const T* __restrict__ x, long ld, long rows, int c, long rows_per_block, float* __restrict__ out) {
+col_sum_kernel(const T* __restrict__ x, long ld, long rows, int c, long rows_per_block, float* __restrict__ out,
+               float* __restrict__ out_sq) {
   // block (32, 8): 32 channels x 8 row lanes
-  __shared__ float s[8][33];
+  __shared__ float s[8][33], s2[8][33];
   const int ch = blockIdx.y * 32 + threadIdx.x;
-  float a = 0.f;
+  float a = 0.f, a2 = 0.f;
   const long r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, rows);
   if (ch < c)
-    for (long r = r0 + threadIdx.y; r < r1; r += 8) a += static_cast<float>(x[r * ld + ch]);
-  s[threadIdx.y][threadIdx.x] = a;
+    for (long r = r0 + threadIdx.y; r < r1; r += 8) {
+      const float v = static_cast<float>(x[r * ld + ch]);
+      a += v; a2 += v * v;
+    }
+  s[threadIdx.y][threadIdx.x] = a; s2[threadIdx.y][threadIdx.x] = a2;
   __syncthreads();
   if (threadIdx.y == 0 && ch < c) {
-    for (int y = 1; y < 8; ++y) a += s[y][threadIdx.x];
+    for (int y = 1; y < 8; ++y) { a += s[y][threadIdx.x]; a2 += s2[y][threadIdx.x]; }
     atomicAdd(out + ch, a);
+    if (out_sq) atomicAdd(out_sq + ch, a2);
   }
 }
 
@@ -316,19 +321,24 @@ extern "C" int yb_bn_bwd_apply(const void* dA, long dA_ld, const void* z, long z
   return YB_OK;
 }
 
+extern "C" int yb_col_stats(const void* x, long ld, long rows, int c, int dtype, float* sum, float* sqsum, void* stream);
 extern "C" int yb_col_sum(const void* x, long ld, long rows, int c, int dtype, float* out, void* stream) {
+  return yb_col_stats(x, ld, rows, c, dtype, out, nullptr, stream);
+}
+extern "C" int yb_col_stats(const void* x, long ld, long rows, int c, int dtype, float* out, float* out_sq, void* stream) {
   YB_REQUIRE(x && out && rows > 0 && c > 0, "col_sum: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   YB_CUDA(cudaMemsetAsync(out, 0, c * 4, st));
+  if (out_sq) YB_CUDA(cudaMemsetAsync(out_sq, 0, c * 4, st));
   const int gy = ceil_div(c, 32);
   long slabs = (long)num_sms() * 8 / gy;
   if (slabs < 1) slabs = 1;
   long rpb = (rows + slabs - 1) / slabs;
   if (rpb < 32) rpb = 32;
   dim3 grid(ceil_div(rows, rpb), gy), block(32, 8);
-  if (dtype == YB_F16) col_sum_kernel<__half><<<grid, block, 0, st>>>((const __half*)x, ld, rows, c, rpb, out);
-  else if (dtype == YB_BF16) col_sum_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, ld, rows, c, rpb, out);
-  else if (dtype == YB_F32) col_sum_kernel<float><<<grid, block, 0, st>>>((const float*)x, ld, rows, c, rpb, out);
+  if (dtype == YB_F16) col_sum_kernel<__half><<<grid, block, 0, st>>>((const __half*)x, ld, rows, c, rpb, out, out_sq);
+  else if (dtype == YB_BF16) col_sum_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, ld, rows, c, rpb, out, out_sq);
+  else if (dtype == YB_F32) col_sum_kernel<float><<<grid, block, 0, st>>>((const float*)x, ld, rows, c, rpb, out, out_sq);
   else { set_error("col_sum: bad dtype"); return YB_ERR_UNSUPPORTED; }
   YB_CUDA(cudaGetLastError());
   return YB_OK;

@@ -9,46 +9,12 @@
 #include "common.cuh"
 #include "conv.cuh"
 
-namespace yb {
-
-struct Ten {          // a view of an activation: buffer id + channel slice
-  int buf = -1;       // -1: network input image
-  int off = 0;        // first channel inside the buffer
-  int c = 0, h = 0, w = 0;
-};
-
-struct Buf {
-  int h, w, ld;       // [n, h, w, ld]
-  int fp32;           // detection outputs are float32
-  size_t offset = 0, bytes = 0;
-};
-
-struct Layer {
-  yb_layer_info info;
-  Ten in, out, res;   // res.buf == -2: none
-  bool upsample = false, out_fp32 = false;
-  int cout_pad = 0;
-  // parameter arena offsets (bytes)
-  size_t w_master = 0, w_packed = 0, gamma = 0, beta = 0, mean = 0, var = 0, bias = 0, scale = 0, shift = 0;
-  // prepared launch state
-  CUtensorMap tmA, tmB;
-  ConvParams params;
-  bool prepared = false;
-};
-
-}  // namespace yb
-
-struct yb_net {
-  int class_num, n, h, w, dtype, training;
-  std::vector<yb::Layer> layers;
-  std::vector<yb::Buf> bufs;
-  int fm_buf[3];
-  size_t act_bytes = 0, param_bytes = 0;
-  uint8_t* act = nullptr;
-  uint8_t* par = nullptr;
-};
+#include "net.cuh"
 
 namespace yb {
+void train_layout(yb_net* net);
+int train_bind(yb_net* net);
+int train_refresh_dgrad_weights(yb_net* net, int layer, void* stream);
 
 static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
@@ -194,11 +160,11 @@ extern "C" int yb_net_create(yb_net** out, int class_num, int n, int h, int w, i
   YB_REQUIRE(class_num > 0 && n > 0, "net_create: bad class_num/batch");
   YB_REQUIRE(h > 0 && w > 0 && h % 32 == 0 && w % 32 == 0, "net_create: H,W must be multiples of 32 (got %dx%d)", h, w);
   YB_REQUIRE(dtype == YB_F16 || dtype == YB_BF16, "net_create: dtype must be f16 or bf16");
-  if (training) { set_error("net_create: training plans are not implemented in this build"); return YB_ERR_UNSUPPORTED; }
   yb_net* net = new yb_net();
   net->class_num = class_num; net->n = n; net->h = h; net->w = w; net->dtype = dtype; net->training = training;
   Builder b{net};
   b.build();
+  if (training) train_layout(net);
   *out = net;
   return YB_OK;
 }
@@ -247,6 +213,7 @@ extern "C" int yb_net_bind(yb_net* net, void* activation_arena, size_t activatio
     if (rc) return rc;
     L.prepared = true;
   }
+  if (net->training) return train_bind(net);
   return YB_OK;
 }
 
@@ -280,6 +247,7 @@ extern "C" int yb_net_set_conv_params(yb_net* net, int layer, const float* w, in
     fill_kernel<<<ceil_div(L.cout_pad, 128), 128, 0, st>>>(scale, L.cout_pad, 1.0f);
     YB_CUDA(cudaGetLastError());
   }
+  if (net->training) return train_refresh_dgrad_weights(net, layer, stream);
   return YB_OK;
 }
 
@@ -294,6 +262,17 @@ extern "C" int yb_net_forward_layers(yb_net* net, const float* images, float* fm
   YB_REQUIRE(first >= 0 && first <= last, "forward: bad layer range");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* user_fm[3] = {fm1, fm2, fm3};
+  if (net->fold_dirty) {   // BN parameters / moving statistics changed by a training step: refold for inference
+    for (auto& L : net->layers) {
+      if (!L.info.has_bn) continue;
+      int rc = yb_bn_fold(reinterpret_cast<const float*>(net->par + L.gamma), reinterpret_cast<const float*>(net->par + L.beta),
+                          reinterpret_cast<const float*>(net->par + L.mean), reinterpret_cast<const float*>(net->par + L.var),
+                          L.info.cout, net->bn_eps, reinterpret_cast<float*>(net->par + L.scale),
+                          reinterpret_cast<float*>(net->par + L.shift), stream);
+      if (rc) return rc;
+    }
+    net->fold_dirty = false;
+  }
   if (first == 0) {
     Layer& L = net->layers[0];
     int rc = yb_stem_conv_fwd(images, reinterpret_cast<const float*>(net->par + L.w_master),

@@ -42,10 +42,11 @@ def _as_cuda_f32(x, device):
 class _Plan:
     """One yb_net (fixed batch/H/W) plus the arenas it is bound to."""
 
-    def __init__(self, model, n, h, w):
+    def __init__(self, model, n, h, w, training=False):
         self.n, self.h, self.w = n, h, w
+        self.training = training
         self.handle = C.c_void_p()
-        check(lib.yb_net_create(C.byref(self.handle), model.class_num, n, h, w, model._dtype_code, 0), "yb_net_create")
+        check(lib.yb_net_create(C.byref(self.handle), model.class_num, n, h, w, model._dtype_code, int(training)), "yb_net_create")
         a, p = C.c_size_t(), C.c_size_t()
         check(lib.yb_net_arena_bytes(self.handle, C.byref(a), C.byref(p)), "yb_net_arena_bytes")
         dev = model.device
@@ -54,6 +55,39 @@ class _Plan:
         check(lib.yb_net_bind(self.handle, ptr(self.act), self.act.numel(), ptr(self.par), self.par.numel()), "yb_net_bind")
         self.param_version = -1
         self.num_layers = lib.yb_net_num_layers(self.handle)
+        self.loss4 = torch.zeros(4, dtype=torch.float64, device=dev) if training else None
+
+    def _view(self, p, shape, dtype=torch.float32):
+        """torch view of `shape` floats at device pointer p inside the parameter arena."""
+        off = p - self.par.data_ptr()
+        n = int(np.prod(shape))
+        return self.par[off: off + n * 4].view(dtype).view(*shape)
+
+    def conv_params(self, i):
+        """Views of layer i's float32 master parameters: dict(w [cout,k,k,cin] OHWI, gamma, beta, mean, var | b)."""
+        ps = [C.c_void_p() for _ in range(6)]
+        check(lib.yb_net_get_conv_params(self.handle, i, *[C.byref(q) for q in ps]), "yb_net_get_conv_params")
+        info = self.layer_info(i)
+        out = {"w": self._view(ps[0].value, (info.cout, info.ksize, info.ksize, info.cin))}
+        for name, q in zip(("gamma", "beta", "mean", "var", "b"), ps[1:]):
+            if q.value:
+                out[name] = self._view(q.value, (info.cout,))
+        return out
+
+    def layer_grads(self, i):
+        ps = [C.c_void_p() for _ in range(4)]
+        check(lib.yb_net_layer_grad(self.handle, i, *[C.byref(q) for q in ps]), "yb_net_layer_grad")
+        info = self.layer_info(i)
+        out = {"w": self._view(ps[0].value, (info.cout, info.ksize, info.ksize, info.cin))}
+        for name, q in zip(("gamma", "beta", "b"), ps[1:]):
+            if q.value:
+                out[name] = self._view(q.value, (info.cout,))
+        return out
+
+    def grad_flat(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        check(lib.yb_net_grad_buffer(self.handle, C.byref(p), C.byref(n)), "yb_net_grad_buffer")
+        return self._view(p.value, (n.value,))
 
     def layer_info(self, i):
         info = _lib.LayerInfo()
@@ -105,6 +139,7 @@ class yolov3(object):
         self._params = None          # list of 75 dicts of CUDA float32 tensors
         self._param_layout = _lib.YB_W_HWIO
         self._param_version = 0
+        self._trained_plan = None    # plan whose master weights are newer than self._params (after train_step)
 
     # ------------------------------------------------------------------ parameters
     @staticmethod
@@ -176,12 +211,17 @@ class yolov3(object):
             ps.append(p)
         self.set_params(ps, "HWIO")
 
-    def _plan(self, n, h, w):
+    def _plan(self, n, h, w, training=False):
         key = (n, h, w)
         plan = self._plans.get(key)
+        if plan is not None and training and not plan.training:
+            plan = None                                  # upgrade an inference plan to a training plan
         if plan is None:
-            plan = _Plan(self, n, h, w)
+            self._sync_params_from_trained()
+            plan = _Plan(self, n, h, w, training)
             self._plans[key] = plan
+        if self._trained_plan is not None and plan is not self._trained_plan:
+            self._sync_params_from_trained()
         if plan.param_version != self._param_version:
             if self._params is None:
                 raise _lib.YoloB200Error("no parameters: call load_weights(model, file), set_params() or init_params()")
@@ -200,17 +240,22 @@ class yolov3(object):
         x = _as_cuda_f32(inputs, self.device)
         if x.dim() != 4 or x.shape[3] != 3:
             raise ValueError(f"inputs must be [N,H,W,3], got {tuple(x.shape)}")
-        if is_training:
-            raise _lib.YoloB200Error("is_training=True is not available in this build of the engine")
         n, h, w = int(x.shape[0]), int(x.shape[1]), int(x.shape[2])
         if h % 32 or w % 32:
             raise ValueError(f"H and W must be multiples of 32, got {h}x{w}")
         self.img_size = (h, w)
-        plan = self._plan(n, h, w)
+        plan = self._plan(n, h, w, training=bool(is_training))
         D = 3 * (5 + self.class_num)
         fms = [torch.empty((n, h // s, w // s, D), dtype=torch.float32, device=self.device) for s in (32, 16, 8)]
-        check(lib.yb_net_forward(plan.handle, ptr(x), ptr(fms[0]), ptr(fms[1]), ptr(fms[2]), stream_handle()),
-              "yb_net_forward")
+        if is_training:
+            # BN uses batch statistics and the moving statistics are updated (UPDATE_OPS, train.py:108-109)
+            check(lib.yb_net_train_fwd_bwd(plan.handle, ptr(x), None, None, None, None, 0, 0, float(self.batch_norm_decay),
+                                           ptr(fms[0]), ptr(fms[1]), ptr(fms[2]), None, 1, stream_handle()),
+                  "yb_net_train_fwd_bwd(forward_only)")
+            self._trained_plan = plan
+        else:
+            check(lib.yb_net_forward(plan.handle, ptr(x), ptr(fms[0]), ptr(fms[1]), ptr(fms[2]), stream_handle()),
+                  "yb_net_forward")
         self._last_plan = plan
         return fms[0], fms[1], fms[2]
 
@@ -317,3 +362,80 @@ class yolov3(object):
         check(lib.yb_loss_finalize(ptr(l4), ptr(out), stream_handle()), "yb_loss_finalize")
         losses = [out[0], out[1], out[2], out[3], out[4]]
         return (losses, grads) if return_grads else losses
+
+    # ------------------------------------------------------------------ train.py:105-115
+    def _sync_params_from_trained(self):
+        """After training steps the newest parameters live in the training plan's arena; pull them back
+        (device copies) before another plan is created or refreshed."""
+        plan = self._trained_plan
+        if plan is None:
+            return
+        out = []
+        for i in range(plan.num_layers):
+            q = {k: v.clone() for k, v in plan.conv_params(i).items()}
+            out.append(q)
+        self._params = out
+        self._param_layout = _lib.YB_W_OHWI
+        self._param_version += 1
+        plan.param_version = self._param_version      # its arena already holds these values
+        self._trained_plan = None
+
+    def get_params(self):
+        """Current parameters as 75 dicts of numpy arrays, weights in TF's HWIO layout."""
+        self._sync_params_from_trained()
+        if self._params is None:
+            raise _lib.YoloB200Error("no parameters")
+        out = []
+        for q in self._params:
+            d = {k: v.detach().cpu().numpy() for k, v in q.items()}
+            if self._param_layout == _lib.YB_W_OHWI:
+                d["w"] = np.ascontiguousarray(np.transpose(d["w"], (1, 2, 3, 0)))
+            elif self._param_layout == _lib.YB_W_OIHW:
+                d["w"] = np.ascontiguousarray(np.transpose(d["w"], (2, 3, 1, 0)))
+            out.append(d)
+        return out
+
+    def train_step(self, images, y_true, learning_rate, momentum=0.9, clip_norm=100.0, process_group=None,
+                   return_feature_maps=False):
+        """One training step of the reference (train.py:105-115): forward(is_training=True) -> compute_loss ->
+        gradients of (loss[0] + l2_loss) w.r.t. all 222 trainable tensors -> per-tensor clip_by_norm(clip_norm)
+        -> Momentum(momentum) update; BN moving statistics updated with self.batch_norm_decay.
+
+        images float32 [N,H,W,3]; y_true = (y_true_13, y_true_26, y_true_52) in process_box format.
+        Data parallel: when torch.distributed is initialised (or process_group is given) the flat gradient is
+        all-reduced (NCCL over NVLink) and averaged over the ranks before the update; every loss term is a
+        mean over the local batch (model.py:276-302), so this equals one big batch of world*N images.
+        Returns [total, xy, wh, conf, class] as 0-dim float32 CUDA tensors of the LOCAL batch."""
+        import torch.distributed as dist
+        x = _as_cuda_f32(images, self.device)
+        ys = [_as_cuda_f32(y, self.device) for y in y_true]
+        n, h, w = int(x.shape[0]), int(x.shape[1]), int(x.shape[2])
+        if h % 32 or w % 32 or x.shape[3] != 3:
+            raise ValueError(f"images must be [N,H,W,3] with H,W multiples of 32, got {tuple(x.shape)}")
+        C_ = self.class_num
+        for y, s in zip(ys, (32, 16, 8)):
+            if tuple(y.shape) != (n, h // s, w // s, 3, 6 + C_):
+                raise ValueError(f"y_true shape {tuple(y.shape)} != {(n, h // s, w // s, 3, 6 + C_)}")
+        self.img_size = (h, w)
+        plan = self._plan(n, h, w, training=True)
+        fms = [None, None, None]
+        if return_feature_maps:
+            fms = [torch.empty((n, h // s, w // s, 3 * (5 + C_)), dtype=torch.float32, device=self.device) for s in (32, 16, 8)]
+        st = stream_handle()
+        check(lib.yb_net_train_fwd_bwd(plan.handle, ptr(x), ptr(ys[0]), ptr(ys[1]), ptr(ys[2]),
+                                       _lib.fptr(self.anchors.reshape(-1)), int(self.use_label_smooth),
+                                       int(self.use_focal_loss), float(self.batch_norm_decay), ptr(fms[0]), ptr(fms[1]),
+                                       ptr(fms[2]), ptr(plan.loss4), 0, st), "yb_net_train_fwd_bwd")
+        world = 1
+        if process_group is not None or (dist.is_available() and dist.is_initialized()):
+            world = dist.get_world_size(process_group)
+            if world > 1:
+                dist.all_reduce(plan.grad_flat(), op=dist.ReduceOp.SUM, group=process_group)   # one NCCL all-reduce per step
+        check(lib.yb_net_train_update(plan.handle, float(learning_rate), 1.0 / world, float(momentum),
+                                      float(self.weight_decay), float(clip_norm), st), "yb_net_train_update")
+        self._trained_plan = plan
+        self._last_plan = plan
+        out = torch.empty(5, dtype=torch.float32, device=self.device)
+        check(lib.yb_loss_finalize(ptr(plan.loss4), ptr(out), st), "yb_loss_finalize")
+        losses = [out[0], out[1], out[2], out[3], out[4]]
+        return (losses, fms) if return_feature_maps else losses
