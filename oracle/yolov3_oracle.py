@@ -611,7 +611,7 @@ def train_step(x_nhwc, y_true, params, velocity, lr, anchors, class_num=80, use_
             mm, mv = new_stats[si]; si += 1
             npar["mean"], npar["var"] = mm.numpy(), mv.numpy()
         grads.append(g); new_params.append(npar); new_vel.append(nv)
-    return [float(l) for l in losses] + [float(l2)], grads, new_params, new_vel
+    return [float(l.detach()) for l in losses] + [float(l2.detach())], grads, new_params, new_vel
 
 
 # --------------------------------------------------------------------------------------

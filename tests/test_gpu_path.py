@@ -276,9 +276,9 @@ def test_compute_loss_full_size_cfg3():
 
 
 # ------------------------------------------------------------------------- training step (A11, A12)
-def _train_case(seed=31, n=2, h=64, w=96, cn=80):
+def _train_case(seed=31, n=2, h=128, w=160, cn=80):
     rng = np.random.default_rng(seed)
-    params = O.make_params(cn, seed=seed, random_bn=True, det_scale=2.0)
+    params = O.make_params(cn, seed=seed, random_bn=True)
     x = gen_inputs(seed + 1, n, h, w)
     ys = [[], [], []]
     for i in range(n):
