@@ -155,7 +155,7 @@ def make_params(class_num: int = 80, seed: int = 1, det_scale: float = 1.0, conf
 def _round_store(t: torch.Tensor, emulate):
     if emulate is None:
         return t
-    dt = torch.float16 if emulate == "fp16" else torch.bfloat16
+    dt = torch.float16 if emulate in ("fp16", "float16") else torch.bfloat16
     return t.to(dt).to(t.dtype)
 
 
