@@ -246,6 +246,10 @@ int yb_net_train_update(yb_net* net, float lr, float grad_scale, float momentum,
 int yb_net_get_conv_params(yb_net* net, int layer, float** w_ohwi, float** gamma, float** beta, float** mean,
                            float** var, float** bias);
 int yb_net_layer_grad(yb_net* net, int layer, float** dw, float** dgamma, float** dbeta, float** dbias);
+/* training scratch of one layer (tests): which = 0 raw conv output z, 1 its gradient dz (zero-inserted at the input
+ * resolution for stride-2 layers), 2 gradient w.r.t. the layer output, 3 the layer's input activation.
+ * All 16-bit [n, h, w, ld]. */
+int yb_net_train_buffer(yb_net* net, int layer, int which, void** ptr, int* ld, int* h, int* w);
 /* device pointer + geometry of one layer's output activation (tests / debugging). */
 int yb_net_layer_output(const yb_net* net, int layer, void** ptr, int* ld, int* dtype);
 /* number of kernels one yb_net_forward enqueues (for bench.py's gpu_launches). */

@@ -365,3 +365,45 @@ def oparams_full(params, newp):
     for p, q in zip(params, newp):
         d = dict(p); d.update(q); out.append(d)
     return out
+
+
+def test_train_backward_self_consistency():
+    """Every layer's backward kernels against PyTorch autograd ON THE ENGINE'S OWN TENSORS (its z, its incoming
+    gradient, its input activation): isolates each BN-backward / wgrad / dgrad launch from upstream noise."""
+    import torch.nn.functional as F
+    params, x, y_true = _train_case()
+    m = _pkg().yolov3(80, O.COCO_ANCHORS, batch_norm_decay=0.99, dtype="fp16")
+    m.set_params(params, "HWIO")
+    m.train_step(torch.from_numpy(x).cuda(), [torch.from_numpy(y).cuda() for y in y_true], 0.0)   # lr 0: weights unchanged
+    plan = m._last_plan
+    rows = []
+    for i in range(74, 0, -1):
+        info = plan.layer_info(i)
+        dz = plan.train_buffer(i, "dz").float()
+        if info.stride == 2:
+            dz = dz[:, ::2, ::2]
+        xin = plan.train_buffer(i, "in").float()
+        e_dz = float("nan")
+        if info.has_bn:
+            z = plan.train_buffer(i, "z").float().requires_grad_(True)
+            dA = plan.train_buffer(i, "dA").float()
+            if info.upsample2x:
+                dA = dA[:, 0::2, 0::2] + dA[:, 1::2, 0::2] + dA[:, 0::2, 1::2] + dA[:, 1::2, 1::2]
+            p = plan.conv_params(i)
+            mu = z.mean(dim=(0, 1, 2)); var = z.var(dim=(0, 1, 2), unbiased=False)
+            y = (z - mu) / torch.sqrt(var + 1e-5) * p["gamma"] + p["beta"]
+            a = torch.where(y > 0, y, 0.1 * y)
+            a.backward(dA)
+            e_dz = float((dz - z.grad).norm() / z.grad.norm().clamp(min=1e-20))
+        w = plan.conv_params(i)["w"].permute(0, 3, 1, 2).contiguous().half().float().requires_grad_(True)   # OHWI -> OIHW
+        xr = xin.permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+        out = F.conv2d(xr, w, None, stride=info.stride, padding=info.ksize // 2)
+        out.backward(dz[..., :info.cout].permute(0, 3, 1, 2))
+        gw = plan.layer_grads(i)["w"]
+        e_w = float((gw - w.grad.permute(0, 2, 3, 1)).norm() / w.grad.norm().clamp(min=1e-20))
+        rows.append((i, info.ksize, info.stride, info.cin, info.cout, e_dz, e_w))
+    print("layer k s cin cout | dz err | dW err   (vs autograd on the engine's own tensors)")
+    for r in rows:
+        print("  %2d %d %d %4d %4d | %.3g | %.3g" % r)
+    bad = [r for r in rows if (r[5] == r[5] and r[5] > 2e-2) or r[6] > 2e-2]
+    assert not bad, bad[:8]

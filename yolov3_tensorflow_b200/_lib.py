@@ -79,6 +79,7 @@ _SIGS = {
     "yb_net_train_update": ([vp, f32, f32, f32, f32, f32, vp], i32),
     "yb_net_get_conv_params": ([vp, i32] + [C.POINTER(vp)] * 6, i32),
     "yb_net_layer_grad": ([vp, i32] + [C.POINTER(vp)] * 4, i32),
+    "yb_net_train_buffer": ([vp, i32, i32, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)], i32),
     "yb_net_layer_output": ([vp, i32, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32)], i32),
     "yb_net_forward_launches": ([vp], i32),
 }

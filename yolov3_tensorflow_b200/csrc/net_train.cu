@@ -378,3 +378,22 @@ extern "C" int yb_net_layer_grad(yb_net* net, int layer, float** dw, float** dga
   if (dbias) *dbias = L.info.has_bn ? nullptr : gradp(net, L.g_bias);
   return YB_OK;
 }
+
+extern "C" int yb_net_train_buffer(yb_net* net, int layer, int which, void** ptr, int* ld, int* rows_h, int* rows_w) {
+  YB_REQUIRE(net && net->training && net->act && layer >= 0 && layer < (int)net->layers.size() && ptr && ld,
+             "train_buffer: bad argument");
+  Layer& L = net->layers[layer];
+  int h = L.info.out_h, w = L.info.out_w;
+  switch (which) {
+    case 0: YB_REQUIRE(L.info.has_bn, "train_buffer: no z for detection convs"); *ptr = net->act + L.z_off; *ld = L.info.cout; break;
+    case 1: *ptr = net->act + L.dz_off; *ld = L.dz_ld; if (L.dz_dilated) { h = L.info.in_h; w = L.info.in_w; } break;
+    case 2: YB_REQUIRE(L.info.has_bn, "train_buffer: no dA for detection convs"); *ptr = gten_ptr(net, L.out); *ld = net->bufs[L.out.buf].ld;
+            if (L.upsample) { h *= 2; w *= 2; } break;
+    case 3: YB_REQUIRE(layer > 0, "train_buffer: layer 0 reads the image"); *ptr = ten_ptr2(net, L.in); *ld = net->bufs[L.in.buf].ld;
+            h = L.info.in_h; w = L.info.in_w; break;
+    default: set_error("train_buffer: which must be 0..3"); return YB_ERR_INVALID_ARGUMENT;
+  }
+  if (rows_h) *rows_h = h;
+  if (rows_w) *rows_w = w;
+  return YB_OK;
+}

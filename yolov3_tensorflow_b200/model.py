@@ -45,6 +45,7 @@ class _Plan:
     def __init__(self, model, n, h, w, training=False):
         self.n, self.h, self.w = n, h, w
         self.training = training
+        self.act_dtype = model._torch_dtype
         self.handle = C.c_void_p()
         check(lib.yb_net_create(C.byref(self.handle), model.class_num, n, h, w, model._dtype_code, int(training)), "yb_net_create")
         a, p = C.c_size_t(), C.c_size_t()
@@ -83,6 +84,20 @@ class _Plan:
             if q.value:
                 out[name] = self._view(q.value, (info.cout,))
         return out
+
+    def train_buffer(self, i, which):
+        """Strided view [n,h,w,c] of layer i's training scratch: which = 'z' | 'dz' | 'dA' | 'in'."""
+        code = {"z": 0, "dz": 1, "dA": 2, "in": 3}[which]
+        p, ld, hh, ww = C.c_void_p(), C.c_int(), C.c_int(), C.c_int()
+        check(lib.yb_net_train_buffer(self.handle, i, code, C.byref(p), C.byref(ld), C.byref(hh), C.byref(ww)), "yb_net_train_buffer")
+        info = self.layer_info(i)
+        c = info.cin if which == "in" else info.cout
+        off = p.value - self.act.data_ptr()
+        h, w = hh.value, ww.value
+        nelem = (self.n * h * w - 1) * ld.value + c
+        tdt = torch.float16 if self.act_dtype == torch.float16 else torch.bfloat16
+        flat = self.act[off: off + nelem * 2].view(tdt)
+        return flat.as_strided((self.n, h, w, c), (h * w * ld.value, w * ld.value, ld.value, 1))
 
     def grad_flat(self):
         p, n = C.c_void_p(), C.c_size_t()
