@@ -12,7 +12,7 @@ for id in $ids; do
   if [ $rc -eq 0 ]; then pass=$((pass+1)); echo "PASS $id"; else
     fail=$((fail+1)); echo "FAIL($rc) $id"
     echo "==================== $id (rc=$rc)" >> $LOG
-    echo "$out" | tail -40 >> $LOG
+    echo "$out" | grep -v "^  " | tail -120 >> $LOG
   fi
 done
 echo "isolated: $pass passed, $fail failed"
