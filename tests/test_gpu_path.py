@@ -366,7 +366,18 @@ def test_train_step_matches_oracle(flags):
             assert e <= 3 * noise + 0.05, f"layer {i} {k}: update rel err {e:.3g} (noise {noise:.3g})"
     # the trained parameters drive the next inference forward (BN refold from the new moving statistics)
     fms = m.forward(torch.from_numpy(x).cuda())
-    ref = O.forward(x, m.get_params(), emulate=dt)
+    rec = []
+    ref = O.forward(x, m.get_params(), emulate=dt, record=rec)
+    for i in range(75):
+        info = plan.layer_info(i)
+        if not info.has_bn:
+            continue
+        r = rec[i].numpy()
+        if info.upsample2x:
+            r = r.repeat(2, axis=1).repeat(2, axis=2)
+        e = _rel_err(plan.layer_output(i).float().cpu().numpy(), r)
+        if e > 5e-3 or i % 10 == 0:
+            print(f"  post-update layer {i:2d} rel err {e:.3g}")
     for a, r in zip(fms, ref):
         print("  post-update inference forward rel err", _rel_err(a.cpu().numpy(), r))
         assert _rel_err(a.cpu().numpy(), r) < (2e-2 if dt == "fp16" else 0.1)
