@@ -135,7 +135,8 @@ struct Builder {
         L.bias = o;  o = align256(o + cb);
       }
       L.scale = o; o = align256(o + cb);
-      L.shift = o; o = align256(o + cb);
+      if (L.info.has_bn) { L.shift = o; o = align256(o + cb); }
+      else L.shift = L.bias;   // detection convs: the epilogue's shift IS the (trainable) bias
     }
     net->param_bytes = o;
   }
@@ -241,9 +242,8 @@ extern "C" int yb_net_set_conv_params(yb_net* net, int layer, const float* w, in
     if (rc) return rc;
   } else {
     YB_REQUIRE(bias, "set_conv_params: layer %d needs a bias", layer);
+    YB_CUDA(cudaMemsetAsync(shift, 0, L.cout_pad * 4, st));          // shift aliases the bias buffer
     YB_CUDA(cudaMemcpyAsync(net->par + L.bias, bias, c * 4, cudaMemcpyDeviceToDevice, st));
-    YB_CUDA(cudaMemsetAsync(shift, 0, L.cout_pad * 4, st));
-    YB_CUDA(cudaMemcpyAsync(shift, bias, c * 4, cudaMemcpyDeviceToDevice, st));
     fill_kernel<<<ceil_div(L.cout_pad, 128), 128, 0, st>>>(scale, L.cout_pad, 1.0f);
     YB_CUDA(cudaGetLastError());
   }
