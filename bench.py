@@ -144,6 +144,30 @@ def run_cpu(size, steps, warmup, sample_images):
                        f"restatement of the TF1 graph; TensorFlow not installable in this image)"), dt / steps
 
 
+def synth_y_true(rng, n, size, anchors, class_num=CLASS_NUM, max_boxes=50):
+    """SURVEY.md §8d cfg 3/4 targets: per image U{1..50} boxes, w,h ~ logU[8,400], best-anchor assignment
+    (utils/data_utils.py:51-115 semantics, vectorised on the host) -> three y_true tensors on the GPU."""
+    import torch
+    ys = [np.zeros((n, size // s, size // s, 3, 6 + class_num), np.float32) for s in (32, 16, 8)]
+    for y in ys:
+        y[..., -1] = 1.0
+    anc = np.asarray(anchors, np.float32)
+    for i in range(n):
+        v = int(rng.integers(1, max_boxes + 1))
+        wh = np.exp(rng.uniform(np.log(8), np.log(400), (v, 2))).clip(max=size)
+        c = rng.uniform(0, size, (v, 2)).clip(wh / 2, size - wh / 2)
+        inter = np.minimum(wh[:, None, :], anc[None]).prod(-1)
+        iou = inter / (wh.prod(-1)[:, None] + anc.prod(-1)[None] - inter + 1e-10)
+        best = iou.argmax(1)
+        for j in range(v):
+            g = 2 - best[j] // 3
+            r = (32, 16, 8)[g]
+            ys[g][i, int(c[j, 1] // r), int(c[j, 0] // r), best[j] % 3, :4] = (c[j, 0], c[j, 1], wh[j, 0], wh[j, 1])
+            ys[g][i, int(c[j, 1] // r), int(c[j, 0] // r), best[j] % 3, 4] = 1.0
+            ys[g][i, int(c[j, 1] // r), int(c[j, 0] // r), best[j] % 3, 5 + int(rng.integers(0, class_num))] = 1.0
+    return [torch.from_numpy(y).cuda() for y in ys]
+
+
 # --------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -154,6 +178,9 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--size", type=int, default=416)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--train-batch", type=int, default=32)
+    ap.add_argument("--train-size", type=int, default=416)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -280,6 +307,38 @@ def main():
                 "peak_source": pk["src"], "ms_per_step_conv": conv_t * 1e3, "ms_per_step_stem": float(np.mean(stem_ms)),
                 "algorithmic_flop_per_step": conv_flop}
 
+    # ---------------- training step (BASELINE.json configs[2]/[3]): fwd + loss + bwd + allreduce + update ----------------
+    train = None
+    if not args.no_train:
+        tb, ts = args.train_batch, args.train_size
+        del model, x_dev
+        torch.cuda.empty_cache()
+        tm = pkg.yolov3(CLASS_NUM, anchors, use_label_smooth=True, use_focal_loss=True, batch_norm_decay=0.99, dtype="bf16")
+        tm.init_params(seed=3)
+        rng = np.random.default_rng(3 + rank)
+        xt = torch.from_numpy(rng.random((tb, ts, ts, 3), dtype=np.float32)).cuda()
+        yts = synth_y_true(rng, tb, ts, anchors)
+        tsteps = max(3, min(args.steps, 8))
+        for _ in range(2):
+            tm.train_step(xt, yts, 1e-4)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(tsteps):
+            tl = tm.train_step(xt, yts, 1e-4)
+        a1.record()
+        barrier()
+        tms = torch.tensor([a0.elapsed_time(a1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        t_step = float(tms) / tsteps * 1e-3
+        gflop = (197.29 if ts == 416 else 197.29 * (ts / 416.0) ** 2)
+        train = {"images_per_s": tb * world / t_step, "ms_per_step": t_step * 1e3, "batch_per_gpu": tb, "image": [ts, ts],
+                 "dtype": "bf16", "loss_total": float(tl[0]), "steps": tsteps,
+                 "tflops": tb * gflop * 1e9 / t_step / 1e12, "frac_of_peak": tb * gflop * 1e9 / t_step / 1e12 / pk["tflops"],
+                 "what": "forward(BN batch stats) + compute_loss(focal, label-smooth) + backward + "
+                         + ("NCCL all-reduce + " if world > 1 else "") + "L2/clip/momentum update, synthetic <=50 boxes/img"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -296,6 +355,8 @@ def main():
             "launches_per_step": {"stem_conv": 1, "conv_igemm(tcgen05)": 74, "predict": 1, "nms": 3},
             "detections_per_step": n_det, "clocks": clocks, "roofline": roofline,
             "fraction_of_conv_flop_roofline": (value / world) * FWD_GFLOP_416 * scale * 1e9 / (pk["tflops"] * 1e12)}
+    if train is not None:
+        line["train"] = train
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = run_cpu(S, 2, 1, sample_images=2)
         line["cpu_baseline"] = cb

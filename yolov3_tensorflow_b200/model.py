@@ -411,7 +411,7 @@ class yolov3(object):
         return out
 
     def train_step(self, images, y_true, learning_rate, momentum=0.9, clip_norm=100.0, process_group=None,
-                   return_feature_maps=False):
+                   return_feature_maps=False, data_parallel=True):
         """One training step of the reference (train.py:105-115): forward(is_training=True) -> compute_loss ->
         gradients of (loss[0] + l2_loss) w.r.t. all 222 trainable tensors -> per-tensor clip_by_norm(clip_norm)
         -> Momentum(momentum) update; BN moving statistics updated with self.batch_norm_decay.
@@ -441,12 +441,11 @@ class yolov3(object):
                                        _lib.fptr(self.anchors.reshape(-1)), int(self.use_label_smooth),
                                        int(self.use_focal_loss), float(self.batch_norm_decay), ptr(fms[0]), ptr(fms[1]),
                                        ptr(fms[2]), ptr(plan.loss4), 0, st), "yb_net_train_fwd_bwd")
-        world = 1
-        if process_group is not None or (dist.is_available() and dist.is_initialized()):
-            world = dist.get_world_size(process_group)
-            if world > 1:
-                dist.all_reduce(plan.grad_flat(), op=dist.ReduceOp.SUM, group=process_group)   # one NCCL all-reduce per step
-        check(lib.yb_net_train_update(plan.handle, float(learning_rate), 1.0 / world, float(momentum),
+        from .parallel import allreduce_gradients
+        grad_scale = 1.0
+        if data_parallel and (process_group is not None or (dist.is_available() and dist.is_initialized())):
+            grad_scale = allreduce_gradients(plan.grad_flat(), process_group)   # one NCCL all-reduce per step
+        check(lib.yb_net_train_update(plan.handle, float(learning_rate), grad_scale, float(momentum),
                                       float(self.weight_decay), float(clip_norm), st), "yb_net_train_update")
         self._trained_plan = plan
         self._last_plan = plan
