@@ -26,24 +26,36 @@ def _worker(rank, world, port, q):
     lo, hi = parallel.shard_batch(4, rank, world)
     xs = torch.from_numpy(x[lo:hi]).cuda()
     ys = [torch.from_numpy(y[lo:hi]).cuda() for y in y_true]
-    # per-rank gradient without the all-reduce (lr 0: parameters untouched)
-    m0 = pkg.yolov3(80, O.COCO_ANCHORS, dtype="bf16")
-    m0.set_params(params, "HWIO")
-    m0.train_step(xs, ys, 0.0, data_parallel=False)
-    g_local = m0._last_plan.grad_flat().clone()
-    gs = [torch.empty_like(g_local) for _ in range(world)]
-    dist.all_gather(gs, g_local)
-    # data-parallel step
+    # local backward (lr 0, no collective), then the data-parallel tail exactly as train_step runs it:
+    # ONE all-reduce of the flat gradient buffer, mean factor folded into the fused optimizer kernel.
+    # (Two separate backward runs are not comparable bit-for-bit: the BN statistics are accumulated with
+    #  fp32 atomics, and at random init this network's BN backward amplifies that last-bit noise.)
+    from yolov3_tensorflow_b200._lib import lib, check, stream_handle
     m = pkg.yolov3(80, O.COCO_ANCHORS, dtype="bf16")
     m.set_params(params, "HWIO")
-    m.train_step(xs, ys, 1e-3)
-    g_dp = m._last_plan.grad_flat()
+    m.train_step(xs, ys, 0.0, data_parallel=False)
+    plan = m._last_plan
+    g_local = plan.grad_flat().clone()
+    gs = [torch.empty_like(g_local) for _ in range(world)]
+    dist.all_gather(gs, g_local)
+    scale = parallel.allreduce_gradients(plan.grad_flat())
+    assert scale == 1.0 / world
     ref = gs[0] + gs[1]
-    err = float((g_dp - ref).abs().max() / ref.abs().max())
-    w = torch.cat([m._last_plan.conv_params(i)["w"].reshape(-1) for i in (0, 30, 74)])
+    err = float((plan.grad_flat() - ref).abs().max() / ref.abs().max())
+    check(lib.yb_net_train_update(plan.handle, 1e-3, scale, 0.9, 5e-4, 100.0, stream_handle()), "update")
+    w = torch.cat([plan.conv_params(i)["w"].reshape(-1) for i in (0, 30, 74)])
     ws = [torch.empty_like(w) for _ in range(world)]
     dist.all_gather(ws, w)
-    same = bool(torch.equal(ws[0], ws[1]))
+    same = bool(torch.equal(ws[0], ws[1])) and not bool(torch.equal(w, torch.cat([torch.from_numpy(
+        np.ascontiguousarray(np.transpose(params[i]["w"], (3, 0, 1, 2)))).reshape(-1) for i in (0, 30, 74)]).cuda()))
+    # and the public API end to end: a DP train_step leaves both ranks with identical parameters
+    m2 = pkg.yolov3(80, O.COCO_ANCHORS, dtype="bf16")
+    m2.set_params(params, "HWIO")
+    m2.train_step(xs, ys, 1e-3)
+    w2 = torch.cat([m2._last_plan.conv_params(i)["w"].reshape(-1) for i in (0, 30, 74)])
+    ws2 = [torch.empty_like(w2) for _ in range(world)]
+    dist.all_gather(ws2, w2)
+    same = same and bool(torch.equal(ws2[0], ws2[1]))
     dist.barrier()
     dist.destroy_process_group()
     q.put((rank, err, same))
