@@ -223,13 +223,13 @@ def main():
 
     def step_device():
         fms = model.forward(x_dev)
-        boxes, confs, probs, scores = model.predict(fms, return_scores=True)
+        boxes, scores = model.predict_scores(fms)
         return batched_nms_raw(boxes, scores, CLASS_NUM, **NMS_ARGS)
 
     def step_e2e():
         xd = x_host.to("cuda", non_blocking=True)                              # H2D, every step
         fms = model.forward(xd)
-        boxes, confs, probs, scores = model.predict(fms, return_scores=True)
+        boxes, scores = model.predict_scores(fms)
         ob, os_, ol, oi, cnt = batched_nms_raw(boxes, scores, CLASS_NUM, **NMS_ARGS)
         counts = cnt.cpu()                                                     # D2H (sync): K per image
         kmax = max(int(counts.max()), 1)

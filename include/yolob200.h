@@ -146,7 +146,7 @@ int yb_reorg_layer(const float* feature_map, int n, int gh, int gw, int img_h, i
                    const float* anchors3x2, float* xy_offset, float* boxes, float* conf_logits,
                    float* prob_logits, void* stream);
 /* predict (model.py:140-190) over the three scales (/32,/16,/8).  anchors9x2: host float[18].
- * boxes [n,B,4] xyxy, confs [n,B,1], probs [n,B,C], scores [n,B,C] = conf*prob (nullable),
+ * boxes [n,B,4] xyxy, confs [n,B,1] (nullable), probs [n,B,C] (nullable), scores [n,B,C] = conf*prob (nullable),
  * B = 3*(h/32*w/32 + h/16*w/16 + h/8*w/8). */
 int yb_predict(const float* fm1, const float* fm2, const float* fm3, int n, int img_h, int img_w, int class_num,
                const float* anchors9x2, float* boxes, float* confs, float* probs, float* scores, void* stream);

@@ -66,104 +66,118 @@ __device__ __forceinline__ long up_row(long r, int h, int w) {
   return ((img * 2 * h + 2 * pp) * (2L * w)) + 2 * q;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256)
-bn_act_apply_kernel(const T* __restrict__ z, long z_ld, const float* __restrict__ scale, const float* __restrict__ shift,
-                    const T* __restrict__ res, long res_ld, T* __restrict__ out, long out_ld, RowGeom g, int leaky,
-                    int upsample) {
-  const int cv = g.c / 8;
-  const long total = g.rows * cv;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const long r = i / cv;
-    const int c0 = (int)(i % cv) * 8;
-    float v[8];
-    load8(z + r * z_ld + c0, v);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      v[j] = fmaf(v[j], __ldg(scale + c0 + j), __ldg(shift + c0 + j));
-      if (leaky) v[j] = leaky01(v[j]);
-    }
-    if (res) {
-      float rv[8];
-      load8(res + r * res_ld + c0, rv);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] += rv[j];
-    }
-    if (!upsample) {
-      store8(out + r * out_ld + c0, v);
-    } else {
-      const long b = up_row(r, g.h, g.w);
-      const long W2 = 2L * g.w;
-      store8(out + b * out_ld + c0, v); store8(out + (b + 1) * out_ld + c0, v);
-      store8(out + (b + W2) * out_ld + c0, v); store8(out + (b + W2 + 1) * out_ld + c0, v);
-    }
-  }
-}
-
-// dA of row r (summing the 4 upsampled copies when the forward stored 2x-upsampled)
+// ---- streaming kernels: thread = (8-channel vector cv, row lane); per-channel coefficients live in registers,
+// ---- rows are walked 4 at a time so several 16-byte loads are in flight per thread.
 template <typename T>
 __device__ __forceinline__ void load_dA(const T* dA, long dA_ld, long r, int c0, const RowGeom& g, int upsample,
                                         float (&v)[8]) {
   if (!upsample) {
     load8(dA + r * dA_ld + c0, v);
-  } else {
+  } else {   // the forward stored this row 2x-upsampled: its gradient is the sum of the 4 copies
     const long b = up_row(r, g.h, g.w);
     const long W2 = 2L * g.w;
-    float t[8];
+    float t0[8], t1[8], t2[8];
     load8(dA + b * dA_ld + c0, v);
-    load8(dA + (b + 1) * dA_ld + c0, t);
+    load8(dA + (b + 1) * dA_ld + c0, t0);
+    load8(dA + (b + W2) * dA_ld + c0, t1);
+    load8(dA + (b + W2 + 1) * dA_ld + c0, t2);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] += t[j];
-    load8(dA + (b + W2) * dA_ld + c0, t);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] += t[j];
-    load8(dA + (b + W2 + 1) * dA_ld + c0, t);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] += t[j];
+    for (int j = 0; j < 8; ++j) v[j] += t0[j] + t1[j] + t2[j];
   }
 }
 
-// grid: (row slabs, channel groups of blockDim.x*8); block (CX, RY): CX threads over channels, RY over rows
+struct StreamGeom {
+  int cv;             // channel vectors per row (c / 8)
+  int lanes;          // row lanes per block (256 / cv)
+  long rows_per_block;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_act_apply_kernel(const T* __restrict__ z, long z_ld, const float* __restrict__ scale, const float* __restrict__ shift,
+                    const T* __restrict__ res, long res_ld, T* __restrict__ out, long out_ld, RowGeom g, StreamGeom sg,
+                    int leaky, int upsample) {
+  const int cvi = threadIdx.x % sg.cv, lane_r = threadIdx.x / sg.cv;
+  const int c0 = cvi * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; }
+  const long r0 = blockIdx.x * sg.rows_per_block, r1 = min(r0 + sg.rows_per_block, g.rows);
+  for (long rb = r0 + lane_r; rb < r1; rb += 4L * sg.lanes) {
+    float v[4][8], rv[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long r = rb + (long)u * sg.lanes;
+      if (r < r1) {
+        load8(z + r * z_ld + c0, v[u]);
+        if (res) load8(res + r * res_ld + c0, rv[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long r = rb + (long)u * sg.lanes;
+      if (r >= r1) break;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float y = fmaf(v[u][j], sc[j], sh[j]);
+        if (leaky) y = leaky01(y);
+        if (res) y += rv[u][j];
+        v[u][j] = y;
+      }
+      if (!upsample) {
+        store8(out + r * out_ld + c0, v[u]);
+      } else {
+        const long b = up_row(r, g.h, g.w);
+        const long W2 = 2L * g.w;
+        store8(out + b * out_ld + c0, v[u]); store8(out + (b + 1) * out_ld + c0, v[u]);
+        store8(out + (b + W2) * out_ld + c0, v[u]); store8(out + (b + W2 + 1) * out_ld + c0, v[u]);
+      }
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const T* __restrict__ dA, long dA_ld, const T* __restrict__ z, long z_ld,
                      const float* __restrict__ scale, const float* __restrict__ shift,
-                     const float* __restrict__ save_mean, const float* __restrict__ save_invstd, RowGeom g, int leaky,
-                     int upsample, long rows_per_block, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  __shared__ float s_g[256][8 + 1], s_b[256][8 + 1];
-  const int c0 = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
-  const bool active = c0 < g.c;
+                     const float* __restrict__ save_mean, const float* __restrict__ save_invstd, RowGeom g,
+                     StreamGeom sg, int leaky, int upsample, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float s_g[256][9], s_b[256][9];
+  const int cvi = threadIdx.x % sg.cv, lane_r = threadIdx.x / sg.cv;
+  const int c0 = cvi * 8;
   float ag[8], ab[8], sc[8], sh[8], mu[8], is[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     ag[j] = ab[j] = 0.f;
-    sc[j] = active ? scale[c0 + j] : 0.f; sh[j] = active ? shift[c0 + j] : 0.f;
-    mu[j] = active ? save_mean[c0 + j] : 0.f; is[j] = active ? save_invstd[c0 + j] : 0.f;
+    sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; mu[j] = save_mean[c0 + j]; is[j] = save_invstd[c0 + j];
   }
-  const long r0 = blockIdx.x * rows_per_block;
-  const long r1 = min(r0 + rows_per_block, g.rows);
-  if (active) {
-    for (long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-      float zv[8], dv[8];
-      load8(z + r * z_ld + c0, zv);
-      load_dA(dA, dA_ld, r, c0, g, upsample, dv);
+  const long r0 = blockIdx.x * sg.rows_per_block, r1 = min(r0 + sg.rows_per_block, g.rows);
+  for (long rb = r0 + lane_r; rb < r1; rb += 4L * sg.lanes) {
+    float zv[4][8], dv[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long r = rb + (long)u * sg.lanes;
+      if (r < r1) { load8(z + r * z_ld + c0, zv[u]); load_dA(dA, dA_ld, r, c0, g, upsample, dv[u]); }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (rb + (long)u * sg.lanes >= r1) break;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float y = fmaf(zv[j], sc[j], sh[j]);
-        const float da = (leaky && y <= 0.f) ? 0.1f * dv[j] : dv[j];
+        const float y = fmaf(zv[u][j], sc[j], sh[j]);
+        const float da = (leaky && y <= 0.f) ? 0.1f * dv[u][j] : dv[u][j];
         ab[j] += da;
-        ag[j] += da * (zv[j] - mu[j]) * is[j];
+        ag[j] = fmaf(da, (zv[u][j] - mu[j]) * is[j], ag[j]);
       }
     }
   }
-  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { s_g[tid][j] = ag[j]; s_b[tid][j] = ab[j]; }
+  for (int j = 0; j < 8; ++j) { s_g[threadIdx.x][j] = ag[j]; s_b[threadIdx.x][j] = ab[j]; }
   __syncthreads();
-  if (threadIdx.y == 0 && active) {
-    for (int y = 1; y < blockDim.y; ++y) {
+  if (lane_r == 0) {
+    for (int y = 1; y < sg.lanes; ++y) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { ag[j] += s_g[y * blockDim.x + threadIdx.x][j]; ab[j] += s_b[y * blockDim.x + threadIdx.x][j]; }
+      for (int j = 0; j < 8; ++j) { ag[j] += s_g[y * sg.cv + cvi][j]; ab[j] += s_b[y * sg.cv + cvi][j]; }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) { atomicAdd(dgamma + c0 + j, ag[j]); atomicAdd(dbeta + c0 + j, ab[j]); }
@@ -175,29 +189,59 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const T* __restrict__ dA, long dA_ld, const T* __restrict__ z, long z_ld,
                     const float* __restrict__ gamma, const float* __restrict__ scale, const float* __restrict__ shift,
                     const float* __restrict__ save_mean, const float* __restrict__ save_invstd,
-                    const float* __restrict__ dgamma, const float* __restrict__ dbeta, RowGeom g, int leaky, int upsample,
-                    int dilate, T* __restrict__ dz, long dz_ld) {
-  const int cv = g.c / 8;
-  const long total = g.rows * cv;
+                    const float* __restrict__ dgamma, const float* __restrict__ dbeta, RowGeom g, StreamGeom sg,
+                    int leaky, int upsample, int dilate, T* __restrict__ dz, long dz_ld) {
+  const int cvi = threadIdx.x % sg.cv, lane_r = threadIdx.x / sg.cv;
+  const int c0 = cvi * 8;
   const float inv_m = 1.f / (float)g.rows;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const long r = i / cv;
-    const int c0 = (int)(i % cv) * 8;
-    float zv[8], dv[8], o[8];
-    load8(z + r * z_ld + c0, zv);
-    load_dA(dA, dA_ld, r, c0, g, upsample, dv);
+  // dz = k1*dact + k2*z + k3   with   k1 = gamma*invstd, k2 = -k1*invstd*dgamma/M, k3 = -k1*dbeta/M - k2*mean
+  float sc[8], sh[8], k1[8], k2[8], k3[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = c0 + j;
-      const float y = fmaf(zv[j], __ldg(scale + c), __ldg(shift + c));
-      const float da = (leaky && y <= 0.f) ? 0.1f * dv[j] : dv[j];
-      const float is = __ldg(save_invstd + c);
-      const float zh = (zv[j] - __ldg(save_mean + c)) * is;
-      o[j] = __ldg(gamma + c) * is * (da - __ldg(dbeta + c) * inv_m - zh * __ldg(dgamma + c) * inv_m);
-    }
-    const long orow = dilate ? up_row(r, g.h, g.w) : r;   // (2p, 2q) of a zero-initialised [n,2h,2w] buffer
-    store8(dz + orow * dz_ld + c0, o);
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    sc[j] = scale[c]; sh[j] = shift[c];
+    const float is = save_invstd[c];
+    k1[j] = gamma[c] * is;
+    k2[j] = -k1[j] * is * dgamma[c] * inv_m;
+    k3[j] = -k1[j] * dbeta[c] * inv_m - k2[j] * save_mean[c];
   }
+  const long r0 = blockIdx.x * sg.rows_per_block, r1 = min(r0 + sg.rows_per_block, g.rows);
+  for (long rb = r0 + lane_r; rb < r1; rb += 4L * sg.lanes) {
+    float zv[4][8], dv[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long r = rb + (long)u * sg.lanes;
+      if (r < r1) { load8(z + r * z_ld + c0, zv[u]); load_dA(dA, dA_ld, r, c0, g, upsample, dv[u]); }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long r = rb + (long)u * sg.lanes;
+      if (r >= r1) break;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float y = fmaf(zv[u][j], sc[j], sh[j]);
+        const float da = (leaky && y <= 0.f) ? 0.1f * dv[u][j] : dv[u][j];
+        o[j] = fmaf(k1[j], da, fmaf(k2[j], zv[u][j], k3[j]));
+      }
+      const long orow = dilate ? up_row(r, g.h, g.w) : r;   // (2p, 2q) of a zero-initialised [n,2h,2w] buffer
+      store8(dz + orow * dz_ld + c0, o);
+    }
+  }
+}
+
+static StreamGeom stream_geom(long rows, int c, int* grid) {
+  StreamGeom sg;
+  sg.cv = c / 8;
+  sg.lanes = 256 / sg.cv;
+  if (sg.lanes < 1) sg.lanes = 1;
+  long blocks = (long)num_sms() * 4;
+  long rpb = (rows + blocks - 1) / blocks;
+  const long unit = 4L * sg.lanes;
+  rpb = (rpb + unit - 1) / unit * unit;
+  sg.rows_per_block = rpb;
+  *grid = (int)((rows + rpb - 1) / rpb);
+  return sg;
 }
 
 template <typename T>
@@ -234,7 +278,7 @@ static int grid1d(long total) {
 using namespace yb;
 
 #define YB_BN_COMMON_CHECK(name)                                                                         \
-  YB_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, name ": bad shape (c must be a multiple of 8)"); \
+  YB_REQUIRE(n > 0 && h > 0 && w > 0 && c >= 8 && c <= 2048 && (c & (c - 1)) == 0, name ": channels must be a power of two in [8, 2048]"); \
   YB_REQUIRE(dtype == YB_F16 || dtype == YB_BF16, name ": dtype must be f16 or bf16");
 
 extern "C" int yb_bn_finalize(const float* sum, const float* sqsum, long count, int c, const float* gamma,
@@ -256,14 +300,15 @@ extern "C" int yb_bn_act_apply(const void* z, long z_ld, const float* scale, con
   YB_REQUIRE(z && scale && shift && out, "bn_act_apply: null pointer");
   RowGeom g{(long)n * h * w, h, w, c};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int grid = grid1d(g.rows * (c / 8));
+  int grid;
+  const StreamGeom sg = stream_geom(g.rows, c, &grid);
   if (dtype == YB_F16)
     bn_act_apply_kernel<__half><<<grid, 256, 0, st>>>((const __half*)z, z_ld, scale, shift, (const __half*)res, res_ld,
-                                                     (__half*)out, out_ld, g, leaky, upsample2x);
+                                                     (__half*)out, out_ld, g, sg, leaky, upsample2x);
   else
     bn_act_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)z, z_ld, scale, shift,
                                                             (const __nv_bfloat16*)res, res_ld, (__nv_bfloat16*)out,
-                                                            out_ld, g, leaky, upsample2x);
+                                                            out_ld, g, sg, leaky, upsample2x);
   YB_CUDA(cudaGetLastError());
   return YB_OK;
 }
@@ -276,23 +321,17 @@ extern "C" int yb_bn_bwd_reduce(const void* dA, long dA_ld, const void* z, long 
   YB_REQUIRE(dA && z && scale && shift && save_mean && save_invstd && dgamma && dbeta, "bn_bwd_reduce: null pointer");
   RowGeom g{(long)n * h * w, h, w, c};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int cx = c / 8 < 32 ? c / 8 : 32;
-  dim3 block(cx, 256 / cx);
-  const int gy = ceil_div(c / 8, cx);
-  long slabs = (long)num_sms() * 8 / gy;
-  if (slabs < 1) slabs = 1;
-  long rpb = (g.rows + slabs - 1) / slabs;
-  if (rpb < (long)block.y * 4) rpb = (long)block.y * 4;
-  dim3 grid(ceil_div(g.rows, rpb), gy);
+  int grid;
+  const StreamGeom sg = stream_geom(g.rows, c, &grid);
   YB_CUDA(cudaMemsetAsync(dgamma, 0, c * 4, st));
   YB_CUDA(cudaMemsetAsync(dbeta, 0, c * 4, st));
   if (dtype == YB_F16)
-    bn_bwd_reduce_kernel<__half><<<grid, block, 0, st>>>((const __half*)dA, dA_ld, (const __half*)z, z_ld, scale, shift,
-                                                        save_mean, save_invstd, g, leaky, upsample2x, rpb, dgamma, dbeta);
+    bn_bwd_reduce_kernel<__half><<<grid, 256, 0, st>>>((const __half*)dA, dA_ld, (const __half*)z, z_ld, scale, shift,
+                                                      save_mean, save_invstd, g, sg, leaky, upsample2x, dgamma, dbeta);
   else
-    bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)dA, dA_ld, (const __nv_bfloat16*)z,
-                                                               z_ld, scale, shift, save_mean, save_invstd, g, leaky,
-                                                               upsample2x, rpb, dgamma, dbeta);
+    bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dA, dA_ld, (const __nv_bfloat16*)z,
+                                                             z_ld, scale, shift, save_mean, save_invstd, g, sg, leaky,
+                                                             upsample2x, dgamma, dbeta);
   YB_CUDA(cudaGetLastError());
   return YB_OK;
 }
@@ -307,16 +346,17 @@ extern "C" int yb_bn_bwd_apply(const void* dA, long dA_ld, const void* z, long z
              "bn_bwd_apply: null pointer");
   RowGeom g{(long)n * h * w, h, w, c};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int grid = grid1d(g.rows * (c / 8));
+  int grid;
+  const StreamGeom sg = stream_geom(g.rows, c, &grid);
   if (dtype == YB_F16)
     bn_bwd_apply_kernel<__half><<<grid, 256, 0, st>>>((const __half*)dA, dA_ld, (const __half*)z, z_ld, gamma, scale,
-                                                     shift, save_mean, save_invstd, dgamma, dbeta, g, leaky,
+                                                     shift, save_mean, save_invstd, dgamma, dbeta, g, sg, leaky,
                                                      upsample2x, dilate2x, (__half*)dz, dz_ld);
   else
     bn_bwd_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dA, dA_ld, (const __nv_bfloat16*)z,
                                                             z_ld, gamma, scale, shift, save_mean, save_invstd, dgamma,
-                                                            dbeta, g, leaky, upsample2x, dilate2x, (__nv_bfloat16*)dz,
-                                                            dz_ld);
+                                                            dbeta, g, sg, leaky, upsample2x, dilate2x,
+                                                            (__nv_bfloat16*)dz, dz_ld);
   YB_CUDA(cudaGetLastError());
   return YB_OK;
 }

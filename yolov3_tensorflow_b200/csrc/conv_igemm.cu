@@ -43,17 +43,39 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BN;  // power of two >= 32 for BN in {64,128,256}
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4 * STAGE_FLOATS * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4 * STAGE_FLOATS * 4 + 2 * BN * 4;
   static constexpr uint32_t SWIZZLE = (BK == 64) ? 2u : 4u;   // UMMA layout_type: 128B / 64B
   static constexpr uint32_t SBO = 8 * BK * 2;                  // bytes between 8-row groups
 };
+
+// tile index -> (m tile, n tile).  Inference walks n fastest (the A tile stays hot in L2 across its n tiles);
+// with BN statistics on, m runs fastest so a CTA's tiles share their n tile and its per-CTA column sums are
+// flushed to global at most num_n_tiles times.
+__device__ __forceinline__ void tile_coords(const ConvParams& p, int tile, int& m_idx, int& n_idx) {
+  if (p.stat_sum != nullptr) { n_idx = tile / p.num_m_tiles; m_idx = tile - n_idx * p.num_m_tiles; }
+  else { m_idx = tile / p.num_n_tiles; n_idx = tile - m_idx * p.num_n_tiles; }
+}
+// executed by the 128 epilogue threads together (named barrier 1)
+template <int BN>
+__device__ __forceinline__ void stat_flush(const ConvParams& p, float* s_stat, int n0, int et /*0..127*/) {
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  for (int c = et; c < BN; c += 128) {
+    if (n0 + c < p.cout) {
+      atomicAdd(p.stat_sum + n0 + c, s_stat[c]);
+      atomicAdd(p.stat_sqsum + n0 + c, s_stat[BN + c]);
+    }
+    s_stat[c] = 0.f;
+    s_stat[BN + c] = 0.f;
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+}
 
 // One epilogue pass of a warp over its 32 accumulator rows x BN columns:
 // TMEM -> registers -> scale/shift (+leaky) (+residual) -> 16-bit / fp32 global stores
 // (channel-slice and 2x-upsample aware), optional BN batch statistics.
 template <typename T, int BN>
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const int row, const int n0, const uint32_t t_row,
-                                              const int lane, float* stage) {
+                                              const int lane, float* stage, float* s_stat) {
   const bool row_ok = row < p.M;
   // output row(s)
   long orow[4];
@@ -77,21 +99,22 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const int row
     tmem_ld_wait();
     const int col0 = n0 + ch * 32;
     if (p.stat_sum != nullptr) {
-      // BN batch statistics of the raw conv output: reduce the warp's 32 rows per column
+      // BN batch statistics of the raw conv output.  Transpose the warp's 32x32 block through its staging
+      // tile so each lane sums ONE column over the 32 rows, then accumulate per-CTA column sums in shared
+      // memory; they are flushed to global once per (CTA, n-tile) by the caller (global atomics contend badly).
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float v = row_ok ? __uint_as_float(r[j]) : 0.f;
-        float s = v, s2 = v * v;
+      for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = row_ok ? __uint_as_float(r[j]) : 0.f;
+      __syncwarp();
+      float cs = 0.f, cs2 = 0.f;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          s += __shfl_xor_sync(0xffffffffu, s, o);
-          s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-        }
-        if (lane == j && col0 + j < p.cout) {
-          atomicAdd(p.stat_sum + col0 + j, s);
-          atomicAdd(p.stat_sqsum + col0 + j, s2);
-        }
+      for (int rr = 0; rr < 32; ++rr) {
+        const float t = stage[rr * 33 + lane];
+        cs += t;
+        cs2 = fmaf(t, t, cs2);
       }
+      __syncwarp();
+      atomicAdd(&s_stat[ch * 32 + lane], cs);
+      atomicAdd(&s_stat[BN + ch * 32 + lane], cs2);
     }
     if (row_ok) {
       float v[32];
@@ -184,6 +207,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tempty_bar = bars + 2 * C::STAGES + 2; // [2] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
   float* stage_base = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
+  float* s_stat = stage_base + 4 * STAGE_FLOATS;   // [2][BN] per-CTA column sums / sums of squares
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -215,8 +239,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / p.num_n_tiles) * BLOCK_M;
-      const int n0 = (tile % p.num_n_tiles) * BN;
+      int m_idx, n_idx;
+      tile_coords(p, tile, m_idx, n_idx);
+      const int m0 = m_idx * BLOCK_M;
+      const int n0 = n_idx * BN;
       // first output pixel of the tile -> (image, row, col); base input pixel of the 3x3 window
       const int q = m0 % p.Q;
       const int pp = (m0 / p.Q) % p.P;
@@ -276,20 +302,33 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are this warp's
+    const int et = threadIdx.x - 64;
+    int cur_n0 = -1;
+    if (p.stat_sum != nullptr) {
+      for (int c = et; c < 2 * BN; c += 128) s_stat[c] = 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m0 = (tile / p.num_n_tiles) * BLOCK_M;
-      const int n0 = (tile % p.num_n_tiles) * BN;
+      int m_idx, n_idx;
+      tile_coords(p, tile, m_idx, n_idx);
+      const int m0 = m_idx * BLOCK_M;
+      const int n0 = n_idx * BN;
+      if (p.stat_sum != nullptr && n0 != cur_n0) {
+        if (cur_n0 >= 0) stat_flush<BN>(p, s_stat, cur_n0, et);
+        cur_n0 = n0;
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_fence_after();
       epilogue_tile<T, BN>(p, m0 + quarter * 32 + lane, n0, tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN, lane,
-                           stage_base + (warp - 2) * STAGE_FLOATS);
+                           stage_base + (warp - 2) * STAGE_FLOATS, s_stat);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
+    if (p.stat_sum != nullptr && cur_n0 >= 0) stat_flush<BN>(p, s_stat, cur_n0, et);
   }
 
   tcgen05_fence_before();
@@ -315,7 +354,7 @@ struct Cfg2 {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 4 * STAGE_FLOATS * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 4 * STAGE_FLOATS * 4 + 2 * BN * 4;
   static constexpr uint32_t SWIZZLE = (BK == 64) ? 2u : 4u;
   static constexpr uint32_t SBO = 8 * BK * 2;
 };
@@ -336,6 +375,7 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   uint64_t* tempty_bar = bars + 2 * C::STAGES + 2;  // [2] used in the leader only (8 arrivals: 4 warps x 2 CTAs)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
   float* stage_base = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
+  float* s_stat = stage_base + 4 * STAGE_FLOATS;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -371,8 +411,10 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int m0 = (tile / p.num_n_tiles) * (2 * BLOCK_M) + (int)rank * BLOCK_M;   // this CTA's 128 rows
-      const int n0 = (tile % p.num_n_tiles) * BN + (int)rank * (BN / 2);             // this CTA's half of B
+      int m_idx, n_idx;
+      tile_coords(p, tile, m_idx, n_idx);
+      const int m0 = m_idx * (2 * BLOCK_M) + (int)rank * BLOCK_M;   // this CTA's 128 rows
+      const int n0 = n_idx * BN + (int)rank * (BN / 2);             // this CTA's half of B
       const int q = m0 % p.Q;
       const int pp = (m0 / p.Q) % p.P;
       const int img = m0 / (p.Q * p.P);
@@ -433,20 +475,33 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   } else {
     // ===================== epilogue (warps 2..5, both CTAs) =====================
     const int quarter = warp & 3;
+    const int et = threadIdx.x - 64;
+    int cur_n0 = -1;
+    if (p.stat_sum != nullptr) {
+      for (int c = et; c < 2 * BN; c += 128) s_stat[c] = 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     int it = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m0 = (tile / p.num_n_tiles) * (2 * BLOCK_M) + (int)rank * BLOCK_M;
-      const int n0 = (tile % p.num_n_tiles) * BN;
+      int m_idx, n_idx;
+      tile_coords(p, tile, m_idx, n_idx);
+      const int m0 = m_idx * (2 * BLOCK_M) + (int)rank * BLOCK_M;
+      const int n0 = n_idx * BN;
+      if (p.stat_sum != nullptr && n0 != cur_n0) {
+        if (cur_n0 >= 0) stat_flush<BN>(p, s_stat, cur_n0, et);
+        cur_n0 = n0;
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_fence_after();
       epilogue_tile<T, BN>(p, m0 + quarter * 32 + lane, n0, tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN, lane,
-                           stage_base + (warp - 2) * STAGE_FLOATS);
+                           stage_base + (warp - 2) * STAGE_FLOATS, s_stat);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);    // the leader's MMA warp waits for both CTAs
     }
+    if (p.stat_sum != nullptr && cur_n0 >= 0) stat_flush<BN>(p, s_stat, cur_n0, et);
   }
 
   tcgen05_fence_before();

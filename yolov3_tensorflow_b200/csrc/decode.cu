@@ -23,29 +23,27 @@ struct DecodeParams {
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// one WARP per box: the 5+C logits of a box are contiguous (coalesced 128-byte reads), the box logits are
+// broadcast by shuffle, and probs / scores rows are written coalesced.  confs / probs / scores are optional
+// (the detection pipeline needs only boxes + scores).
 __global__ void __launch_bounds__(256) predict_kernel(const DecodeParams p) {
-  const long total = (long)p.n * p.B * p.E;
-  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-    const int j = (int)(e % p.E);
-    const long gb = e / p.E;
+  const int lane = threadIdx.x & 31;
+  const long nbox = (long)p.n * p.B;
+  for (long gb = (long)blockIdx.x * 8 + (threadIdx.x >> 5); gb < nbox; gb += (long)gridDim.x * 8) {
     const int img = (int)(gb / p.B);
-    const int b = (int)(gb % p.B);
+    const int b = (int)(gb - (long)img * p.B);
     const int s = b < p.box_off[1] ? 0 : (b < p.box_off[2] ? 1 : 2);
     const int lb = b - p.box_off[s];
     const int per_img = p.box_off[s + 1] - p.box_off[s];
     const float* row = p.fm[s] + ((long)img * per_img + lb) * p.E;
-    if (j >= 5) {
-      const float pr = sigmoidf_(row[j]);
-      p.probs[gb * p.C + (j - 5)] = pr;                                   // model.py:168
-      if (p.scores) p.scores[gb * p.C + (j - 5)] = __fmul_rn(sigmoidf_(row[4]), pr);  // test_single_image.py:55
-    } else if (j == 4) {
-      p.confs[gb] = sigmoidf_(row[4]);                                    // model.py:167
-    } else {
+    const float head = lane < 5 ? row[lane] : 0.f;
+    const float conf = sigmoidf_(__shfl_sync(0xffffffffu, head, 4));
+    if (lane < 4) {
       const int a = lb % 3;
       const int cell = lb / 3;
-      const int axis = j & 1;  // 0: x / width, 1: y / height
-      const float t_c = row[axis];
-      const float t_s = row[2 + axis];
+      const int axis = lane & 1;  // 0: x / width, 1: y / height
+      const float t_c = __shfl_sync(0xfu, head, axis);
+      const float t_s = __shfl_sync(0xfu, head, 2 + axis);
       const float off = axis == 0 ? (float)(cell % p.gw[s]) : (float)(cell / p.gw[s]);
       const float ratio = axis == 0 ? p.ratio_w[s] : p.ratio_h[s];
       const int ai = (2 - s) * 3 + a;                                     // anchor groups 6:9, 3:6, 0:3
@@ -53,7 +51,13 @@ __global__ void __launch_bounds__(256) predict_kernel(const DecodeParams p) {
       const float center = __fmul_rn(__fadd_rn(sigmoidf_(t_c), off), ratio);          // model.py:118-120
       const float size = __fmul_rn(__fmul_rn(expf(t_s), __fdiv_rn(anc, ratio)), ratio);  // :94,:123-126
       const float half = __fmul_rn(size, 0.5f);
-      p.boxes[gb * 4 + j] = j < 2 ? __fsub_rn(center, half) : __fadd_rn(center, half);  // :182-188
+      p.boxes[gb * 4 + lane] = lane < 2 ? __fsub_rn(center, half) : __fadd_rn(center, half);  // :182-188
+    }
+    if (lane == 0 && p.confs) p.confs[gb] = conf;                          // model.py:167
+    for (int k = lane; k < p.C; k += 32) {
+      const float pr = sigmoidf_(row[5 + k]);
+      if (p.probs) p.probs[gb * p.C + k] = pr;                             // model.py:168
+      if (p.scores) p.scores[gb * p.C + k] = __fmul_rn(conf, pr);          // test_single_image.py:55
     }
   }
 }
@@ -110,7 +114,7 @@ using namespace yb;
 extern "C" int yb_predict(const float* fm1, const float* fm2, const float* fm3, int n, int img_h, int img_w,
                           int class_num, const float* anchors9x2, float* boxes, float* confs, float* probs,
                           float* scores, void* stream) {
-  YB_REQUIRE(fm1 && fm2 && fm3 && anchors9x2 && boxes && confs && probs, "predict: null pointer");
+  YB_REQUIRE(fm1 && fm2 && fm3 && anchors9x2 && boxes, "predict: null pointer");
   YB_REQUIRE(n > 0 && class_num > 0, "predict: bad n/class_num");
   YB_REQUIRE(img_h % 32 == 0 && img_w % 32 == 0 && img_h > 0 && img_w > 0,
              "predict: image size must be a multiple of 32 (got %dx%d)", img_h, img_w);
@@ -128,8 +132,10 @@ extern "C" int yb_predict(const float* fm1, const float* fm2, const float* fm3, 
   for (int i = 0; i < 9; ++i) { p.anchor_w[i] = anchors9x2[2 * i]; p.anchor_h[i] = anchors9x2[2 * i + 1]; }
   p.n = n; p.C = class_num; p.E = 5 + class_num; p.B = p.box_off[3];
   p.boxes = boxes; p.confs = confs; p.probs = probs; p.scores = scores;
-  const long total = (long)n * p.B * p.E;
-  predict_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  long blocks = ((long)n * p.B + 7) / 8;
+  const long capb = (long)num_sms() * 32;
+  if (blocks > capb) blocks = capb;
+  predict_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   YB_CUDA(cudaGetLastError());
   return YB_OK;
 }

@@ -321,6 +321,22 @@ class yolov3(object):
             return boxes, confs, probs, scores
         return boxes, confs, probs
 
+    def predict_scores(self, feature_maps):
+        """Detection-pipeline variant of predict(): only what gpu_nms consumes — boxes [N,B,4] and
+        scores = confs*probs [N,B,C] (test_single_image.py:53-55 fused into one pass, nothing else written)."""
+        if self.img_size is None:
+            raise _lib.YoloB200Error("predict_scores: call forward() first (it records img_size, model.py:33)")
+        fms = [_as_cuda_f32(f, self.device) for f in feature_maps]
+        n = fms[0].shape[0]
+        h, w = self.img_size
+        C_ = self.class_num
+        B = 3 * sum((h // s) * (w // s) for s in (32, 16, 8))
+        boxes = torch.empty((n, B, 4), dtype=torch.float32, device=self.device)
+        scores = torch.empty((n, B, C_), dtype=torch.float32, device=self.device)
+        check(lib.yb_predict(ptr(fms[0]), ptr(fms[1]), ptr(fms[2]), n, h, w, C_, _lib.fptr(self.anchors.reshape(-1)),
+                             ptr(boxes), None, None, ptr(scores), stream_handle()), "yb_predict")
+        return boxes, scores
+
     # ------------------------------------------------------------------ model.py:192-304
     def _loss_scale(self, feature_map_i, y_true, anchors, loss4, want_grad=False, grad_out=None):
         fm = _as_cuda_f32(feature_map_i, self.device)
