@@ -226,15 +226,41 @@ def main():
         boxes, scores = model.predict_scores(fms)
         return batched_nms_raw(boxes, scores, CLASS_NUM, **NMS_ARGS)
 
-    def step_e2e():
-        xd = x_host.to("cuda", non_blocking=True)                              # H2D, every step
-        fms = model.forward(xd)
+    # End-to-end pipeline through the public API: pinned host images -> H2D on a copy stream (double buffered,
+    # overlapping the previous batch's compute) -> forward/predict/nms -> D2H of the detections into pinned host
+    # buffers.  Every step's H2D copy and D2H read happen inside the timed region.
+    copy_stream = torch.cuda.Stream()
+    x_bufs = [torch.empty_like(x_dev) for _ in range(2)]
+    h2d_done = [torch.cuda.Event() for _ in range(2)]
+    buf_free = [torch.cuda.Event() for _ in range(2)]
+    cap = CLASS_NUM * NMS_ARGS["max_boxes"]
+    h_counts = torch.empty((B,), dtype=torch.int32).pin_memory()
+    h_boxes = torch.empty((B, cap, 4), dtype=torch.float32).pin_memory()
+    h_scores = torch.empty((B, cap), dtype=torch.float32).pin_memory()
+    h_labels = torch.empty((B, cap), dtype=torch.int32).pin_memory()
+
+    def e2e_prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(buf_free[i % 2])
+            x_bufs[i % 2].copy_(x_host, non_blocking=True)                     # H2D, every step
+            h2d_done[i % 2].record(copy_stream)
+
+    def step_e2e(i):
+        e2e_prefetch(i + 1)                                                    # next batch's copy overlaps this compute
+        cur = torch.cuda.current_stream()
+        cur.wait_event(h2d_done[i % 2])
+        fms = model.forward(x_bufs[i % 2])
+        buf_free[i % 2].record(cur)
         boxes, scores = model.predict_scores(fms)
         ob, os_, ol, oi, cnt = batched_nms_raw(boxes, scores, CLASS_NUM, **NMS_ARGS)
-        counts = cnt.cpu()                                                     # D2H (sync): K per image
-        kmax = max(int(counts.max()), 1)
-        res = (ob[:, :kmax].cpu(), os_[:, :kmax].cpu(), ol[:, :kmax].cpu())    # D2H: detections
-        return counts, res, kmax
+        h_counts.copy_(cnt, non_blocking=True)
+        torch.cuda.current_stream().synchronize()                              # D2H (sync): K per image
+        kmax = max(int(h_counts.max()), 1)
+        h_boxes[:, :kmax].copy_(ob[:, :kmax], non_blocking=True)               # D2H: detections
+        h_scores[:, :kmax].copy_(os_[:, :kmax], non_blocking=True)
+        h_labels[:, :kmax].copy_(ol[:, :kmax], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return h_counts, kmax
 
     def barrier():
         if world > 1:
@@ -265,15 +291,18 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     # ---------------- timed: end to end (host -> host) ----------------
-    for _ in range(2):
-        step_e2e()
+    for ev in buf_free:
+        ev.record()
+    e2e_prefetch(0)
+    for i in range(2):
+        step_e2e(i)
     barrier()
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     d2h = 0
-    for _ in range(args.steps):
-        counts, res, kmax = step_e2e()
-        d2h = counts.numel() * 4 + sum(r.numel() * r.element_size() for r in res)
+    for i in range(2, 2 + args.steps):
+        counts, kmax = step_e2e(i)
+        d2h = counts.numel() * 4 + B * kmax * (16 + 4 + 4)
     t1.record()
     barrier()
     ms2 = torch.tensor([t0.elapsed_time(t1)], device="cuda")
