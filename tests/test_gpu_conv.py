@@ -12,11 +12,13 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["1cta", "2cta"], autouse=True)
+@pytest.fixture(params=["1cta", "2cta", "mc"], autouse=True)
 def conv_mode(request, monkeypatch):
-    """Every conv test runs against both tcgen05 kernels: cta_group::1 (128-row tiles) and
-    cta_group::2 (a CTA pair per 256-row tile).  YB_CONV_MODE overrides the size heuristic."""
-    monkeypatch.setenv("YB_CONV_MODE", request.param)
+    """Every conv test runs against the three tcgen05 kernels: cta_group::1 (128-row tiles), cta_group::2 (a CTA
+    pair per 256-row tile) and the cluster-multicast pair kernel (2x2 / 2x1 pairs; only 256-wide tiles take it,
+    the other shapes fall back to the plain pair kernel).  YB_CONV_MODE / YB_CONV_MC override the heuristics."""
+    monkeypatch.setenv("YB_CONV_MODE", "2cta" if request.param == "mc" else request.param)
+    monkeypatch.setenv("YB_CONV_MC", "1" if request.param == "mc" else "0")
     return request.param
 
 
@@ -156,6 +158,18 @@ def test_conv3x3_bf16_and_stats():
 
 def test_conv3x3_tiny_tensor_under_128k():
     _run_conv(1, 4, 4, 64, 64, 3, 1)              # exercises the small-tensor im2col descriptor workaround
+
+
+def test_conv3x3_wide_odd_mtiles_residual():
+    _run_conv(3, 16, 16, 128, 512, 3, 1, residual=True)      # M=768: 3 m-tiles (odd: a pair of the 2x2 cluster idles), 2 n-tiles
+
+
+def test_conv3x3_s2_wide():
+    _run_conv(2, 52, 52, 128, 256, 3, 2)                     # 1 n-tile -> 2x1 cluster (B multicast only)
+
+
+def test_conv1x1_wide_1024_bf16_stats():
+    _run_conv(4, 13, 13, 512, 1024, 1, 1, dtype=torch.bfloat16, stats=True)   # 4 n-tiles, statistics epilogue
 
 
 def test_conv_rejects_bad_arguments():

@@ -252,6 +252,33 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
       "h"((uint16_t)3)
       : "memory");
 }
+// ---- cluster multicast variants (cta_group::2 + .multicast::cluster): the box lands at the same smem offset in
+// ---- every CTA of `mask`, and each destination's bytes are credited to ITS pair leader's barrier
+__device__ __forceinline__ void tma_load_2d_2sm_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                   uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "h"(mask), "r"(c0),
+      "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d_2sm_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c, int w,
+                                                          int h, int n, uint16_t ow, uint16_t oh, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5, %6, %7}], [%2], {%8, %9}, %3;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "h"(mask), "r"(c),
+      "r"(w), "r"(h), "r"(n), "h"(ow), "h"(oh)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm_mask(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
 // arrive on the barrier at the same offset in CTA `cta` of the cluster
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
   asm volatile(

@@ -514,6 +514,182 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 }
 
 // ----------------------------------------------------------------------------------
+// Cluster-multicast variant of the pair kernel, BN = 256: a cluster of CM x CN CTA pairs computes a
+// (CM*256) x (CN*256) super-tile.  The A tile of an m-tile is needed by the CN pairs of its row, the B tile of an
+// n-tile by the CM pairs of its column: each CTA fetches only 1/CN of its A rows and 1/CM of its B rows and the
+// TMA multicasts the box to the CTAs that share it, so the L2 -> shared-memory fill per FLOP drops by another
+// (1/CN + 1/CM)/2 (2x2: half of the pair kernel, a quarter of the 1-CTA kernel).
+// ----------------------------------------------------------------------------------
+template <typename T, int BK, int CM, int CN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_igemm_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const ConvParams p) {
+  constexpr int BN = 256;
+  constexpr int CSIZE = 2 * CM * CN;
+  using C = Cfg2<BN, BK>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + C::STAGES * C::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;                        // [STAGES] used in the leader only
+  uint64_t* empty_bar = bars + C::STAGES;           // [STAGES] one per CTA (multicast commit)
+  uint64_t* tfull_bar = bars + 2 * C::STAGES;       // [2] one per CTA (multicast commit)
+  uint64_t* tempty_bar = bars + 2 * C::STAGES + 2;  // [2] used in the leader only (8 arrivals: 4 warps x 2 CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+  float* stage_base = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
+  float* s_stat = stage_base + 4 * STAGE_FLOATS;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const uint32_t rank = crank & 1;                  // 0 = leader of its pair
+  const int pid = crank >> 1, pn = pid % CN, pm = pid / CN;
+  const int cluster_id = blockIdx.x / CSIZE;
+  const int num_clusters = gridDim.x / CSIZE;
+  const int SM_T = (p.num_m_tiles + CM - 1) / CM, SN_T = p.num_n_tiles / CN;   // super-tiles
+  const int num_tiles = SM_T * SN_T;
+  const int kb_per_tap = p.cin / BK;
+  const int num_kb = p.ksize * p.ksize * kb_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], CM * CN);              // every pair leader of the cluster commits to it
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm<C::TMEM_COLS>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();                               // peer barriers are initialised before any remote arrive / TMA
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    // multicast masks: A goes to the CTAs with the same (pm, rank), B to those with the same (pn, rank)
+    uint16_t maskA = 0, maskB = 0;
+#pragma unroll
+    for (int j = 0; j < CN; ++j) maskA |= (uint16_t)(1u << (((pm * CN + j) << 1) | rank));
+#pragma unroll
+    for (int j = 0; j < CM; ++j) maskB |= (uint16_t)(1u << (((j * CN + pn) << 1) | rank));
+    constexpr int A_ROWS = BLOCK_M / CN, B_ROWS = (BN / 2) / CM;   // rows this CTA fetches itself
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      int sm, sn;
+      if (p.stat_sum != nullptr) { sn = tile / SM_T; sm = tile - sn * SM_T; } else { sm = tile / SN_T; sn = tile - sm * SN_T; }
+      const int m_idx = sm * CM + pm, n_idx = sn * CN + pn;
+      const int m0 = m_idx * (2 * BLOCK_M) + (int)rank * BLOCK_M + pn * A_ROWS;   // first A row this CTA fetches
+      const int n0 = n_idx * BN + (int)rank * (BN / 2) + pm * B_ROWS;             // first B row this CTA fetches
+      const int q = m0 % p.Q;
+      const int pp = (m0 / p.Q) % p.P;
+      const int img = m0 / (p.Q * p.P);
+      const int w_base = q * p.stride - p.pad;
+      const int h_base = pp * p.stride - p.pad;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int tap = kb / kb_per_tap;
+        const int c0 = (kb - tap * kb_per_tap) * BK;
+        if (lane == 0) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);   // both CTAs' bytes
+          uint8_t* adst = sA + stage * C::A_BYTES + pn * A_ROWS * (BK * 2);
+          uint8_t* bdst = sB + stage * C::B_BYTES + pm * B_ROWS * (BK * 2);
+          if (p.im2col) {
+            tma_load_im2col_4d_2sm_mc(adst, &tmA, &full_bar[stage], c0, w_base, h_base, img, (uint16_t)(tap % p.ksize),
+                                      (uint16_t)(tap / p.ksize), maskA);
+          } else {
+            tma_load_2d_2sm_mc(adst, &tmA, &full_bar[stage], c0, m0, maskA);
+          }
+          tma_load_2d_2sm_mc(bdst, &tmB, &full_bar[stage], tap * p.cin + c0, n0, maskB);
+        }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(2 * BLOCK_M, BN, std::is_same<T, __nv_bfloat16>::value);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        if (lane == 0) mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        __syncwarp();
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          if (lane == 0) {
+            mbar_wait(&full_bar[stage], phase);
+            tcgen05_fence_after();
+            const uint32_t a_addr = smem_u32(sA + stage * C::A_BYTES);
+            const uint32_t b_addr = smem_u32(sB + stage * C::B_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t adesc = make_kmajor_desc(a_addr + k * UMMA_K * 2, C::SBO, C::SWIZZLE);
+              const uint64_t bdesc = make_kmajor_desc(b_addr + k * UMMA_K * 2, C::SBO, C::SWIZZLE);
+              umma_f16_2sm(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+            }
+            umma_commit_2sm_mask(&empty_bar[stage], (uint16_t)((1u << CSIZE) - 1));     // one of CM*CN arrivals, in every CTA
+            if (kb == num_kb - 1) umma_commit_2sm_mask(&tfull_bar[acc], (uint16_t)(3u << (pid << 1)));   // own pair
+          }
+          __syncwarp();
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5, both CTAs) =====================
+    const int quarter = warp & 3;
+    const int et = threadIdx.x - 64;
+    int cur_n0 = -1;
+    if (p.stat_sum != nullptr) {
+      for (int c = et; c < 2 * BN; c += 128) s_stat[c] = 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    int it = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      int sm, sn;
+      if (p.stat_sum != nullptr) { sn = tile / SM_T; sm = tile - sn * SM_T; } else { sm = tile / SN_T; sn = tile - sm * SN_T; }
+      const int m0 = (sm * CM + pm) * (2 * BLOCK_M) + (int)rank * BLOCK_M;
+      const int n0 = (sn * CN + pn) * BN;
+      if (p.stat_sum != nullptr && n0 != cur_n0) {
+        if (cur_n0 >= 0) stat_flush<BN>(p, s_stat, cur_n0, et);
+        cur_n0 = n0;
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      epilogue_tile<T, BN>(p, m0 + quarter * 32 + lane, n0, tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN, lane,
+                           stage_base + (warp - 2) * STAGE_FLOATS, s_stat);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], crank & ~1u);   // this pair's leader
+    }
+    if (p.stat_sum != nullptr && cur_n0 >= 0) stat_flush<BN>(p, s_stat, cur_n0, et);
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();                               // nobody exits while the peer may still signal / read its smem
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc_2sm<C::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ----------------------------------------------------------------------------------
 // host: tensor maps (driver entry points fetched at run time: no link-time libcuda)
 // ----------------------------------------------------------------------------------
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode_tiled = nullptr;
@@ -639,6 +815,36 @@ static int launch_cfg2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
   return YB_OK;
 }
 
+template <typename T, int BK, int CM, int CN>
+static int launch_mc(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t st) {
+  using C = Cfg2<256, BK>;
+  constexpr int CSIZE = 2 * CM * CN;
+  static int max_clusters = -1;
+  auto kern = conv_igemm_mc_kernel<T, BK, CM, CN>;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CSIZE; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (max_clusters < 0) {
+    YB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    cfg.gridDim = dim3(CSIZE * (num_sms() / CSIZE));
+    int nc = 0;
+    YB_CUDA(cudaOccupancyMaxActiveClusters(&nc, kern, &cfg));
+    max_clusters = nc > 0 ? nc : 1;
+  }
+  const int super_tiles = ((p.num_m_tiles + CM - 1) / CM) * (p.num_n_tiles / CN);
+  const int clusters = super_tiles < max_clusters ? super_tiles : max_clusters;
+  cfg.gridDim = dim3(CSIZE * clusters);
+  YB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+  return YB_OK;
+}
+
 int conv_block_k(int cin) { return (cin % 64 == 0) ? 64 : 32; }
 // 1-CTA tile width
 int conv_block_n(int cout_pad) { return (cout_pad % 128 == 0) ? 128 : 64; }
@@ -649,6 +855,16 @@ int conv_block_n2(int cout_pad) { return (cout_pad % 256 == 0) ? 256 : ((cout_pa
 int conv_launch(int dtype, int cout_pad, const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p,
                 cudaStream_t st) {
   const int bk = conv_block_k(p.cin);
+  if (p.two_cta && p.mc_m * p.mc_n > 1) {
+#define YB_DISPATCH_MC(T)                                                                  \
+  if (bk == 64 && p.mc_m == 2 && p.mc_n == 2) return launch_mc<T, 64, 2, 2>(tmA, tmB, p, st); \
+  if (bk == 64 && p.mc_m == 2 && p.mc_n == 1) return launch_mc<T, 64, 2, 1>(tmA, tmB, p, st);
+    if (dtype == YB_F16) { YB_DISPATCH_MC(__half) }
+    else if (dtype == YB_BF16) { YB_DISPATCH_MC(__nv_bfloat16) }
+#undef YB_DISPATCH_MC
+    set_error("conv_launch: unsupported multicast configuration");
+    return YB_ERR_UNSUPPORTED;
+  }
   if (p.two_cta) {
     const int bn = conv_block_n2(cout_pad);
 #define YB_DISPATCH2(T)                                                         \
@@ -712,6 +928,15 @@ int conv_prepare(const yb_conv_desc* d, const void* x, const void* w_packed, con
   if (force && force[0] == '1') two = false;
   if (force && force[0] == '2') two = true;
   p->two_cta = two ? 1 : 0;
+  // cluster multicast on top of the pair kernel: 2x2 pairs when there are >= 2 n-tiles, 2x1 (share B) otherwise
+  int mc_m = 1, mc_n = 1;
+  const char* mcf = getenv("YB_CONV_MC");       // "0": off, "1": force on where legal (testing)
+  if (two && bk == 64 && cout_pad % 256 == 0 && !(mcf && mcf[0] == '0')) {
+    const int mt = ceil_div(p->M, 2 * BLOCK_M), nt = cout_pad / 256;
+    const bool big = (long)mt * nt >= 64 || (mcf && mcf[0] == '1');
+    if (big && mt >= 2) { mc_m = 2; mc_n = (nt % 2 == 0) ? 2 : 1; }
+  }
+  p->mc_m = mc_m; p->mc_n = mc_n;
   const int bn = two ? conv_block_n2(cout_pad) : conv_block_n(cout_pad);
   p->cout = d->cout; p->cin = d->cin; p->ksize = d->ksize; p->stride = d->stride; p->pad = pad;
   p->im2col = d->ksize == 3;
@@ -723,13 +948,14 @@ int conv_prepare(const yb_conv_desc* d, const void* x, const void* w_packed, con
   p->stat_sum = stat_sum; p->stat_sqsum = stat_sqsum;
   int rc;
   if (p->im2col) {
-    rc = make_tmap_im2col(tmA, x, d->dtype, d->n, d->h, d->w, d->cin, d->in_ld, d->ksize, d->stride, pad, bk);
+    rc = make_tmap_im2col_px(tmA, x, d->dtype, d->n, d->h, d->w, d->cin, d->in_ld, d->ksize, d->stride, pad, bk,
+                             BLOCK_M / mc_n);
   } else {
-    rc = make_tmap_2d(tmA, x, d->dtype, (long)d->n * d->h * d->w, d->cin, d->in_ld, BLOCK_M, bk, 0);
+    rc = make_tmap_2d(tmA, x, d->dtype, (long)d->n * d->h * d->w, d->cin, d->in_ld, BLOCK_M / mc_n, bk, 0);
   }
   if (rc) return rc;
   rc = make_tmap_2d(tmB, w_packed, d->dtype, cout_pad, (long)d->ksize * d->ksize * d->cin,
-                    (long)d->ksize * d->ksize * d->cin, two ? bn / 2 : bn, bk, 1);
+                    (long)d->ksize * d->ksize * d->cin, (two ? bn / 2 : bn) / mc_m, bk, 1);
   if (rc) return rc;
   *cout_pad_out = cout_pad;
   return YB_OK;
