@@ -112,8 +112,8 @@ def cpu_step(O, x, params, anchors):
     scores = confs * probs
     k = 0
     for i in range(x.shape[0]):
-        r = O.gpu_nms(boxes[i:i + 1], scores[i:i + 1], CLASS_NUM, NMS_ARGS["max_boxes"], NMS_ARGS["score_thresh"],
-                      NMS_ARGS["nms_thresh"], nms_fn=O.nms_fast if hasattr(O, "nms_fast") else None)
+        r = O.gpu_nms_c(boxes[i:i + 1], scores[i:i + 1], CLASS_NUM, NMS_ARGS["max_boxes"], NMS_ARGS["score_thresh"],
+                        NMS_ARGS["nms_thresh"])     # C restatement of TF's single-threaded CPU kernel
         k += len(r[1])
     return k
 
@@ -142,6 +142,41 @@ def run_cpu(size, steps, warmup, sample_images):
     return dict(value=sample_images * steps / dt, unit="images/s", cores=cores, kind="port", cpu_model=model,
                 sample=f"{steps} passes over {sample_images} image(s) {size}x{size} (forward+decode+NMS, fp32, torch-CPU conv2d "
                        f"restatement of the TF1 graph; TensorFlow not installable in this image)"), dt / steps
+
+
+def nms_stress(pkg, with_cpu):
+    """BASELINE.json configs[4]: 100k pre-NMS boxes x 80 classes, gpu_nms(200, 0.3, 0.45); sparse (s=u1*u2, ~5% pass)
+    and dense (s~U[0,1), 70% pass) score variants.  Unit: (box, class) pairs per second = 8e6 / t."""
+    import torch
+    from tests.synth import gen_nms_boxes
+    from yolov3_tensorflow_b200.utils.nms_utils import batched_nms_raw
+    out = {}
+    for name, dense in (("sparse", False), ("dense", True)):
+        b, sc = gen_nms_boxes(5, 100000, CLASS_NUM, dense=dense)
+        bd, sd = torch.from_numpy(b[None]).cuda(), torch.from_numpy(sc[None]).cuda()
+        for _ in range(3):
+            r = batched_nms_raw(bd, sd, CLASS_NUM, **NMS_ARGS)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        iters = 10
+        e0.record()
+        for _ in range(iters):
+            r = batched_nms_raw(bd, sd, CLASS_NUM, **NMS_ARGS)
+        e1.record()
+        torch.cuda.synchronize()
+        t = e0.elapsed_time(e1) / iters * 1e-3
+        rec = {"ms": t * 1e3, "pairs_per_s": 8e6 / t, "kept": int(r[4][0]), "candidates": int((sc >= 0.3).sum()),
+               "read_gbs": 33.6e6 / t / 1e9}
+        if with_cpu:
+            from oracle import yolov3_oracle as O
+            t0 = time.perf_counter()
+            ob = O.gpu_nms_c(b[None], sc[None], CLASS_NUM, NMS_ARGS["max_boxes"], NMS_ARGS["score_thresh"], NMS_ARGS["nms_thresh"])
+            tc = time.perf_counter() - t0
+            rec["cpu_port_ms"] = tc * 1e3
+            rec["cpu_port_pairs_per_s"] = 8e6 / tc
+            rec["indices_bit_exact_vs_cpu"] = bool(np.array_equal(ob[3], r[3][0, :len(ob[3])].cpu().numpy()) and len(ob[3]) == int(r[4][0]))
+        out[name] = rec
+    return out
 
 
 def synth_y_true(rng, n, size, anchors, class_num=CLASS_NUM, max_boxes=50):
@@ -386,6 +421,8 @@ def main():
             "fraction_of_conv_flop_roofline": (value / world) * FWD_GFLOP_416 * scale * 1e9 / (pk["tflops"] * 1e12)}
     if train is not None:
         line["train"] = train
+    if world == 1:
+        line["nms_stress"] = nms_stress(pkg, with_cpu=not args.no_cpu_baseline)
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = run_cpu(S, 2, 1, sample_images=2)
         line["cpu_baseline"] = cb

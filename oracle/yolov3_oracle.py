@@ -403,6 +403,40 @@ def gpu_nms(boxes, scores, num_classes, max_boxes=50, score_thresh=0.5, nms_thre
             np.concatenate(ll, 0), np.concatenate(il, 0))
 
 
+# ---- C restatement of the same NMS (oracle/nms_tf_cpu.c; built by `make -C oracle`) ----
+_NMS_C = None
+
+
+def _nms_c():
+    global _NMS_C
+    if _NMS_C is None:
+        import ctypes, os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libnms_oracle.so")
+        if not os.path.exists(path):
+            import subprocess
+            subprocess.run(["make", "-C", os.path.dirname(path)], check=True, capture_output=True)
+        lib = ctypes.CDLL(path)
+        lib.yo_gpu_nms.restype = ctypes.c_int
+        lib.yo_tf_nms.restype = ctypes.c_int
+        _NMS_C = lib
+    return _NMS_C
+
+
+def gpu_nms_c(boxes, scores, num_classes, max_boxes=50, score_thresh=0.5, nms_thresh=0.5):
+    """gpu_nms() through the C restatement (single thread).  Same outputs as gpu_nms()."""
+    import ctypes
+    lib = _nms_c()
+    boxes = np.ascontiguousarray(boxes, F32).reshape(-1, 4)
+    score = np.ascontiguousarray(scores, F32).reshape(-1, num_classes)
+    B = boxes.shape[0]
+    cap = max(num_classes * max_boxes, 1)
+    ob = np.empty((cap, 4), F32); os_ = np.empty(cap, F32); ol = np.empty(cap, np.int32); oi = np.empty(cap, np.int32)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    k = lib.yo_gpu_nms(P(boxes), P(score), B, num_classes, int(max_boxes), ctypes.c_float(score_thresh),
+                       ctypes.c_float(nms_thresh), P(ob), P(os_), P(ol), P(oi))
+    return ob[:k].copy(), os_[:k].copy(), ol[:k].copy(), oi[:k].copy()
+
+
 # --------------------------------------------------------------------------------------
 # Loss (model.py:192-365) — torch (any float dtype) so autograd restates TF autodiff
 # --------------------------------------------------------------------------------------

@@ -171,3 +171,16 @@ def test_darknet_weights_roundtrip(tmp_path):
     for a, b in zip(params, back):
         for k in a:
             assert np.array_equal(a[k], b[k]), k
+
+
+def test_c_nms_oracle_equals_numpy_oracle(golden_dir):
+    from tests.synth import gen_nms_boxes
+    g = _load(golden_dir, "nms.npz")
+    for boxes, scores, cn, mb in [(g["boxes_in"], g["scores_in"], 6, 20)] + [
+            gen_nms_boxes(5, 1500, 9, dense=d, extent=160.0) + (9, 40) for d in (False, True)]:
+        a = O.gpu_nms(boxes[None], scores[None], cn, mb, 0.3, 0.45)
+        b = O.gpu_nms_c(boxes[None], scores[None], cn, mb, 0.3, 0.45)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    b = O.gpu_nms_c(g["boxes_in"][None], g["scores_in"][None], 6, 20, 0.3, 0.45)
+    assert np.array_equal(b[0], g["gpu_boxes"]) and np.array_equal(b[2], g["gpu_labels"])
