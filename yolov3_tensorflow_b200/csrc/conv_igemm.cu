@@ -425,14 +425,17 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const int c0 = (kb - tap * kb_per_tap) * BK;
         if (lane == 0) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);   // both CTAs' bytes
-          if (p.im2col) {
-            tma_load_im2col_4d_2sm(sA + stage * C::A_BYTES, &tmA, &full_bar[stage], c0, w_base, h_base, img,
-                                   (uint16_t)(tap % p.ksize), (uint16_t)(tap / p.ksize));
-          } else {
-            tma_load_2d_2sm(sA + stage * C::A_BYTES, &tmA, &full_bar[stage], c0, m0);
+          if (rank == 0)
+            mbar_arrive_expect_tx(&full_bar[stage], 2 * (((p.dbg & 1) ? 0 : C::A_BYTES) + ((p.dbg & 2) ? 0 : C::B_BYTES)));
+          if (!(p.dbg & 1)) {
+            if (p.im2col) {
+              tma_load_im2col_4d_2sm(sA + stage * C::A_BYTES, &tmA, &full_bar[stage], c0, w_base, h_base, img,
+                                     (uint16_t)(tap % p.ksize), (uint16_t)(tap / p.ksize));
+            } else {
+              tma_load_2d_2sm(sA + stage * C::A_BYTES, &tmA, &full_bar[stage], c0, m0);
+            }
           }
-          tma_load_2d_2sm(sB + stage * C::B_BYTES, &tmB, &full_bar[stage], tap * p.cin + c0, n0);
+          if (!(p.dbg & 2)) tma_load_2d_2sm(sB + stage * C::B_BYTES, &tmB, &full_bar[stage], tap * p.cin + c0, n0);
         }
         __syncwarp();
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -462,7 +465,7 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t adesc = make_kmajor_desc(a_addr + k * UMMA_K * 2, C::SBO, C::SWIZZLE);
               const uint64_t bdesc = make_kmajor_desc(b_addr + k * UMMA_K * 2, C::SBO, C::SWIZZLE);
-              umma_f16_2sm(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+              if (!(p.dbg & 4)) umma_f16_2sm(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
             }
             umma_commit_2sm(&empty_bar[stage]);                       // frees the slot in BOTH CTAs
             if (kb == num_kb - 1) umma_commit_2sm(&tfull_bar[acc]);   // accumulator ready in BOTH CTAs
@@ -933,10 +936,13 @@ int conv_prepare(const yb_conv_desc* d, const void* x, const void* w_packed, con
   const char* mcf = getenv("YB_CONV_MC");       // "0": off, "1": force on where legal (testing)
   if (two && bk == 64 && cout_pad % 256 == 0 && !(mcf && mcf[0] == '0')) {
     const int mt = ceil_div(p->M, 2 * BLOCK_M), nt = cout_pad / 256;
-    const bool big = (long)mt * nt >= 64 || (mcf && mcf[0] == '1');
+    // measured (profiles/r01_e): +10 % per SM but only 120-132 SMs are schedulable in 8-/4-CTA clusters -> no net gain;
+    // the multicast kernel therefore stays opt-in (YB_CONV_MC=1)
+    const bool big = (mcf && mcf[0] == '1');
     if (big && mt >= 2) { mc_m = 2; mc_n = (nt % 2 == 0) ? 2 : 1; }
   }
   p->mc_m = mc_m; p->mc_n = mc_n;
+  { const char* dbg = getenv("YB_CONV_DBG"); p->dbg = dbg ? atoi(dbg) : 0; }
   const int bn = two ? conv_block_n2(cout_pad) : conv_block_n(cout_pad);
   p->cout = d->cout; p->cin = d->cin; p->ksize = d->ksize; p->stride = d->stride; p->pad = pad;
   p->im2col = d->ksize == 3;
