@@ -288,14 +288,12 @@ def main():
         buf_free[i % 2].record(cur)
         boxes, scores = model.predict_scores(fms)
         ob, os_, ol, oi, cnt = batched_nms_raw(boxes, scores, CLASS_NUM, **NMS_ARGS)
-        h_counts.copy_(cnt, non_blocking=True)
-        torch.cuda.current_stream().synchronize()                              # D2H (sync): K per image
-        kmax = max(int(h_counts.max()), 1)
-        h_boxes[:, :kmax].copy_(ob[:, :kmax], non_blocking=True)               # D2H: detections
-        h_scores[:, :kmax].copy_(os_[:, :kmax], non_blocking=True)
-        h_labels[:, :kmax].copy_(ol[:, :kmax], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return h_counts, kmax
+        h_counts.copy_(cnt, non_blocking=True)                                 # D2H: K per image
+        h_boxes.copy_(ob, non_blocking=True)                                   # D2H: detections (fixed-size, contiguous)
+        h_scores.copy_(os_, non_blocking=True)
+        h_labels.copy_(ol, non_blocking=True)
+        torch.cuda.current_stream().synchronize()                              # results are on the host
+        return h_counts, cap
 
     def barrier():
         if world > 1:
