@@ -430,3 +430,31 @@ def test_train_backward_self_consistency():
         print("  %2d %d %d %4d %4d | %.3g | %.3g" % r)
     bad = [r for r in rows if (r[5] == r[5] and r[5] > 2e-2) or r[6] > 2e-2]
     assert not bad, bad[:8]
+
+
+# ------------------------------------------------------------------------- NMS band logic (many candidates per class)
+def test_nms_many_candidates_multiple_bands():
+    # 20k candidates in one class, tiny boxes (little suppression) and max_boxes 3000: the selection must walk
+    # through several score bands of the shared-memory staging (capacity 2048) and stay bit-exact
+    boxes, scores = gen_nms_boxes(13, 20000, 2, dense=True, extent=4000.0, lo=2.0, hi=6.0)
+    _check_nms(boxes, scores, 2, 3000, 0.05, 0.45)
+
+
+def test_nms_band_capacity_overflow_identical_scores():
+    # > 2048 candidates with one identical score: falls back to the unbanded sweep; ties -> lowest index first
+    boxes, _ = gen_nms_boxes(14, 6000, 1, dense=True, extent=3000.0, lo=2.0, hi=8.0)
+    scores = np.full((6000, 1), 0.75, np.float32)
+    scores[::3, 0] = 0.5                       # two plateaus
+    _check_nms(boxes, scores, 1, 400, 0.3, 0.45)
+
+
+def test_nms_stress_shape_small_sample():
+    # cfg-5 shape scaled down (same generators): 100k boxes x 4 classes, sparse and dense
+    for dense in (False, True):
+        boxes, scores = gen_nms_boxes(5, 100000, 4, dense=dense)
+        pkg = _pkg()
+        gb, gs, gl, gi = pkg.gpu_nms(torch.from_numpy(boxes[None]).cuda(), torch.from_numpy(scores[None]).cuda(), 4,
+                                     max_boxes=200, score_thresh=0.3, nms_thresh=0.45, return_indices=True)
+        ob, os_, ol, oi = O.gpu_nms_c(boxes[None], scores[None], 4, 200, 0.3, 0.45)
+        assert np.array_equal(gi.cpu().numpy(), oi) and np.array_equal(gl.cpu().numpy(), ol)
+        assert np.array_equal(gs.cpu().numpy(), os_) and np.array_equal(gb.cpu().numpy(), ob)

@@ -92,13 +92,57 @@ __device__ __forceinline__ float ord2f(uint32_t u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
+// block-wide max of a 64-bit key (all threads get the result)
+__device__ __forceinline__ unsigned long long block_max_u64(unsigned long long v, unsigned long long* s_red,
+                                                            unsigned long long* s_out) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
+    v = other > v ? other : v;
+  }
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    unsigned long long t = threadIdx.x < SELECT_THREADS / 32 ? s_red[threadIdx.x] : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, t, o);
+      t = other > t ? other : t;
+    }
+    if (threadIdx.x == 0) *s_out = t;
+  }
+  __syncthreads();
+  const unsigned long long r = *s_out;
+  __syncthreads();
+  return r;
+}
+
+static constexpr int BAND_CAP = 2048;      // candidates staged in shared memory per band
+static constexpr int BAND_TARGET = 1024;   // stop widening a band once it holds this many
+static constexpr int HIST_BINS = 4096;     // top 12 bits of the order-preserving score key
+
+// One CTA per (image, class).  Exact greedy NMS in descending-score BANDS:
+//   1. a 12-bit histogram of the candidates' score keys below the current upper bound picks a lower bound so that the
+//      band [lower, upper) holds ~1-2 k candidates (bisection inside one histogram bin if that bin alone overflows);
+//   2. the band is staged in shared memory (key + normalised box), candidates overlapping an already selected box are
+//      dropped, then rounds of (block-wide argmax || suppress-by-previous-pick) select from it;
+//   3. if fewer than max_boxes were selected the next (strictly lower-scored) band is visited.
+// Every candidate of a lower band scores below every candidate of a higher band, so this is exactly the TF kernel's
+// visit order; typical inputs finish inside the first band.  More than BAND_CAP candidates with IDENTICAL score fall
+// back to the unbanded global-memory sweep (use_global).
 __global__ void __launch_bounds__(SELECT_THREADS)
 nms_select_kernel(const float* __restrict__ boxes, int B, int C, int max_boxes, float iou_thr,
                   const int* __restrict__ cand_count, const float* __restrict__ cand_score,
                   int* __restrict__ cand_idx, int* __restrict__ sel_count, int* __restrict__ sel_idx,
                   float* __restrict__ sel_score) {
+  extern __shared__ __align__(16) uint8_t nms_smem[];
+  unsigned long long* bkey = reinterpret_cast<unsigned long long*>(nms_smem);        // [BAND_CAP]
+  BoxN* bbox = reinterpret_cast<BoxN*>(bkey + BAND_CAP);                              // [BAND_CAP]
+  BoxN* sbox = bbox + BAND_CAP;                                                       // [max_boxes]
+  int* hist = reinterpret_cast<int*>(sbox + max_boxes);                               // [HIST_BINS]
   __shared__ unsigned long long s_red[SELECT_THREADS / 32];
   __shared__ unsigned long long s_best;
+  __shared__ int s_cnt, s_flag;
   const int c = blockIdx.x, img = blockIdx.y;
   const long segi = (long)img * C + c;
   const int cnt = min(cand_count[segi], B);
@@ -106,46 +150,150 @@ nms_select_kernel(const float* __restrict__ boxes, int B, int C, int max_boxes, 
   int* ix = cand_idx + segi * B;
   const float4* bx = reinterpret_cast<const float4*>(boxes) + (long)img * B;
   int nsel = 0;
-  int last = -1;
-  BoxN lastb = {0, 0, 0, 0, 0};
-  while (nsel < max_boxes) {
-    unsigned long long best = 0ull;
+  bool use_global = false;
+  unsigned long long upper = 1ull << 32;          // exclusive upper bound on the 32-bit score key
+
+  while (nsel < max_boxes && !use_global) {
+    // ---- 1. choose the band [lower, top) just below `upper` ----
+    // highest remaining key
+    unsigned long long mk = 0ull;
     for (int i = threadIdx.x; i < cnt; i += SELECT_THREADS) {
-      const int id = ix[i];
-      if (id < 0) continue;
-      if (last >= 0) {
-        if (id == last || iou_gt(load_box(bx, id), lastb, iou_thr)) { ix[i] = -1; continue; }
+      const unsigned long long o = f2ord(sc[i]);
+      if (o < upper && o + 1 > mk) mk = o + 1;
+    }
+    const unsigned long long top = block_max_u64(mk, s_red, &s_best);      // exclusive; 0: nothing left
+    if (top == 0ull) break;
+    // descending histogram below `top`: coarse bins of 2^20 keys, refined to 2^8 keys if the first bin overflows
+    unsigned long long lower = 0ull;
+    bool found = false;
+    for (int level = 0; level < 2 && !found; ++level) {
+      const int shift = level == 0 ? 20 : 8;
+      for (int i = threadIdx.x; i < HIST_BINS; i += SELECT_THREADS) hist[i] = 0;
+      __syncthreads();
+      for (int i = threadIdx.x; i < cnt; i += SELECT_THREADS) {
+        const unsigned long long o = f2ord(sc[i]);
+        if (o < top) {
+          const unsigned long long d = (top - 1 - o) >> shift;
+          if (d < HIST_BINS) atomicAdd(&hist[(int)d], 1);
+        }
       }
-      const unsigned long long key = ((unsigned long long)f2ord(sc[i]) << 32) | (0xFFFFFFFFu - (uint32_t)id);
-      best = key > best ? key : best;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
-      best = other > best ? other : best;
-    }
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = best;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      unsigned long long v = threadIdx.x < SELECT_THREADS / 32 ? s_red[threadIdx.x] : 0ull;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
-        v = other > v ? other : v;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int acc = 0, nb = 0;
+        for (int bsel = 0; bsel < HIST_BINS; ++bsel) {
+          const int hb = hist[bsel];
+          if (acc > 0 && acc + hb > BAND_CAP) break;
+          acc += hb; nb = bsel + 1;
+          if (acc > BAND_CAP || acc >= BAND_TARGET) break;
+        }
+        s_cnt = acc; s_flag = nb;
       }
-      if (threadIdx.x == 0) s_best = v;
+      __syncthreads();
+      const int acc = s_cnt, nb = s_flag;
+      __syncthreads();
+      if (acc <= BAND_CAP) {
+        const unsigned long long span = (unsigned long long)nb << shift;
+        lower = top > span ? top - span : 0ull;
+        found = true;
+      }
+    }
+    if (!found) {
+      // > BAND_CAP candidates inside 256 consecutive key values: bisect; identical keys beyond capacity -> global sweep
+      unsigned long long lo = top > 256 ? top - 256 : 0ull, hi = top;       // count([hi,top)) <= CAP < count([lo,top))
+      while (hi - lo > 1) {
+        const unsigned long long mid = lo + (hi - lo) / 2;
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        int local = 0;
+        for (int i = threadIdx.x; i < cnt; i += SELECT_THREADS) {
+          const unsigned long long o = f2ord(sc[i]);
+          local += (o >= mid && o < top) ? 1 : 0;
+        }
+        if (local) atomicAdd(&s_cnt, local);
+        __syncthreads();
+        const int cm = s_cnt;
+        __syncthreads();
+        if (cm > BAND_CAP) lo = mid; else hi = mid;
+      }
+      if (hi >= top) { use_global = true; break; }
+      lower = hi;
+    }
+    upper = top;
+    // ---- 2. stage the band ----
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt; i += SELECT_THREADS) {
+      const uint32_t o = f2ord(sc[i]);
+      if (o >= lower && o < upper) {
+        const int id = ix[i];
+        const int slot = atomicAdd(&s_cnt, 1);
+        bkey[slot] = ((unsigned long long)o << 32) | (0xFFFFFFFFu - (uint32_t)id);
+        bbox[slot] = load_box(bx, id);
+      }
     }
     __syncthreads();
-    const unsigned long long k = s_best;
-    __syncthreads();   // s_best/s_red are rewritten next round
-    if (k == 0ull) break;
-    last = (int)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
-    lastb = load_box(bx, last);
-    if (threadIdx.x == 0) {
-      sel_idx[segi * max_boxes + nsel] = last;
-      sel_score[segi * max_boxes + nsel] = ord2f((uint32_t)(k >> 32));
+    const int n = s_cnt;
+    // drop what the boxes selected in higher bands already suppress
+    for (int j = threadIdx.x; j < n; j += SELECT_THREADS) {
+      const BoxN bj = bbox[j];
+      for (int k = 0; k < nsel; ++k)
+        if (iou_gt(bj, sbox[k], iou_thr)) { bkey[j] = 0ull; break; }
     }
-    ++nsel;
+    __syncthreads();
+    // ---- 3. greedy rounds inside the band ----
+    unsigned long long lastkey = 0ull;
+    BoxN lastb = {0, 0, 0, 0, 0};
+    while (nsel < max_boxes) {
+      unsigned long long best = 0ull;
+      for (int j = threadIdx.x; j < n; j += SELECT_THREADS) {
+        const unsigned long long kj = bkey[j];
+        if (kj == 0ull) continue;
+        if (lastkey != 0ull && (kj == lastkey || iou_gt(bbox[j], lastb, iou_thr))) { bkey[j] = 0ull; continue; }
+        best = kj > best ? kj : best;
+      }
+      const unsigned long long k = block_max_u64(best, s_red, &s_best);
+      if (k == 0ull) break;
+      const int id = (int)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
+      lastkey = k;
+      lastb = load_box(bx, id);
+      if (threadIdx.x == 0) {
+        sel_idx[segi * max_boxes + nsel] = id;
+        sel_score[segi * max_boxes + nsel] = ord2f((uint32_t)(k >> 32));
+        sbox[nsel] = lastb;
+      }
+      ++nsel;
+    }
+    __syncthreads();
+    upper = lower;
+    if (upper == 0ull) break;
+  }
+
+  if (use_global) {
+    // unbanded sweep over the global candidate list (marks dead entries in cand_idx)
+    nsel = 0;
+    int last = -1;
+    BoxN lastb = {0, 0, 0, 0, 0};
+    while (nsel < max_boxes) {
+      unsigned long long best = 0ull;
+      for (int i = threadIdx.x; i < cnt; i += SELECT_THREADS) {
+        const int id = ix[i];
+        if (id < 0) continue;
+        if (last >= 0) {
+          if (id == last || iou_gt(load_box(bx, id), lastb, iou_thr)) { ix[i] = -1; continue; }
+        }
+        const unsigned long long key = ((unsigned long long)f2ord(sc[i]) << 32) | (0xFFFFFFFFu - (uint32_t)id);
+        best = key > best ? key : best;
+      }
+      const unsigned long long k = block_max_u64(best, s_red, &s_best);
+      if (k == 0ull) break;
+      last = (int)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
+      lastb = load_box(bx, last);
+      if (threadIdx.x == 0) {
+        sel_idx[segi * max_boxes + nsel] = last;
+        sel_score[segi * max_boxes + nsel] = ord2f((uint32_t)(k >> 32));
+      }
+      ++nsel;
+    }
   }
   if (threadIdx.x == 0) sel_count[segi] = nsel;
 }
@@ -241,8 +389,16 @@ extern "C" int yb_nms(const float* boxes, const float* scores, int n_images, int
       scores, num_boxes, num_classes, bpb, score_thresh, cand_count, cand_score, cand_idx);
   YB_CUDA(cudaGetLastError());
   dim3 g2(num_classes, n_images);
-  nms_select_kernel<<<g2, SELECT_THREADS, 0, st>>>(boxes, num_boxes, num_classes, max_boxes, iou_thresh, cand_count,
-                                                   cand_score, cand_idx, sel_count, sel_idx, sel_score);
+  const size_t sel_smem = (size_t)BAND_CAP * (sizeof(unsigned long long) + sizeof(BoxN)) + (size_t)max_boxes * sizeof(BoxN) +
+                          HIST_BINS * sizeof(int);
+  YB_REQUIRE(sel_smem <= 200 * 1024, "nms: max_boxes %d too large for the shared-memory staging", max_boxes);
+  static size_t smem_set = 0;
+  if (sel_smem > smem_set) {
+    YB_CUDA(cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+    smem_set = sel_smem;
+  }
+  nms_select_kernel<<<g2, SELECT_THREADS, sel_smem, st>>>(boxes, num_boxes, num_classes, max_boxes, iou_thresh, cand_count,
+                                                          cand_score, cand_idx, sel_count, sel_idx, sel_score);
   YB_CUDA(cudaGetLastError());
   nms_gather_kernel<<<n_images, 256, (num_classes + 1) * sizeof(int), st>>>(
       boxes, num_boxes, num_classes, max_boxes, sel_count, sel_idx, sel_score, out_boxes, out_scores, out_labels,
