@@ -87,6 +87,14 @@ int yb_conv_cout_pad(int cout);
 int yb_stem_conv_fwd(const float* x, const float* w_ohwi, const float* scale, const float* shift, int n, int h,
                      int w, int cout, int dtype, int leaky, void* out, void* stream);
 
+/* Thin-layer fast paths (HBM-bound layers at the top of Darknet-53; see csrc/conv_thin.cu): same contract as
+ * yb_conv2d_fwd / yb_stem_conv_fwd, restricted to 3x3, cin = 32, cout in {32,64} (no statistics, 16-bit output),
+ * resp. the 3->32 stem.  Halo tile + resident weights in shared memory, warp-level tensor path. */
+int yb_conv3x3_thin_fwd(const yb_conv_desc* d, const void* x, const void* w_packed, const float* scale,
+                        const float* shift, const void* res, void* out, void* stream);
+int yb_stem_conv_fwd_tc(const float* x, const float* w_ohwi, const float* scale, const float* shift, int n, int h,
+                        int w, int dtype, int leaky, void* out, void* stream);
+
 /* Weight repack (utils/misc_utils.py:114-123 does (Cout,Cin,kh,kw) -> HWIO on the host):
  * src float32 in `layout` -> dst `dtype` (or float32) OHWI [cout_pad,k,k,cin], rows >= cout zeroed. */
 int yb_pack_conv_weights(const float* src, int layout, int cout, int cin, int ksize, int cout_pad, int dtype,

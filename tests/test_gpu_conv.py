@@ -216,3 +216,63 @@ def test_pack_weights_layouts():
         L.check(L.lib.yb_pack_conv_weights(L.ptr(src), lay, cout, cin, k, 64, L.YB_F16, L.ptr(dst), L.stream_handle()), "pack")
         assert torch.equal(dst[:cout], ohwi.half())
         assert torch.all(dst[cout:] == 0)
+
+
+# ------------------------------------------------------------------------- thin-layer kernels (csrc/conv_thin.cu)
+@pytest.mark.parametrize("n,h,w,cout,s,res,dtype", [
+    (2, 32, 48, 64, 1, True, torch.float16),      # darknet53_body/Conv_3 shape family (+ residual)
+    (2, 64, 96, 64, 2, False, torch.float16),     # Conv_1: stride 2
+    (1, 40, 24, 64, 1, False, torch.bfloat16),    # partial tiles (40 % 8 == 0, 24 % 16 != 0)
+    (3, 26, 26, 32, 2, False, torch.float16),     # odd sizes, cout 32
+])
+def test_conv3x3_thin(n, h, w, cout, s, res, dtype, conv_mode):
+    if conv_mode != "1cta":
+        pytest.skip("independent of the tcgen05 kernel mode")
+    L = _lib()
+    g = torch.Generator().manual_seed(11)
+    cin = 32
+    x = torch.randn((n, h, w, cin), generator=g).to(dtype).cuda()
+    wt = (torch.randn((cout, 3, 3, cin), generator=g) / (3 * cin ** 0.5)).cuda()
+    cp = L.lib.yb_conv_cout_pad(cout)
+    wp = torch.zeros((cp, 3, 3, cin), dtype=dtype, device="cuda")
+    code = L.YB_F16 if dtype == torch.float16 else L.YB_BF16
+    L.check(L.lib.yb_pack_conv_weights(L.ptr(wt), L.YB_W_OHWI, cout, cin, 3, cp, code, L.ptr(wp), L.stream_handle()), "pack")
+    sc = (torch.rand(cp, generator=g) + 0.5).cuda(); sh = (torch.randn(cp, generator=g) * 0.1).cuda()
+    ho, wo = h // s, w // s
+    r = torch.randn((n, ho, wo, cout), generator=g).to(dtype).cuda() if res else None
+    out = torch.full((n, ho, wo, cout), -7.0, dtype=dtype, device="cuda")
+    d = L.ConvDesc(n=n, h=h, w=w, cin=cin, cout=cout, ksize=3, stride=s, in_ld=cin, out_ld=cout, res_ld=cout, dtype=code,
+                   out_fp32=0, leaky=1, upsample2x=0)
+    L.check(L.lib.yb_conv3x3_thin_fwd(C.byref(d), L.ptr(x), L.ptr(wp), L.ptr(sc), L.ptr(sh), L.ptr(r), L.ptr(out), L.stream_handle()), "thin")
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), wp[:cout].float().permute(0, 3, 1, 2), None, stride=s, padding=1)
+    y = y * sc[:cout].view(1, -1, 1, 1) + sh[:cout].view(1, -1, 1, 1)
+    y = torch.where(y > 0, y, 0.1 * y)
+    if res:
+        y = y + r.float().permute(0, 3, 1, 2)
+    ref = y.permute(0, 2, 3, 1)
+    eps = 2.0 ** -9 if dtype == torch.float16 else 2.0 ** -6
+    err = (out.float() - ref).abs()
+    assert torch.all(err <= eps * torch.clamp(ref.abs(), min=1.0)), float(err.max())
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_stem_conv_tensor_core(dtype, conv_mode):
+    if conv_mode != "1cta":
+        pytest.skip("independent of the tcgen05 kernel mode")
+    L = _lib()
+    g = torch.Generator().manual_seed(3)
+    n, h, w = 2, 40, 56
+    x = torch.rand((n, h, w, 3), generator=g).cuda()
+    wt = (torch.randn((32, 3, 3, 3), generator=g) * 0.2).cuda()
+    sc = (torch.rand(32, generator=g) + 0.5).cuda(); sh = (torch.randn(32, generator=g) * 0.1).cuda()
+    out = torch.empty((n, h, w, 32), dtype=dtype, device="cuda")
+    code = L.YB_F16 if dtype == torch.float16 else L.YB_BF16
+    L.check(L.lib.yb_stem_conv_fwd_tc(L.ptr(x), L.ptr(wt), L.ptr(sc), L.ptr(sh), n, h, w, code, 1, L.ptr(out), L.stream_handle()), "stem_tc")
+    # operands are rounded to the 16-bit storage type before the tensor-core product (the oracle's storage model)
+    xr = x.to(dtype).float(); wr = wt.to(dtype).float()
+    ref = F.conv2d(xr.permute(0, 3, 1, 2), wr.permute(0, 3, 1, 2), None, padding=1)
+    ref = ref * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)
+    ref = torch.where(ref > 0, ref, 0.1 * ref).permute(0, 2, 3, 1)
+    eps = 2.0 ** -9 if dtype == torch.float16 else 2.0 ** -6
+    err = (out.float() - ref).abs()
+    assert torch.all(err <= eps * torch.clamp(ref.abs(), min=1.0)), float(err.max())

@@ -1,0 +1,296 @@
+// Direct 3x3 convolution for the THIN layers at the top of Darknet-53 (the stem 3->32 and the Cin = 32
+// layers darknet53_body/Conv_1, Conv_3; utils/layer_utils.py:35-36,27): they are HBM-bound (12-64 B in,
+// 64-128 B out per pixel, <= 1.6 GFLOP/img) and the implicit-GEMM path is a poor fit for them — with 32
+// input channels an im2col row is 64 B, which halves the TMA line rate, and every input pixel is re-fetched
+// 9x from L2 (profiles/r01_b: 630 us per layer against a 140-160 us HBM bound).  Here every input pixel is
+// read from global memory ONCE per tile into a shared-memory halo tile, the (tiny) weight matrix stays
+// resident in shared memory, and the 9-tap reduction runs out of shared memory on the warp-level tensor
+// path (ldmatrix + mma.sync m16n8k16, fp32 accumulate) — per-warp gathers through ldmatrix row addresses
+// need no im2col copy at all.  Epilogue: scale/shift + leaky (+ residual), staged through shared memory so
+// that global stores are full 128-byte rows.
+#include "common.cuh"
+
+namespace yb {
+
+static constexpr int TH = 8, TW = 16;          // output pixels per CTA tile: 8 rows x 16 cols = 128
+static constexpr int THIN_THREADS = 128;       // 4 warps, each 2 output rows (two m16 tiles) x all channels
+
+struct ThinParams {
+  const void* x;        // input activation (16-bit NHWC) or float32 image for the stem
+  long x_ld;            // elements between input pixels
+  const void* w;        // packed weights [cout_pad][9*cin] 16-bit (layers) / OHWI float32 [32][27] (stem)
+  const float* scale;
+  const float* shift;
+  const void* res;      // nullable, 16-bit [n, ho, wo, res_ld]
+  long res_ld;
+  void* out;            // 16-bit [n, ho, wo, out_ld]
+  long out_ld;
+  int n, h, w;          // input spatial size
+  int ho, wo;           // output spatial size
+  int tiles_y, tiles_x, num_tiles;
+  int leaky;
+};
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+template <typename T>
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1);
+template <>
+__device__ __forceinline__ void mma16816<__half>(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <>
+__device__ __forceinline__ void mma16816<__nv_bfloat16>(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// CIN = 32 (layers) ; STEM: CIN = 3 float32 image, K padded 27 -> 32
+template <typename T, int COUT, int STRIDE, bool STEM>
+struct ThinCfg {
+  static constexpr int CIN = STEM ? 3 : 32;
+  static constexpr int K = STEM ? 32 : 9 * 32;                  // GEMM K
+  static constexpr int HH = TH * STRIDE + 2, HW = TW * STRIDE + 2;   // halo tile
+  static constexpr int PIX_PITCH = STEM ? 0 : (32 * 2 + 16);    // bytes per halo pixel (padded: conflict-free ldmatrix)
+  static constexpr int HALO_BYTES = STEM ? HH * HW * 3 * 4 : HH * HW * PIX_PITCH;
+  static constexpr int W_PITCH = K * 2 + 16;                    // bytes per weight row (one output channel)
+  static constexpr int W_BYTES = COUT * W_PITCH;
+  static constexpr int A_PITCH = 32 * 2 + 16;                   // stem only: im2col'd [128][32] tile
+  static constexpr int A_BYTES = STEM ? 128 * A_PITCH : 0;
+  static constexpr int O_PITCH = COUT * 2 + 16;                 // output staging [128 px][COUT]
+  static constexpr int O_BYTES = 128 * O_PITCH;
+  static constexpr int SMEM = ((HALO_BYTES + 127) / 128) * 128 + W_BYTES + A_BYTES + O_BYTES + 128;
+};
+
+template <typename T, int COUT, int STRIDE, bool STEM>
+__global__ void __launch_bounds__(THIN_THREADS)
+conv_thin_kernel(const ThinParams p) {
+  using C = ThinCfg<T, COUT, STRIDE, STEM>;
+  extern __shared__ __align__(128) uint8_t tsm[];
+  uint8_t* s_halo = tsm;
+  uint8_t* s_w = tsm + ((C::HALO_BYTES + 127) / 128) * 128;
+  uint8_t* s_a = s_w + C::W_BYTES;
+  uint8_t* s_o = s_a + C::A_BYTES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- weights: resident for the whole (persistent) CTA ----
+  if (STEM) {
+    const float* wf = static_cast<const float*>(p.w);           // [COUT][27]
+    for (int i = tid; i < COUT * 32; i += THIN_THREADS) {
+      const int co = i >> 5, k = i & 31;
+      reinterpret_cast<T*>(s_w + co * C::W_PITCH)[k] = static_cast<T>(k < 27 ? wf[co * 27 + k] : 0.f);
+    }
+  } else {
+    const uint8_t* wg = static_cast<const uint8_t*>(p.w);       // [cout_pad][288] 16-bit
+    constexpr int CH = C::K * 2 / 16;                           // 16-byte chunks per row
+    for (int i = tid; i < COUT * CH; i += THIN_THREADS) {
+      const int co = i / CH, ch = i - co * CH;
+      cp_async16(s_w + co * C::W_PITCH + ch * 16, wg + ((long)co * C::K * 2) + ch * 16, 16);
+    }
+  }
+
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    const int tx = tile % p.tiles_x;
+    const int ty = (tile / p.tiles_x) % p.tiles_y;
+    const int img = tile / (p.tiles_x * p.tiles_y);
+    const int oy0 = ty * TH, ox0 = tx * TW;
+    const int iy0 = oy0 * STRIDE - 1, ix0 = ox0 * STRIDE - 1;
+    __syncthreads();                                            // previous tile done with s_halo / s_o
+    // ---- halo tile ----
+    if (STEM) {
+      const float* xin = static_cast<const float*>(p.x) + (long)img * p.h * p.w * 3;
+      float* hf = reinterpret_cast<float*>(s_halo);
+      for (int i = tid; i < C::HH * C::HW * 3; i += THIN_THREADS) {
+        const int c = i % 3, px = (i / 3) % C::HW, py = i / (3 * C::HW);
+        const int gy = iy0 + py, gx = ix0 + px;
+        hf[i] = (gy >= 0 && gy < p.h && gx >= 0 && gx < p.w) ? xin[((long)gy * p.w + gx) * 3 + c] : 0.f;
+      }
+    } else {
+      const T* xin = static_cast<const T*>(p.x) + (long)img * p.h * p.w * p.x_ld;
+      for (int i = tid; i < C::HH * C::HW * 4; i += THIN_THREADS) {
+        const int ch = i & 3, px = (i >> 2) % C::HW, py = (i >> 2) / C::HW;
+        const int gy = iy0 + py, gx = ix0 + px;
+        const bool ok = gy >= 0 && gy < p.h && gx >= 0 && gx < p.w;
+        const T* src = ok ? xin + ((long)gy * p.w + gx) * p.x_ld + ch * 8 : xin;
+        cp_async16(s_halo + (py * C::HW + px) * C::PIX_PITCH + ch * 16, src, ok ? 16 : 0);   // zero-fill outside
+      }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    if (STEM) {
+      // im2col of the thread's pixel: 27 taps -> one 32-wide fp16 row
+      const float* hf = reinterpret_cast<const float*>(s_halo);
+      const int py = tid / TW, px = tid % TW;
+      T* arow = reinterpret_cast<T*>(s_a + tid * C::A_PITCH);
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s = 0; s < 3; ++s)
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            arow[(r * 3 + s) * 3 + c] = static_cast<T>(hf[((py + r) * C::HW + (px + s)) * 3 + c]);
+#pragma unroll
+      for (int k = 27; k < 32; ++k) arow[k] = static_cast<T>(0.f);
+      __syncthreads();
+    }
+    // ---- main loop: each warp computes 2 output rows (2 x m16) x COUT ----
+    constexpr int NT = COUT / 8;                                // n8 tiles
+    float acc[2][NT][4];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int nj = 0; nj < NT; ++nj)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[mi][nj][q] = 0.f;
+    constexpr int KSTEPS = C::K / 16;
+#pragma unroll 1
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+      uint32_t a[2][4];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        const int y = warp * 2 + mi, x = lane & 15, kh = lane >> 4;          // row of the m16 tile / k half
+        const uint8_t* ap;
+        if (STEM) {
+          ap = s_a + (y * TW + x) * C::A_PITCH + (ks * 16 + kh * 8) * 2;
+        } else {
+          const int tap = ks >> 1, kc = ks & 1;
+          const int r = tap / 3, s = tap - r * 3;
+          ap = s_halo + ((y * STRIDE + r) * C::HW + (x * STRIDE + s)) * C::PIX_PITCH + (kc * 16 + kh * 8) * 2;
+        }
+        ldmatrix_x4(a[mi], ap);
+      }
+#pragma unroll
+      for (int nb = 0; nb < NT / 2; ++nb) {
+        // 16 output channels x k16: matrices (n0-7,k0-7), (n0-7,k8-15), (n8-15,k0-7), (n8-15,k8-15)
+        uint32_t b[4];
+        const int nrow = nb * 16 + (lane & 7) + ((lane >> 4) & 1) * 8;
+        const int kof = ks * 16 + ((lane >> 3) & 1) * 8;
+        ldmatrix_x4(b, s_w + nrow * C::W_PITCH + kof * 2);
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) {
+          mma16816<T>(acc[mi][2 * nb], a[mi], b[0], b[1]);
+          mma16816<T>(acc[mi][2 * nb + 1], a[mi], b[2], b[3]);
+        }
+      }
+    }
+    // ---- epilogue: scale/shift/leaky -> shared staging ----
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+      const int y = warp * 2 + mi;
+#pragma unroll
+      for (int nj = 0; nj < NT; ++nj) {
+        const int c0 = nj * 8 + (lane & 3) * 2;
+        const float sc0 = __ldg(p.scale + c0), sc1 = __ldg(p.scale + c0 + 1);
+        const float sh0 = __ldg(p.shift + c0), sh1 = __ldg(p.shift + c0 + 1);
+#pragma unroll
+        for (int hrow = 0; hrow < 2; ++hrow) {
+          const int x = (lane >> 2) + hrow * 8;
+          float v0 = fmaf(acc[mi][nj][hrow * 2 + 0], sc0, sh0);
+          float v1 = fmaf(acc[mi][nj][hrow * 2 + 1], sc1, sh1);
+          if (p.leaky) { v0 = leaky01(v0); v1 = leaky01(v1); }
+          if (p.res == nullptr) {
+            *reinterpret_cast<uint32_t*>(s_o + (y * TW + x) * C::O_PITCH + c0 * 2) = Pack2<T>::pack(v0, v1);
+          } else {   // keep fp32 precision until the residual is added: stage as two halves of a float2? no room -> add here
+            const int oy = oy0 + y, ox = ox0 + x;
+            if (oy < p.ho && ox < p.wo) {
+              const uint32_t ru = *reinterpret_cast<const uint32_t*>(static_cast<const T*>(p.res) +
+                                                                    (((long)img * p.ho + oy) * p.wo + ox) * p.res_ld + c0);
+              const float2 rf = Pack2<T>::unpack(ru);
+              v0 += rf.x; v1 += rf.y;
+            }
+            *reinterpret_cast<uint32_t*>(s_o + (y * TW + x) * C::O_PITCH + c0 * 2) = Pack2<T>::pack(v0, v1);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- coalesced copy-out: one 16-byte chunk per thread-iteration, full rows of COUT*2 bytes ----
+    constexpr int OCH = COUT * 2 / 16;
+    for (int i = tid; i < 128 * OCH; i += THIN_THREADS) {
+      const int px = i / OCH, ch = i - px * OCH;
+      const int oy = oy0 + px / TW, ox = ox0 + px % TW;
+      if (oy < p.ho && ox < p.wo) {
+        const uint4 v = *reinterpret_cast<const uint4*>(s_o + px * C::O_PITCH + ch * 16);
+        *reinterpret_cast<uint4*>(static_cast<T*>(p.out) + (((long)img * p.ho + oy) * p.wo + ox) * p.out_ld + ch * 8) = v;
+      }
+    }
+  }
+  cp_async_wait_all();
+}
+
+template <typename T, int COUT, int STRIDE, bool STEM>
+static int launch_thin(const ThinParams& p, cudaStream_t st) {
+  using C = ThinCfg<T, COUT, STRIDE, STEM>;
+  auto kern = conv_thin_kernel<T, COUT, STRIDE, STEM>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    YB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    attr_done = true;
+  }
+  int per_sm = 227 * 1024 / (C::SMEM + 1024);
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 8) per_sm = 8;
+  const int grid = p.num_tiles < num_sms() * per_sm ? p.num_tiles : num_sms() * per_sm;
+  kern<<<grid, THIN_THREADS, C::SMEM, st>>>(p);
+  YB_CUDA(cudaGetLastError());
+  return YB_OK;
+}
+
+}  // namespace yb
+
+using namespace yb;
+
+// 3x3 conv, cin = 32, cout in {32, 64}, stride 1|2, no BN statistics (inference epilogue).
+extern "C" int yb_conv3x3_thin_fwd(const yb_conv_desc* d, const void* x, const void* w_packed, const float* scale,
+                                   const float* shift, const void* res, void* out, void* stream) {
+  YB_REQUIRE(d && x && w_packed && scale && shift && out, "conv_thin: null pointer");
+  YB_REQUIRE(d->ksize == 3 && d->cin == 32 && (d->cout == 64 || d->cout == 32) && (d->stride == 1 || d->stride == 2),
+             "conv_thin: supports 3x3, cin=32, cout in {32,64}, stride 1|2 (got k=%d cin=%d cout=%d s=%d)", d->ksize, d->cin,
+             d->cout, d->stride);
+  YB_REQUIRE(d->dtype == YB_F16 || d->dtype == YB_BF16, "conv_thin: dtype must be f16 or bf16");
+  YB_REQUIRE(!d->out_fp32 && !d->upsample2x, "conv_thin: 16-bit, non-upsampled outputs only");
+  YB_REQUIRE(d->in_ld % 8 == 0 && d->out_ld % 8 == 0 && (!res || d->res_ld % 2 == 0), "conv_thin: bad leading dimensions");
+  ThinParams p;
+  p.x = x; p.x_ld = d->in_ld; p.w = w_packed; p.scale = scale; p.shift = shift; p.res = res; p.res_ld = d->res_ld;
+  p.out = out; p.out_ld = d->out_ld; p.n = d->n; p.h = d->h; p.w = d->w;
+  p.ho = d->h / d->stride; p.wo = d->w / d->stride;
+  p.tiles_y = ceil_div(p.ho, TH); p.tiles_x = ceil_div(p.wo, TW);
+  p.num_tiles = p.tiles_x * p.tiles_y * d->n;
+  p.leaky = d->leaky;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define YB_THIN(T)                                                                         \
+  if (d->cout == 64 && d->stride == 1) return launch_thin<T, 64, 1, false>(p, st);        \
+  if (d->cout == 64 && d->stride == 2) return launch_thin<T, 64, 2, false>(p, st);        \
+  if (d->cout == 32 && d->stride == 1) return launch_thin<T, 32, 1, false>(p, st);        \
+  return launch_thin<T, 32, 2, false>(p, st);
+  if (d->dtype == YB_F16) { YB_THIN(__half) }
+  YB_THIN(__nv_bfloat16)
+#undef YB_THIN
+}
+
+// Stem on the warp-level tensor path: float32 image [n,h,w,3] -> 16-bit [n,h,w,32]; w_ohwi float32 [32][27].
+extern "C" int yb_stem_conv_fwd_tc(const float* x, const float* w_ohwi, const float* scale, const float* shift, int n,
+                                   int h, int w, int dtype, int leaky, void* out, void* stream) {
+  YB_REQUIRE(x && w_ohwi && scale && shift && out && n > 0 && h > 0 && w > 0, "stem_tc: bad argument");
+  ThinParams p;
+  p.x = x; p.x_ld = 3; p.w = w_ohwi; p.scale = scale; p.shift = shift; p.res = nullptr; p.res_ld = 0;
+  p.out = out; p.out_ld = 32; p.n = n; p.h = h; p.w = w; p.ho = h; p.wo = w;
+  p.tiles_y = ceil_div(h, TH); p.tiles_x = ceil_div(w, TW);
+  p.num_tiles = p.tiles_x * p.tiles_y * n;
+  p.leaky = leaky;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == YB_F16) return launch_thin<__half, 32, 1, true>(p, st);
+  if (dtype == YB_BF16) return launch_thin<__nv_bfloat16, 32, 1, true>(p, st);
+  set_error("stem_tc: dtype must be f16 or bf16");
+  return YB_ERR_UNSUPPORTED;
+}

@@ -2,6 +2,7 @@
 // for a fixed (batch, H, W, dtype): layer schedule, activation/parameter arena layout,
 // TMA tensor maps.  concat (model.py:62,72) and NN-upsample (utils/layer_utils.py:82-87)
 // never run as ops: producers store straight into channel slices of the concat buffers.
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -273,16 +274,38 @@ extern "C" int yb_net_forward_layers(yb_net* net, const float* images, float* fm
     }
     net->fold_dirty = false;
   }
+  static const bool thin = !(getenv("YB_THIN") && getenv("YB_THIN")[0] == '0');   // A/B switch for the thin-layer kernels
   if (first == 0) {
     Layer& L = net->layers[0];
-    int rc = yb_stem_conv_fwd(images, reinterpret_cast<const float*>(net->par + L.w_master),
-                              reinterpret_cast<const float*>(net->par + L.scale),
-                              reinterpret_cast<const float*>(net->par + L.shift), net->n, net->h, net->w, L.info.cout,
-                              net->dtype, 1, ten_ptr(net, L.out), stream);
+    int rc;
+    if (thin)
+      rc = yb_stem_conv_fwd_tc(images, reinterpret_cast<const float*>(net->par + L.w_master),
+                               reinterpret_cast<const float*>(net->par + L.scale),
+                               reinterpret_cast<const float*>(net->par + L.shift), net->n, net->h, net->w, net->dtype, 1,
+                               ten_ptr(net, L.out), stream);
+    else
+      rc = yb_stem_conv_fwd(images, reinterpret_cast<const float*>(net->par + L.w_master),
+                            reinterpret_cast<const float*>(net->par + L.scale),
+                            reinterpret_cast<const float*>(net->par + L.shift), net->n, net->h, net->w, L.info.cout,
+                            net->dtype, 1, ten_ptr(net, L.out), stream);
     if (rc) return rc;
   }
   for (size_t i = first > 1 ? first : 1; i < net->layers.size() && (int)i <= last; ++i) {
     Layer& L = net->layers[i];
+    if (thin && L.info.ksize == 3 && L.info.cin == 32 && L.info.has_bn && !L.upsample) {
+      // Cin = 32: 64-byte im2col rows halve the TMA line rate -> direct halo-tile kernel (csrc/conv_thin.cu)
+      yb_conv_desc d;
+      memset(&d, 0, sizeof(d));
+      d.n = net->n; d.h = L.info.in_h; d.w = L.info.in_w; d.cin = 32; d.cout = L.info.cout; d.ksize = 3;
+      d.stride = L.info.stride; d.in_ld = net->bufs[L.in.buf].ld; d.out_ld = net->bufs[L.out.buf].ld;
+      d.res_ld = L.res.buf >= 0 ? net->bufs[L.res.buf].ld : 0; d.dtype = net->dtype; d.leaky = 1;
+      int rc = yb_conv3x3_thin_fwd(&d, ten_ptr(net, L.in), net->par + L.w_packed,
+                                   reinterpret_cast<const float*>(net->par + L.scale),
+                                   reinterpret_cast<const float*>(net->par + L.shift),
+                                   L.res.buf >= 0 ? ten_ptr(net, L.res) : nullptr, ten_ptr(net, L.out), stream);
+      if (rc) return rc;
+      continue;
+    }
     ConvParams* p = &L.params;
     if (!L.info.has_bn) {
       int which = L.out.buf == net->fm_buf[0] ? 0 : (L.out.buf == net->fm_buf[1] ? 1 : 2);
