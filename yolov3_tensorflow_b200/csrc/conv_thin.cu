@@ -18,7 +18,7 @@ static constexpr int THIN_THREADS = 128;       // 4 warps, each 2 output rows (t
 struct ThinParams {
   const void* x;        // input activation (16-bit NHWC) or float32 image for the stem
   long x_ld;            // elements between input pixels
-  const void* w;        // packed weights [cout_pad][9*cin] 16-bit (layers) / OHWI float32 [32][27] (stem)
+  const void* wt;       // packed weights [cout_pad][9*cin] 16-bit (layers) / OHWI float32 [32][27] (stem)
   const float* scale;
   const float* shift;
   const void* res;      // nullable, 16-bit [n, ho, wo, res_ld]
@@ -85,13 +85,13 @@ conv_thin_kernel(const ThinParams p) {
 
   // ---- weights: resident for the whole (persistent) CTA ----
   if (STEM) {
-    const float* wf = static_cast<const float*>(p.w);           // [COUT][27]
+    const float* wf = static_cast<const float*>(p.wt);          // [COUT][27]
     for (int i = tid; i < COUT * 32; i += THIN_THREADS) {
       const int co = i >> 5, k = i & 31;
       reinterpret_cast<T*>(s_w + co * C::W_PITCH)[k] = static_cast<T>(k < 27 ? wf[co * 27 + k] : 0.f);
     }
   } else {
-    const uint8_t* wg = static_cast<const uint8_t*>(p.w);       // [cout_pad][288] 16-bit
+    const uint8_t* wg = static_cast<const uint8_t*>(p.wt);      // [cout_pad][288] 16-bit
     constexpr int CH = C::K * 2 / 16;                           // 16-byte chunks per row
     for (int i = tid; i < COUT * CH; i += THIN_THREADS) {
       const int co = i / CH, ch = i - co * CH;
@@ -261,7 +261,7 @@ extern "C" int yb_conv3x3_thin_fwd(const yb_conv_desc* d, const void* x, const v
   YB_REQUIRE(!d->out_fp32 && !d->upsample2x, "conv_thin: 16-bit, non-upsampled outputs only");
   YB_REQUIRE(d->in_ld % 8 == 0 && d->out_ld % 8 == 0 && (!res || d->res_ld % 2 == 0), "conv_thin: bad leading dimensions");
   ThinParams p;
-  p.x = x; p.x_ld = d->in_ld; p.w = w_packed; p.scale = scale; p.shift = shift; p.res = res; p.res_ld = d->res_ld;
+  p.x = x; p.x_ld = d->in_ld; p.wt = w_packed; p.scale = scale; p.shift = shift; p.res = res; p.res_ld = d->res_ld;
   p.out = out; p.out_ld = d->out_ld; p.n = d->n; p.h = d->h; p.w = d->w;
   p.ho = d->h / d->stride; p.wo = d->w / d->stride;
   p.tiles_y = ceil_div(p.ho, TH); p.tiles_x = ceil_div(p.wo, TW);
@@ -283,7 +283,7 @@ extern "C" int yb_stem_conv_fwd_tc(const float* x, const float* w_ohwi, const fl
                                    int h, int w, int dtype, int leaky, void* out, void* stream) {
   YB_REQUIRE(x && w_ohwi && scale && shift && out && n > 0 && h > 0 && w > 0, "stem_tc: bad argument");
   ThinParams p;
-  p.x = x; p.x_ld = 3; p.w = w_ohwi; p.scale = scale; p.shift = shift; p.res = nullptr; p.res_ld = 0;
+  p.x = x; p.x_ld = 3; p.wt = w_ohwi; p.scale = scale; p.shift = shift; p.res = nullptr; p.res_ld = 0;
   p.out = out; p.out_ld = 32; p.n = n; p.h = h; p.w = w; p.ho = h; p.wo = w;
   p.tiles_y = ceil_div(h, TH); p.tiles_x = ceil_div(w, TW);
   p.num_tiles = p.tiles_x * p.tiles_y * n;
