@@ -435,13 +435,13 @@ def test_train_backward_self_consistency():
 # ------------------------------------------------------------------------- NMS band logic (many candidates per class)
 def test_nms_many_candidates_multiple_bands():
     # 20k candidates in one class, tiny boxes (little suppression) and max_boxes 3000: the selection must walk
-    # through several score bands of the shared-memory staging (capacity 2048) and stay bit-exact
+    # through several score bands of the shared-memory staging (capacity 1024) and stay bit-exact
     boxes, scores = gen_nms_boxes(13, 20000, 2, dense=True, extent=4000.0, lo=2.0, hi=6.0)
     _check_nms(boxes, scores, 2, 3000, 0.05, 0.45)
 
 
 def test_nms_band_capacity_overflow_identical_scores():
-    # > 2048 candidates with one identical score: falls back to the unbanded sweep; ties -> lowest index first
+    # > 1024 candidates with one identical score: falls back to the unbanded sweep; ties -> lowest index first
     boxes, _ = gen_nms_boxes(14, 6000, 1, dense=True, extent=3000.0, lo=2.0, hi=8.0)
     scores = np.full((6000, 1), 0.75, np.float32)
     scores[::3, 0] = 0.5                       # two plateaus

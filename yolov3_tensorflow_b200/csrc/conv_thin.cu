@@ -34,9 +34,6 @@ struct ThinParams {
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async4(void* dst, const void* src, int src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
-}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* p) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -72,8 +69,7 @@ struct ThinCfg {
   static constexpr int A_BYTES = STEM ? 128 * A_PITCH : 0;
   static constexpr int O_PITCH = COUT * 2 + 16;                 // output staging [128 px][COUT]
   static constexpr int O_BYTES = 128 * O_PITCH;
-  static constexpr int HALO_STRIDE = ((HALO_BYTES + 127) / 128) * 128;
-  static constexpr int SMEM = 2 * HALO_STRIDE + W_BYTES + A_BYTES + O_BYTES + 128;   // halo tile is double-buffered
+  static constexpr int SMEM = ((HALO_BYTES + 127) / 128) * 128 + W_BYTES + A_BYTES + O_BYTES + 128;
 };
 
 template <typename T, int COUT, int STRIDE, bool STEM>
@@ -81,8 +77,8 @@ __global__ void __launch_bounds__(THIN_THREADS)
 conv_thin_kernel(const ThinParams p) {
   using C = ThinCfg<T, COUT, STRIDE, STEM>;
   extern __shared__ __align__(128) uint8_t tsm[];
-  uint8_t* s_halo0 = tsm;
-  uint8_t* s_w = tsm + 2 * C::HALO_STRIDE;
+  uint8_t* s_halo = tsm;
+  uint8_t* s_w = tsm + ((C::HALO_BYTES + 127) / 128) * 128;
   uint8_t* s_a = s_w + C::W_BYTES;
   uint8_t* s_o = s_a + C::A_BYTES;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -103,19 +99,21 @@ conv_thin_kernel(const ThinParams p) {
     }
   }
 
-  // asynchronous load of one tile's input halo (zero-filled outside the image) into buffer `dstb`
-  auto issue_halo = [&](int tile, uint8_t* dstb) {
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
     const int tx = tile % p.tiles_x;
     const int ty = (tile / p.tiles_x) % p.tiles_y;
     const int img = tile / (p.tiles_x * p.tiles_y);
-    const int iy0 = ty * TH * STRIDE - 1, ix0 = tx * TW * STRIDE - 1;
+    const int oy0 = ty * TH, ox0 = tx * TW;
+    const int iy0 = oy0 * STRIDE - 1, ix0 = ox0 * STRIDE - 1;
+    __syncthreads();                                            // previous tile done with s_halo / s_o
+    // ---- halo tile ----
     if (STEM) {
       const float* xin = static_cast<const float*>(p.x) + (long)img * p.h * p.w * 3;
+      float* hf = reinterpret_cast<float*>(s_halo);
       for (int i = tid; i < C::HH * C::HW * 3; i += THIN_THREADS) {
         const int c = i % 3, px = (i / 3) % C::HW, py = i / (3 * C::HW);
         const int gy = iy0 + py, gx = ix0 + px;
-        const bool ok = gy >= 0 && gy < p.h && gx >= 0 && gx < p.w;
-        cp_async4(dstb + i * 4, ok ? xin + ((long)gy * p.w + gx) * 3 + c : xin, ok ? 4 : 0);
+        hf[i] = (gy >= 0 && gy < p.h && gx >= 0 && gx < p.w) ? xin[((long)gy * p.w + gx) * 3 + c] : 0.f;
       }
     } else {
       const T* xin = static_cast<const T*>(p.x) + (long)img * p.h * p.w * p.x_ld;
@@ -124,23 +122,11 @@ conv_thin_kernel(const ThinParams p) {
         const int gy = iy0 + py, gx = ix0 + px;
         const bool ok = gy >= 0 && gy < p.h && gx >= 0 && gx < p.w;
         const T* src = ok ? xin + ((long)gy * p.w + gx) * p.x_ld + ch * 8 : xin;
-        cp_async16(dstb + (py * C::HW + px) * C::PIX_PITCH + ch * 16, src, ok ? 16 : 0);   // zero-fill outside
+        cp_async16(s_halo + (py * C::HW + px) * C::PIX_PITCH + ch * 16, src, ok ? 16 : 0);   // zero-fill outside
       }
     }
-  };
-
-  int buf = 0;
-  if ((int)blockIdx.x < p.num_tiles) issue_halo(blockIdx.x, s_halo0);
-  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-    const int tx = tile % p.tiles_x;
-    const int ty = (tile / p.tiles_x) % p.tiles_y;
-    const int img = tile / (p.tiles_x * p.tiles_y);
-    const int oy0 = ty * TH, ox0 = tx * TW;
-    uint8_t* s_halo = s_halo0 + buf * C::HALO_STRIDE;
-    cp_async_wait_all();                                        // this tile's halo (and, first time, the weights)
-    __syncthreads();                                            // ... visible to all; previous tile done with s_o / other buffer
-    if (tile + (int)gridDim.x < p.num_tiles) issue_halo(tile + gridDim.x, s_halo0 + (buf ^ 1) * C::HALO_STRIDE);
-    buf ^= 1;
+    cp_async_wait_all();
+    __syncthreads();
     if (STEM) {
       // im2col of the thread's pixel: 27 taps -> one 32-wide fp16 row
       const float* hf = reinterpret_cast<const float*>(s_halo);

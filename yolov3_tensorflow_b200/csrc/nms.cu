@@ -117,8 +117,8 @@ __device__ __forceinline__ unsigned long long block_max_u64(unsigned long long v
   return r;
 }
 
-static constexpr int BAND_CAP = 2048;      // candidates staged in shared memory per band
-static constexpr int BAND_TARGET = 1024;   // stop widening a band once it holds this many
+static constexpr int BAND_CAP = 1024;      // candidates staged in shared memory per band
+static constexpr int BAND_TARGET = 512;    // stop widening a band once it holds this many
 static constexpr int HIST_BINS = 4096;     // top 12 bits of the order-preserving score key
 
 // One CTA per (image, class).  Exact greedy NMS in descending-score BANDS:
@@ -139,7 +139,7 @@ nms_select_kernel(const float* __restrict__ boxes, int B, int C, int max_boxes, 
   unsigned long long* bkey = reinterpret_cast<unsigned long long*>(nms_smem);        // [BAND_CAP]
   BoxN* bbox = reinterpret_cast<BoxN*>(bkey + BAND_CAP);                              // [BAND_CAP]
   BoxN* sbox = bbox + BAND_CAP;                                                       // [max_boxes]
-  int* hist = reinterpret_cast<int*>(sbox + max_boxes);                               // [HIST_BINS]
+  int* hist = reinterpret_cast<int*>(nms_smem);   // [HIST_BINS] aliases the band staging (used only before staging)
   __shared__ unsigned long long s_red[SELECT_THREADS / 32];
   __shared__ unsigned long long s_best;
   __shared__ int s_cnt, s_flag;
@@ -155,6 +155,12 @@ nms_select_kernel(const float* __restrict__ boxes, int B, int C, int max_boxes, 
 
   while (nsel < max_boxes && !use_global) {
     // ---- 1. choose the band [lower, top) just below `upper` ----
+    unsigned long long lower = 0ull;
+    if (cnt <= BAND_CAP && upper == (1ull << 32)) {
+      // common case (a few dozen candidates per class after the score filter): everything fits in one band
+      goto stage_band;
+    }
+    {
     // highest remaining key
     unsigned long long mk = 0ull;
     for (int i = threadIdx.x; i < cnt; i += SELECT_THREADS) {
@@ -164,7 +170,6 @@ nms_select_kernel(const float* __restrict__ boxes, int B, int C, int max_boxes, 
     const unsigned long long top = block_max_u64(mk, s_red, &s_best);      // exclusive; 0: nothing left
     if (top == 0ull) break;
     // descending histogram below `top`: coarse bins of 2^20 keys, refined to 2^8 keys if the first bin overflows
-    unsigned long long lower = 0ull;
     bool found = false;
     for (int level = 0; level < 2 && !found; ++level) {
       const int shift = level == 0 ? 20 : 8;
@@ -219,6 +224,8 @@ nms_select_kernel(const float* __restrict__ boxes, int B, int C, int max_boxes, 
       lower = hi;
     }
     upper = top;
+    }
+  stage_band:
     // ---- 2. stage the band ----
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
@@ -389,8 +396,8 @@ extern "C" int yb_nms(const float* boxes, const float* scores, int n_images, int
       scores, num_boxes, num_classes, bpb, score_thresh, cand_count, cand_score, cand_idx);
   YB_CUDA(cudaGetLastError());
   dim3 g2(num_classes, n_images);
-  const size_t sel_smem = (size_t)BAND_CAP * (sizeof(unsigned long long) + sizeof(BoxN)) + (size_t)max_boxes * sizeof(BoxN) +
-                          HIST_BINS * sizeof(int);
+  static_assert(HIST_BINS * sizeof(int) <= BAND_CAP * (sizeof(unsigned long long) + sizeof(BoxN)), "histogram must fit the staging area");
+  const size_t sel_smem = (size_t)BAND_CAP * (sizeof(unsigned long long) + sizeof(BoxN)) + (size_t)max_boxes * sizeof(BoxN);
   YB_REQUIRE(sel_smem <= 200 * 1024, "nms: max_boxes %d too large for the shared-memory staging", max_boxes);
   static size_t smem_set = 0;
   if (sel_smem > smem_set) {
