@@ -129,10 +129,12 @@ int yb_bn_act_apply(const void* z, long z_ld, const float* scale, const float* s
                     void* out, long out_ld, int n, int h, int w, int c, int dtype, int leaky, int upsample2x,
                     void* stream);
 /* dgamma/dbeta (fp32 [c], overwritten) from dA (gradient w.r.t. the layer output; upsample2x: summed over the
- * 4 copies) and the saved z. */
+ * 4 copies) and the saved z.  workspace: NULL (atomic accumulation) or yb_bn_bwd_reduce_workspace_bytes() bytes,
+ * zero-initialised once (two-stage deterministic reduction, no same-address atomics). */
+int yb_bn_bwd_reduce_workspace_bytes(size_t* bytes);
 int yb_bn_bwd_reduce(const void* dA, long dA_ld, const void* z, long z_ld, const float* scale, const float* shift,
                      const float* save_mean, const float* save_invstd, int n, int h, int w, int c, int dtype,
-                     int leaky, int upsample2x, float* dgamma, float* dbeta, void* stream);
+                     int leaky, int upsample2x, float* dgamma, float* dbeta, void* workspace, void* stream);
 /* dz = gamma*invstd*(dact - dbeta/M - zhat*dgamma/M); dilate2x stores row (p,q) at (2p,2q) of [n,2h,2w,dz_ld]. */
 int yb_bn_bwd_apply(const void* dA, long dA_ld, const void* z, long z_ld, const float* gamma, const float* scale,
                     const float* shift, const float* save_mean, const float* save_invstd, const float* dgamma,

@@ -145,10 +145,15 @@ def test_bn_train_forward_backward(upsample, res, c):
     dA = (torch.randn(a.shape, generator=g) * 0.1).to(dt).cuda()
     a.backward(dA.float())
     dgam = torch.empty(c).cuda(); dbet = torch.empty(c).cuda()
-    L.check(lib.yb_bn_bwd_reduce(ptr(dA), c, ptr(z), c, ptr(scale), ptr(shift), ptr(smean), ptr(sinv), n, h, w, c, L.YB_BF16, 1,
-                                 int(upsample), ptr(dgam), ptr(dbet), st()), "bwd_reduce")
-    torch.testing.assert_close(dgam, gr.grad, rtol=2e-3, atol=2e-3)
-    torch.testing.assert_close(dbet, br.grad, rtol=2e-3, atol=2e-3)
+    need = C.c_size_t()
+    L.check(lib.yb_bn_bwd_reduce_workspace_bytes(C.byref(need)), "ws")
+    ws = torch.zeros(need.value, dtype=torch.uint8, device="cuda")
+    for workspace in (None, ws, ws):          # atomic path, two-stage path (twice: the ticket must reset itself)
+        dgam.fill_(-1); dbet.fill_(-1)
+        L.check(lib.yb_bn_bwd_reduce(ptr(dA), c, ptr(z), c, ptr(scale), ptr(shift), ptr(smean), ptr(sinv), n, h, w, c, L.YB_BF16, 1,
+                                     int(upsample), ptr(dgam), ptr(dbet), ptr(workspace), st()), "bwd_reduce")
+        torch.testing.assert_close(dgam, gr.grad, rtol=2e-3, atol=2e-3)
+        torch.testing.assert_close(dbet, br.grad, rtol=2e-3, atol=2e-3)
     for dil in (0, 1):
         dz = torch.zeros((n, h * (2 if dil else 1), w * (2 if dil else 1), c), dtype=dt, device="cuda")
         L.check(lib.yb_bn_bwd_apply(ptr(dA), c, ptr(z), c, ptr(gamma), ptr(scale), ptr(shift), ptr(smean), ptr(sinv), ptr(dgam), ptr(dbet),

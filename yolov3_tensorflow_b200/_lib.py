@@ -55,7 +55,8 @@ _SIGS = {
     "yb_pack_dgrad_weights": ([vp, i32, i32, i32, i32, i32, i32, vp, vp], i32),
     "yb_bn_finalize": ([vp, vp, C.c_long, i32, vp, vp, f32, f32, vp, vp, vp, vp, vp, vp, vp], i32),
     "yb_bn_act_apply": ([vp, C.c_long, vp, vp, vp, C.c_long, vp, C.c_long, i32, i32, i32, i32, i32, i32, i32, vp], i32),
-    "yb_bn_bwd_reduce": ([vp, C.c_long, vp, C.c_long, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp], i32),
+    "yb_bn_bwd_reduce_workspace_bytes": ([C.POINTER(sz)], i32),
+    "yb_bn_bwd_reduce": ([vp, C.c_long, vp, C.c_long, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp], i32),
     "yb_bn_bwd_apply": ([vp, C.c_long, vp, C.c_long, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, C.c_long, vp], i32),
     "yb_col_sum": ([vp, C.c_long, C.c_long, i32, i32, vp, vp], i32),
     "yb_col_stats": ([vp, C.c_long, C.c_long, i32, i32, vp, vp, vp], i32),

@@ -93,7 +93,27 @@ struct StreamGeom {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+  float2 f;
+  f = Pack2<T>::unpack(u.x); v[0] = f.x; v[1] = f.y;
+  f = Pack2<T>::unpack(u.y); v[2] = f.x; v[3] = f.y;
+  f = Pack2<T>::unpack(u.z); v[4] = f.x; v[5] = f.y;
+  f = Pack2<T>::unpack(u.w); v[6] = f.x; v[7] = f.y;
+}
+// packed gradient of row r (sum of the 4 copies when the forward stored the row 2x-upsampled)
+template <typename T>
+__device__ __forceinline__ uint4 load_dA_packed(const T* dA, long dA_ld, long r, int c0, const RowGeom& g, int upsample) {
+  if (!upsample) return *reinterpret_cast<const uint4*>(dA + r * dA_ld + c0);
+  float v[8];
+  load_dA(dA, dA_ld, r, c0, g, 1, v);
+  uint4 u;
+  u.x = Pack2<T>::pack(v[0], v[1]); u.y = Pack2<T>::pack(v[2], v[3]);
+  u.z = Pack2<T>::pack(v[4], v[5]); u.w = Pack2<T>::pack(v[6], v[7]);
+  return u;   // (16-bit rounding of the 4-way sum: same precision as the stored gradients)
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 3)
 bn_act_apply_kernel(const T* __restrict__ z, long z_ld, const float* __restrict__ scale, const float* __restrict__ shift,
                     const T* __restrict__ res, long res_ld, T* __restrict__ out, long out_ld, RowGeom g, StreamGeom sg,
                     int leaky, int upsample) {
@@ -104,70 +124,77 @@ bn_act_apply_kernel(const T* __restrict__ z, long z_ld, const float* __restrict_
   for (int j = 0; j < 8; ++j) { sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; }
   const long r0 = blockIdx.x * sg.rows_per_block, r1 = min(r0 + sg.rows_per_block, g.rows);
   for (long rb = r0 + lane_r; rb < r1; rb += 4L * sg.lanes) {
-    float v[4][8], rv[4][8];
+    uint4 zq[4], rq[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const long r = rb + (long)u * sg.lanes;
       if (r < r1) {
-        load8(z + r * z_ld + c0, v[u]);
-        if (res) load8(res + r * res_ld + c0, rv[u]);
+        zq[u] = *reinterpret_cast<const uint4*>(z + r * z_ld + c0);
+        if (res) rq[u] = *reinterpret_cast<const uint4*>(res + r * res_ld + c0);
       }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const long r = rb + (long)u * sg.lanes;
       if (r >= r1) break;
+      float v[8], rv[8];
+      unpack8<T>(zq[u], v);
+      if (res) unpack8<T>(rq[u], rv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float y = fmaf(v[u][j], sc[j], sh[j]);
+        float y = fmaf(v[j], sc[j], sh[j]);
         if (leaky) y = leaky01(y);
-        if (res) y += rv[u][j];
-        v[u][j] = y;
+        if (res) y += rv[j];
+        v[j] = y;
       }
       if (!upsample) {
-        store8(out + r * out_ld + c0, v[u]);
+        store8(out + r * out_ld + c0, v);
       } else {
-        const long b = up_row(r, g.h, g.w);
+        const long bb = up_row(r, g.h, g.w);
         const long W2 = 2L * g.w;
-        store8(out + b * out_ld + c0, v[u]); store8(out + (b + 1) * out_ld + c0, v[u]);
-        store8(out + (b + W2) * out_ld + c0, v[u]); store8(out + (b + W2 + 1) * out_ld + c0, v[u]);
+        store8(out + bb * out_ld + c0, v); store8(out + (bb + 1) * out_ld + c0, v);
+        store8(out + (bb + W2) * out_ld + c0, v); store8(out + (bb + W2 + 1) * out_ld + c0, v);
       }
     }
   }
 }
 
+// Stage 1: every block reduces its row slab to per-channel partial sums.  With a workspace the partials go to
+// [grid][2][c] and the LAST block to finish (ticket counter) adds them up in a fixed order (deterministic, and free of
+// the ~600-deep same-address atomics that dominated the first version); without one they are added atomically.
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 bn_bwd_reduce_kernel(const T* __restrict__ dA, long dA_ld, const T* __restrict__ z, long z_ld,
                      const float* __restrict__ scale, const float* __restrict__ shift,
                      const float* __restrict__ save_mean, const float* __restrict__ save_invstd, RowGeom g,
-                     StreamGeom sg, int leaky, int upsample, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                     StreamGeom sg, int leaky, int upsample, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                     float* __restrict__ partial, unsigned int* __restrict__ ticket) {
   __shared__ float s_g[256][9], s_b[256][9];
+  __shared__ unsigned int s_last;
   const int cvi = threadIdx.x % sg.cv, lane_r = threadIdx.x / sg.cv;
   const int c0 = cvi * 8;
-  float ag[8], ab[8], sc[8], sh[8], mu[8], is[8];
+  float ag[8], ab[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    ag[j] = ab[j] = 0.f;
-    sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; mu[j] = save_mean[c0 + j]; is[j] = save_invstd[c0 + j];
-  }
+  for (int j = 0; j < 8; ++j) ag[j] = ab[j] = 0.f;
   const long r0 = blockIdx.x * sg.rows_per_block, r1 = min(r0 + sg.rows_per_block, g.rows);
   for (long rb = r0 + lane_r; rb < r1; rb += 4L * sg.lanes) {
-    float zv[4][8], dv[4][8];
+    uint4 zq[4], dq[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const long r = rb + (long)u * sg.lanes;
-      if (r < r1) { load8(z + r * z_ld + c0, zv[u]); load_dA(dA, dA_ld, r, c0, g, upsample, dv[u]); }
+      if (r < r1) { zq[u] = *reinterpret_cast<const uint4*>(z + r * z_ld + c0); dq[u] = load_dA_packed(dA, dA_ld, r, c0, g, upsample); }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       if (rb + (long)u * sg.lanes >= r1) break;
+      float zv[8], dv[8];
+      unpack8<T>(zq[u], zv); unpack8<T>(dq[u], dv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float y = fmaf(zv[u][j], sc[j], sh[j]);
-        const float da = (leaky && y <= 0.f) ? 0.1f * dv[u][j] : dv[u][j];
+        const float y = fmaf(zv[j], __ldg(scale + c0 + j), __ldg(shift + c0 + j));
+        const float da = (leaky && y <= 0.f) ? 0.1f * dv[j] : dv[j];
         ab[j] += da;
-        ag[j] = fmaf(da, (zv[u][j] - mu[j]) * is[j], ag[j]);
+        ag[j] = fmaf(da, (zv[j] - __ldg(save_mean + c0 + j)) * __ldg(save_invstd + c0 + j), ag[j]);
       }
     }
   }
@@ -179,13 +206,36 @@ bn_bwd_reduce_kernel(const T* __restrict__ dA, long dA_ld, const T* __restrict__
 #pragma unroll
       for (int j = 0; j < 8; ++j) { ag[j] += s_g[y * sg.cv + cvi][j]; ab[j] += s_b[y * sg.cv + cvi][j]; }
     }
+    if (partial == nullptr) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { atomicAdd(dgamma + c0 + j, ag[j]); atomicAdd(dbeta + c0 + j, ab[j]); }
+      for (int j = 0; j < 8; ++j) { atomicAdd(dgamma + c0 + j, ag[j]); atomicAdd(dbeta + c0 + j, ab[j]); }
+    } else {
+      float* pg = partial + (long)blockIdx.x * 2 * g.c;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { pg[c0 + j] = ag[j]; pg[g.c + c0 + j] = ab[j]; }
+    }
   }
+  if (partial == nullptr) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int c = threadIdx.x; c < g.c; c += 256) {
+    float sg_ = 0.f, sb_ = 0.f;
+    for (unsigned int bk = 0; bk < gridDim.x; ++bk) {
+      sg_ += partial[(long)bk * 2 * g.c + c];
+      sb_ += partial[(long)bk * 2 * g.c + g.c + c];
+    }
+    dgamma[c] = sg_;
+    dbeta[c] = sb_;
+  }
+  if (threadIdx.x == 0) *ticket = 0u;   // ready for the next launch
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 bn_bwd_apply_kernel(const T* __restrict__ dA, long dA_ld, const T* __restrict__ z, long z_ld,
                     const float* __restrict__ gamma, const float* __restrict__ scale, const float* __restrict__ shift,
                     const float* __restrict__ save_mean, const float* __restrict__ save_invstd,
@@ -207,22 +257,23 @@ bn_bwd_apply_kernel(const T* __restrict__ dA, long dA_ld, const T* __restrict__ 
   }
   const long r0 = blockIdx.x * sg.rows_per_block, r1 = min(r0 + sg.rows_per_block, g.rows);
   for (long rb = r0 + lane_r; rb < r1; rb += 4L * sg.lanes) {
-    float zv[4][8], dv[4][8];
+    uint4 zq[4], dq[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const long r = rb + (long)u * sg.lanes;
-      if (r < r1) { load8(z + r * z_ld + c0, zv[u]); load_dA(dA, dA_ld, r, c0, g, upsample, dv[u]); }
+      if (r < r1) { zq[u] = *reinterpret_cast<const uint4*>(z + r * z_ld + c0); dq[u] = load_dA_packed(dA, dA_ld, r, c0, g, upsample); }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const long r = rb + (long)u * sg.lanes;
       if (r >= r1) break;
-      float o[8];
+      float zv[8], dv[8], o[8];
+      unpack8<T>(zq[u], zv); unpack8<T>(dq[u], dv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float y = fmaf(zv[u][j], sc[j], sh[j]);
-        const float da = (leaky && y <= 0.f) ? 0.1f * dv[u][j] : dv[u][j];
-        o[j] = fmaf(k1[j], da, fmaf(k2[j], zv[u][j], k3[j]));
+        const float y = fmaf(zv[j], sc[j], sh[j]);
+        const float da = (leaky && y <= 0.f) ? 0.1f * dv[j] : dv[j];
+        o[j] = fmaf(k1[j], da, fmaf(k2[j], zv[j], k3[j]));
       }
       const long orow = dilate ? up_row(r, g.h, g.w) : r;   // (2p, 2q) of a zero-initialised [n,2h,2w] buffer
       store8(dz + orow * dz_ld + c0, o);
@@ -313,25 +364,37 @@ extern "C" int yb_bn_act_apply(const void* z, long z_ld, const float* scale, con
   return YB_OK;
 }
 
+extern "C" int yb_bn_bwd_reduce_workspace_bytes(size_t* bytes) {
+  YB_REQUIRE(bytes, "bn_bwd_reduce_workspace_bytes: null pointer");
+  *bytes = 256 + (size_t)num_sms() * 4 * 2 * 2048 * sizeof(float);
+  return YB_OK;
+}
+
 extern "C" int yb_bn_bwd_reduce(const void* dA, long dA_ld, const void* z, long z_ld, const float* scale,
                                 const float* shift, const float* save_mean, const float* save_invstd, int n, int h,
                                 int w, int c, int dtype, int leaky, int upsample2x, float* dgamma, float* dbeta,
-                                void* stream) {
+                                void* workspace, void* stream) {
   YB_BN_COMMON_CHECK("bn_bwd_reduce");
   YB_REQUIRE(dA && z && scale && shift && save_mean && save_invstd && dgamma && dbeta, "bn_bwd_reduce: null pointer");
   RowGeom g{(long)n * h * w, h, w, c};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int grid;
   const StreamGeom sg = stream_geom(g.rows, c, &grid);
-  YB_CUDA(cudaMemsetAsync(dgamma, 0, c * 4, st));
-  YB_CUDA(cudaMemsetAsync(dbeta, 0, c * 4, st));
+  // workspace (zero-initialised once by the caller): [0,256) ticket counter, then per-block partials
+  unsigned int* ticket = static_cast<unsigned int*>(workspace);
+  float* partial = workspace ? reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + 256) : nullptr;
+  if (!workspace) {
+    YB_CUDA(cudaMemsetAsync(dgamma, 0, c * 4, st));
+    YB_CUDA(cudaMemsetAsync(dbeta, 0, c * 4, st));
+  }
   if (dtype == YB_F16)
     bn_bwd_reduce_kernel<__half><<<grid, 256, 0, st>>>((const __half*)dA, dA_ld, (const __half*)z, z_ld, scale, shift,
-                                                      save_mean, save_invstd, g, sg, leaky, upsample2x, dgamma, dbeta);
+                                                      save_mean, save_invstd, g, sg, leaky, upsample2x, dgamma, dbeta,
+                                                      partial, ticket);
   else
     bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dA, dA_ld, (const __nv_bfloat16*)z,
                                                              z_ld, scale, shift, save_mean, save_invstd, g, sg, leaky,
-                                                             upsample2x, dgamma, dbeta);
+                                                             upsample2x, dgamma, dbeta, partial, ticket);
   YB_CUDA(cudaGetLastError());
   return YB_OK;
 }

@@ -69,7 +69,9 @@ struct ThinCfg {
   static constexpr int A_BYTES = STEM ? 128 * A_PITCH : 0;
   static constexpr int O_PITCH = COUT * 2 + 16;                 // output staging [128 px][COUT]
   static constexpr int O_BYTES = 128 * O_PITCH;
-  static constexpr int SMEM = ((HALO_BYTES + 127) / 128) * 128 + W_BYTES + A_BYTES + O_BYTES + 128;
+  // the output staging tile reuses the halo tile's storage (the halo is dead once the MMAs are done)
+  static constexpr int HALO_OR_OUT = (HALO_BYTES > O_BYTES ? HALO_BYTES : O_BYTES);
+  static constexpr int SMEM = ((HALO_OR_OUT + 127) / 128) * 128 + W_BYTES + A_BYTES + 128;
 };
 
 template <typename T, int COUT, int STRIDE, bool STEM>
@@ -78,9 +80,9 @@ conv_thin_kernel(const ThinParams p) {
   using C = ThinCfg<T, COUT, STRIDE, STEM>;
   extern __shared__ __align__(128) uint8_t tsm[];
   uint8_t* s_halo = tsm;
-  uint8_t* s_w = tsm + ((C::HALO_BYTES + 127) / 128) * 128;
+  uint8_t* s_w = tsm + ((C::HALO_OR_OUT + 127) / 128) * 128;
   uint8_t* s_a = s_w + C::W_BYTES;
-  uint8_t* s_o = s_a + C::A_BYTES;
+  uint8_t* s_o = tsm;                                             // aliases s_halo
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   // ---- weights: resident for the whole (persistent) CTA ----
@@ -183,6 +185,7 @@ conv_thin_kernel(const ThinParams p) {
         }
       }
     }
+    __syncthreads();                                            // every warp is done reading the halo tile (s_o aliases it)
     // ---- epilogue: scale/shift/leaky -> shared staging ----
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi) {

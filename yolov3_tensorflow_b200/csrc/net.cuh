@@ -58,6 +58,7 @@ struct yb_net {
   size_t dfm_off[3] = {0, 0, 0};     // 16-bit [rows, 256] loss gradients of the three detection maps
   size_t stats_off = 0, stats_bytes = 0;   // per-step zeroed BN sums
   size_t lossws_off = 0, lossws_bytes = 0;
+  size_t bnws_off = 0, bnws_bytes = 0;     // two-stage BN-backward reduction scratch (zeroed at bind)
   size_t ones_off = 0, zeros_off = 0;      // fp32 [1024] constants (param arena)
   size_t grad_off = 0, vel_off = 0; long grad_count = 0;   // flat fp32 gradient / velocity (param arena)
   size_t opt_tensors_off = 0, opt_chunks_off = 0, opt_norm_off = 0; int num_opt_tensors = 0, num_opt_chunks = 0;

@@ -73,6 +73,8 @@ void train_layout(yb_net* net) {
     lw = std::max(lw, b);
   }
   net->lossws_off = o; net->lossws_bytes = lw; o = al256(o + lw);
+  yb_bn_bwd_reduce_workspace_bytes(&net->bnws_bytes);
+  net->bnws_off = o; o = al256(o + net->bnws_bytes);
   net->act_bytes = o;
 
   // ---- parameter arena ----
@@ -140,6 +142,7 @@ int train_bind(yb_net* net) {
   YB_CUDA(cudaMemset(net->par + net->zeros_off, 0, 1024 * 4));
   YB_CUDA(cudaMemset(net->par + net->vel_off, 0, (size_t)net->grad_count * 4));
   YB_CUDA(cudaMemset(net->par + net->grad_off, 0, (size_t)net->grad_count * 4));
+  YB_CUDA(cudaMemset(net->act + net->bnws_off, 0, net->bnws_bytes));
   const float* ones = fpar(net, net->ones_off);
   const float* zeros = fpar(net, net->zeros_off);
   for (auto& L : net->layers) {
@@ -305,7 +308,7 @@ extern "C" int yb_net_train_fwd_bwd(yb_net* net, const float* images, const floa
       const long dA_ld = net->bufs[L.out.buf].ld;
       rc = yb_bn_bwd_reduce(dA, dA_ld, net->act + L.z_off, L.info.cout, fact(net, L.st_scale), fact(net, L.st_shift),
                             fact(net, L.st_mean), fact(net, L.st_invstd), n, L.info.out_h, L.info.out_w, L.info.cout, dt, 1,
-                            L.upsample ? 1 : 0, dgamma, dbeta, stream);
+                            L.upsample ? 1 : 0, dgamma, dbeta, net->act + net->bnws_off, stream);
       if (rc) return rc;
       rc = yb_bn_bwd_apply(dA, dA_ld, net->act + L.z_off, L.info.cout, fpar(net, L.gamma), fact(net, L.st_scale),
                            fact(net, L.st_shift), fact(net, L.st_mean), fact(net, L.st_invstd), dgamma, dbeta, n,
