@@ -43,7 +43,7 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BN;  // power of two >= 32 for BN in {64,128,256}
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4 * STAGE_FLOATS * 4 + 2 * BN * 4;
+  static constexpr int SMEM_BYTES = SMEM_BUDGET + 1024 /*align*/ + 256 /*barriers*/ + 4 * STAGE_FLOATS * 4 + 2 * BN * 4;
   static constexpr uint32_t SWIZZLE = (BK == 64) ? 2u : 4u;   // UMMA layout_type: 128B / 64B
   static constexpr uint32_t SBO = 8 * BK * 2;                  // bytes between 8-row groups
 };
@@ -198,15 +198,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   using C = Cfg<BN, BK>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int kb_per_tap_ = p.cin / BK;
+  const int num_kb_ = p.ksize * p.ksize * kb_per_tap_;
+  // operand ring: [nst x A][nst x B], or with resident weights [nst x A][num_kb x B] (B loaded once per CTA)
+  int nst = C::STAGES;
+  if (p.b_resident) {
+    nst = (SMEM_BUDGET - num_kb_ * C::B_BYTES) / C::A_BYTES;
+    if (nst > 8) nst = 8;
+  }
   uint8_t* sA = smem;
-  uint8_t* sB = smem + C::STAGES * C::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
-  uint64_t* full_bar = bars;                       // [STAGES] TMA -> MMA
-  uint64_t* empty_bar = bars + C::STAGES;          // [STAGES] MMA -> TMA
-  uint64_t* tfull_bar = bars + 2 * C::STAGES;      // [2] MMA -> epilogue
-  uint64_t* tempty_bar = bars + 2 * C::STAGES + 2; // [2] epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
-  float* stage_base = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
+  uint8_t* sB = smem + nst * C::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BUDGET);
+  uint64_t* full_bar = bars;                       // [<=8] TMA -> MMA
+  uint64_t* empty_bar = bars + 8;                  // [<=8] MMA -> TMA
+  uint64_t* tfull_bar = bars + 16;                 // [2] MMA -> epilogue
+  uint64_t* tempty_bar = bars + 18;                // [2] epilogue -> MMA
+  uint64_t* bres_bar = bars + 20;                  // resident weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  float* stage_base = reinterpret_cast<float*>(smem + SMEM_BUDGET + 256);
   float* s_stat = stage_base + 4 * STAGE_FLOATS;   // [2][BN] per-CTA column sums / sums of squares
 
   const int warp = threadIdx.x >> 5;
@@ -218,7 +227,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int i = 0; i < C::STAGES; ++i) {
+    for (int i = 0; i < 8; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
@@ -226,6 +235,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
     }
+    mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
@@ -238,6 +248,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
+    if (p.b_resident && lane == 0 && (int)blockIdx.x < num_tiles) {
+      mbar_arrive_expect_tx(bres_bar, (uint32_t)(num_kb * C::B_BYTES));
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int tap = kb / kb_per_tap;
+        tma_load_2d(sB + kb * C::B_BYTES, &tmB, bres_bar, tap * p.cin + (kb - tap * kb_per_tap) * BK, 0);
+      }
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m_idx, n_idx;
       tile_coords(p, tile, m_idx, n_idx);
@@ -254,17 +271,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int c0 = (kb - tap * kb_per_tap) * BK;
         if (lane == 0) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          mbar_arrive_expect_tx(&full_bar[stage], p.b_resident ? C::A_BYTES : C::STAGE_BYTES);
           if (p.im2col) {
             tma_load_im2col_4d(sA + stage * C::A_BYTES, &tmA, &full_bar[stage], c0, w_base, h_base, img,
                                (uint16_t)(tap % p.ksize), (uint16_t)(tap / p.ksize));
           } else {
             tma_load_2d(sA + stage * C::A_BYTES, &tmA, &full_bar[stage], c0, m0);
           }
-          tma_load_2d(sB + stage * C::B_BYTES, &tmB, &full_bar[stage], tap * p.cin + c0, n0);
+          if (!p.b_resident) tma_load_2d(sB + stage * C::B_BYTES, &tmB, &full_bar[stage], tap * p.cin + c0, n0);
         }
         __syncwarp();
-        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == nst) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -273,6 +290,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
+    if (p.b_resident && lane == 0 && (int)blockIdx.x < num_tiles) mbar_wait(bres_bar, 0);
+    __syncwarp();
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -285,7 +304,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * C::A_BYTES);
-          const uint32_t b_addr = smem_u32(sB + stage * C::B_BYTES);
+          const uint32_t b_addr = smem_u32(sB + (p.b_resident ? kb : stage) * C::B_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adesc = make_kmajor_desc(a_addr + k * UMMA_K * 2, C::SBO, C::SWIZZLE);
@@ -296,7 +315,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
         }
         __syncwarp();
-        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == nst) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -944,6 +963,12 @@ int conv_prepare(const yb_conv_desc* d, const void* x, const void* w_packed, con
   p->mc_m = mc_m; p->mc_n = mc_n;
   { const char* dbg = getenv("YB_CONV_DBG"); p->dbg = dbg ? atoi(dbg) : 0; }
   const int bn = two ? conv_block_n2(cout_pad) : conv_block_n(cout_pad);
+  {
+    // resident weights (1-CTA kernel): one n-tile, and the [BN, K] tile leaves room for >= 3 A stages
+    const long b_bytes = (long)d->ksize * d->ksize * d->cin * bn * 2;
+    const char* br = getenv("YB_CONV_BRES");
+    p->b_resident = (!two && cout_pad == bn && SMEM_BUDGET - b_bytes >= 3L * BLOCK_M * bk * 2 && !(br && br[0] == '0')) ? 1 : 0;
+  }
   p->cout = d->cout; p->cin = d->cin; p->ksize = d->ksize; p->stride = d->stride; p->pad = pad;
   p->im2col = d->ksize == 3;
   p->num_m_tiles = ceil_div(p->M, two ? 2 * BLOCK_M : BLOCK_M);
