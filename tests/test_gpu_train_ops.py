@@ -27,6 +27,7 @@ def _rel(a, b):
     (2, 26, 26, 128, 256, 3, 1, 256),     # input is a channel slice; 2 co tiles
     (2, 13, 13, 256, 255, 1, 1, 0),       # detection head: cout=255, dz_ld=256
     (2, 52, 52, 64, 128, 3, 2, 0),        # stride 2 (plain dz)
+    (2, 32, 32, 32, 64, 3, 2, 0),         # layer-1 shape: cin=32, stride 2, all 9 taps in one CTA
 ])
 @pytest.mark.parametrize("dtype", [torch.bfloat16])
 def test_wgrad_matches_autograd(n, h, w, cin, cout, k, s, in_extra, dtype):

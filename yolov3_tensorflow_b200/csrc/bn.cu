@@ -100,18 +100,6 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
   f = Pack2<T>::unpack(u.z); v[4] = f.x; v[5] = f.y;
   f = Pack2<T>::unpack(u.w); v[6] = f.x; v[7] = f.y;
 }
-// packed gradient of row r (sum of the 4 copies when the forward stored the row 2x-upsampled)
-template <typename T>
-__device__ __forceinline__ uint4 load_dA_packed(const T* dA, long dA_ld, long r, int c0, const RowGeom& g, int upsample) {
-  if (!upsample) return *reinterpret_cast<const uint4*>(dA + r * dA_ld + c0);
-  float v[8];
-  load_dA(dA, dA_ld, r, c0, g, 1, v);
-  uint4 u;
-  u.x = Pack2<T>::pack(v[0], v[1]); u.y = Pack2<T>::pack(v[2], v[3]);
-  u.z = Pack2<T>::pack(v[4], v[5]); u.w = Pack2<T>::pack(v[6], v[7]);
-  return u;   // (16-bit rounding of the 4-way sum: same precision as the stored gradients)
-}
-
 template <typename T>
 __global__ void __launch_bounds__(256, 3)
 bn_act_apply_kernel(const T* __restrict__ z, long z_ld, const float* __restrict__ scale, const float* __restrict__ shift,
@@ -182,13 +170,15 @@ bn_bwd_reduce_kernel(const T* __restrict__ dA, long dA_ld, const T* __restrict__
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const long r = rb + (long)u * sg.lanes;
-      if (r < r1) { zq[u] = *reinterpret_cast<const uint4*>(z + r * z_ld + c0); dq[u] = load_dA_packed(dA, dA_ld, r, c0, g, upsample); }
+      if (r < r1) { zq[u] = *reinterpret_cast<const uint4*>(z + r * z_ld + c0); if (!upsample) dq[u] = *reinterpret_cast<const uint4*>(dA + r * dA_ld + c0); }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       if (rb + (long)u * sg.lanes >= r1) break;
       float zv[8], dv[8];
-      unpack8<T>(zq[u], zv); unpack8<T>(dq[u], dv);
+      unpack8<T>(zq[u], zv);
+      if (!upsample) unpack8<T>(dq[u], dv);
+      else load_dA(dA, dA_ld, rb + (long)u * sg.lanes, c0, g, 1, dv);   // fp32 sum of the 4 upsampled copies
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float y = fmaf(zv[j], __ldg(scale + c0 + j), __ldg(shift + c0 + j));
@@ -261,14 +251,16 @@ bn_bwd_apply_kernel(const T* __restrict__ dA, long dA_ld, const T* __restrict__ 
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const long r = rb + (long)u * sg.lanes;
-      if (r < r1) { zq[u] = *reinterpret_cast<const uint4*>(z + r * z_ld + c0); dq[u] = load_dA_packed(dA, dA_ld, r, c0, g, upsample); }
+      if (r < r1) { zq[u] = *reinterpret_cast<const uint4*>(z + r * z_ld + c0); if (!upsample) dq[u] = *reinterpret_cast<const uint4*>(dA + r * dA_ld + c0); }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const long r = rb + (long)u * sg.lanes;
       if (r >= r1) break;
       float zv[8], dv[8], o[8];
-      unpack8<T>(zq[u], zv); unpack8<T>(dq[u], dv);
+      unpack8<T>(zq[u], zv);
+      if (!upsample) unpack8<T>(dq[u], dv);
+      else load_dA(dA, dA_ld, r, c0, g, 1, dv);   // fp32 sum of the 4 upsampled copies
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float y = fmaf(zv[j], sc[j], sh[j]);

@@ -271,14 +271,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int c0 = (kb - tap * kb_per_tap) * BK;
         if (lane == 0) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], p.b_resident ? C::A_BYTES : C::STAGE_BYTES);
-          if (p.im2col) {
-            tma_load_im2col_4d(sA + stage * C::A_BYTES, &tmA, &full_bar[stage], c0, w_base, h_base, img,
-                               (uint16_t)(tap % p.ksize), (uint16_t)(tap / p.ksize));
-          } else {
-            tma_load_2d(sA + stage * C::A_BYTES, &tmA, &full_bar[stage], c0, m0);
+          const bool ld_a = !(p.dbg & 1), ld_b = !p.b_resident && !(p.dbg & 2);
+          if (ld_a || ld_b) mbar_arrive_expect_tx(&full_bar[stage], (ld_a ? C::A_BYTES : 0) + (ld_b ? C::B_BYTES : 0));
+          else mbar_arrive(&full_bar[stage]);
+          if (ld_a) {
+            if (p.im2col) {
+              tma_load_im2col_4d(sA + stage * C::A_BYTES, &tmA, &full_bar[stage], c0, w_base, h_base, img,
+                                 (uint16_t)(tap % p.ksize), (uint16_t)(tap / p.ksize));
+            } else {
+              tma_load_2d(sA + stage * C::A_BYTES, &tmA, &full_bar[stage], c0, m0);
+            }
           }
-          if (!p.b_resident) tma_load_2d(sB + stage * C::B_BYTES, &tmB, &full_bar[stage], tap * p.cin + c0, n0);
+          if (ld_b) tma_load_2d(sB + stage * C::B_BYTES, &tmB, &full_bar[stage], tap * p.cin + c0, n0);
         }
         __syncwarp();
         if (++stage == nst) { stage = 0; phase ^= 1; }
@@ -309,7 +313,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adesc = make_kmajor_desc(a_addr + k * UMMA_K * 2, C::SBO, C::SWIZZLE);
             const uint64_t bdesc = make_kmajor_desc(b_addr + k * UMMA_K * 2, C::SBO, C::SWIZZLE);
-            umma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+            if (!(p.dbg & 4)) umma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
           }
           umma_commit(&empty_bar[stage]);                       // smem slot reusable once these MMAs retire
           if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
@@ -341,8 +345,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_fence_after();
-      epilogue_tile<T, BN>(p, m0 + quarter * 32 + lane, n0, tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN, lane,
-                           stage_base + (warp - 2) * STAGE_FLOATS, s_stat);
+      if (!(p.dbg & 8))
+        epilogue_tile<T, BN>(p, m0 + quarter * 32 + lane, n0, tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN, lane,
+                             stage_base + (warp - 2) * STAGE_FLOATS, s_stat);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -967,7 +972,7 @@ int conv_prepare(const yb_conv_desc* d, const void* x, const void* w_packed, con
     // resident weights (1-CTA kernel): one n-tile, and the [BN, K] tile leaves room for >= 3 A stages
     const long b_bytes = (long)d->ksize * d->ksize * d->cin * bn * 2;
     const char* br = getenv("YB_CONV_BRES");
-    p->b_resident = (!two && cout_pad == bn && SMEM_BUDGET - b_bytes >= 3L * BLOCK_M * bk * 2 && !(br && br[0] == '0')) ? 1 : 0;
+    p->b_resident = (!two && cout_pad == bn && SMEM_BUDGET - b_bytes >= 3L * BLOCK_M * bk * 2 && (br && br[0] == '1')) ? 1 : 0;   // opt-in: measured no gain (profiles/r01_i)
   }
   p->cout = d->cout; p->cin = d->cin; p->ksize = d->ksize; p->stride = d->stride; p->pad = pad;
   p->im2col = d->ksize == 3;

@@ -9,6 +9,9 @@
 //                zero-filled border/stride handling as the forward conv — also MN-major.
 //   D = fp32 in TMEM; every CTA reduces one pixel range (split-K) of one output tile and
 //       adds it into the fp32 gradient with vector atomics.
+//   A CTA accumulates TP filter taps at once (TP x BNW TMEM columns: one kernel row of a 3x3 filter, or all 9 taps
+//   when cin = 32): the dz tile is loaded once per TP taps instead of once per tap — the first version re-read dz
+//   9x and, on the 208x208 / 104x104 layers whose dz + x exceed the L2, ran at HBM speed (profiles/r01_i).
 // Replaces the wgrad half of TF autodiff for slim.conv2d (train.py:112).
 #include <cudaTypedefs.h>
 
@@ -39,15 +42,17 @@ struct WgradParams {
   float* dw;           // [cout, k*k*cin] fp32, accumulated
 };
 
-template <int BNW>
+template <int BNW, int TP>
 struct WCfg {
   static constexpr int BCH = BNW < 64 ? BNW : 64;            // channels per im2col box / swizzle row
   static constexpr int NB = BNW / BCH;                       // boxes per stage for B
   static constexpr int A_BYTES = WG_BM * WG_BKP * 2;         // 2 boxes of 64co x 64px
-  static constexpr int B_BYTES = BNW * WG_BKP * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int B_BYTES = BNW * WG_BKP * 2;             // one tap
+  static constexpr int STAGE_BYTES = A_BYTES + TP * B_BYTES;
   static constexpr int STAGES = (192 * 1024 / STAGE_BYTES) > 8 ? 8 : (192 * 1024 / STAGE_BYTES);
-  static constexpr int TMEM_COLS = BNW < 32 ? 32 : BNW;
+  static constexpr int ACC_COLS = TP * BNW;
+  static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
+  static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
   static constexpr uint32_t B_ROW = BCH * 2;                 // bytes per pixel row of a B box
   static constexpr uint32_t B_SWZ = BCH == 64 ? 2u : 4u;     // 128B / 64B swizzle
@@ -66,14 +71,14 @@ __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t saddr, uint32_t l
   return d;
 }
 
-template <typename T, int BNW>
+template <typename T, int BNW, int TP>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgradParams p) {
-  using C = WCfg<BNW>;
+  using C = WCfg<BNW, TP>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
-  uint8_t* sB = smem + C::STAGES * C::A_BYTES;
+  uint8_t* sB = smem + C::STAGES * C::A_BYTES;              // [stage][tap in group][B_BYTES]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::STAGES;
@@ -81,8 +86,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // tile coordinates: blockIdx.x = pixel split, blockIdx.y = n tile (tap, ci chunk), blockIdx.z = co tile
-  const int tap = blockIdx.y / p.n_chunks;
+  // tile coordinates: blockIdx.x = pixel split, blockIdx.y = n tile (tap group, ci chunk), blockIdx.z = co tile
+  const int tap0 = (blockIdx.y / p.n_chunks) * TP;
   const int ci0 = (blockIdx.y % p.n_chunks) * BNW;
   const int co0 = blockIdx.z * WG_BM;
   const int kb0 = blockIdx.x * p.kb_per_split;
@@ -111,7 +116,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int q = (int)(p0 % p.wo), pp = (int)((p0 / p.wo) % p.ho), img = (int)(p0 / ((long)p.wo * p.ho));
           mbar_wait(&empty_bar[stage], phase ^ 1);
           const bool two_a = co0 + 64 < p.cout;   // second 64-channel block exists (else its rows are masked anyway)
-          mbar_arrive_expect_tx(&full_bar[stage], C::B_BYTES + (two_a ? C::A_BYTES : C::A_BYTES / 2));
+          mbar_arrive_expect_tx(&full_bar[stage], TP * C::B_BYTES + (two_a ? C::A_BYTES : C::A_BYTES / 2));
           uint8_t* a = sA + stage * C::A_BYTES;
           if (p.a_dilated) {
             tma_load_im2col_4d(a, &tmA, &full_bar[stage], co0, 2 * q, 2 * pp, img, 0, 0);
@@ -120,12 +125,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tma_load_2d(a, &tmA, &full_bar[stage], co0, (int)p0);
             if (two_a) tma_load_2d(a + WG_BKP * 128, &tmA, &full_bar[stage], co0 + 64, (int)p0);
           }
-          uint8_t* b = sB + stage * C::B_BYTES;
 #pragma unroll
-          for (int j = 0; j < C::NB; ++j)
-            tma_load_im2col_4d(b + j * WG_BKP * C::B_ROW, &tmB, &full_bar[stage], ci0 + j * C::BCH,
-                               q * p.stride - p.pad, pp * p.stride - p.pad, img, (uint16_t)(tap % p.ksize),
-                               (uint16_t)(tap / p.ksize));
+          for (int t = 0; t < TP; ++t) {
+            uint8_t* b = sB + (stage * TP + t) * C::B_BYTES;
+            const int tap = tap0 + t;
+#pragma unroll
+            for (int j = 0; j < C::NB; ++j)
+              tma_load_im2col_4d(b + j * WG_BKP * C::B_ROW, &tmB, &full_bar[stage], ci0 + j * C::BCH,
+                                 q * p.stride - p.pad, pp * p.stride - p.pad, img, (uint16_t)(tap % p.ksize),
+                                 (uint16_t)(tap / p.ksize));
+          }
         }
         __syncwarp();
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -139,12 +148,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * C::A_BYTES);
-          const uint32_t b_addr = smem_u32(sB + stage * C::B_BYTES);
 #pragma unroll
-          for (int k = 0; k < WG_BKP / 16; ++k) {
-            const uint64_t adesc = make_mnmajor_desc(a_addr + k * 16 * 128, WG_BKP * 128, 1024, 2u);
-            const uint64_t bdesc = make_mnmajor_desc(b_addr + k * 16 * C::B_ROW, WG_BKP * C::B_ROW, 8 * C::B_ROW, C::B_SWZ);
-            umma_f16(tmem_base, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          for (int t = 0; t < TP; ++t) {
+            const uint32_t b_addr = smem_u32(sB + (stage * TP + t) * C::B_BYTES);
+#pragma unroll
+            for (int k = 0; k < WG_BKP / 16; ++k) {
+              const uint64_t adesc = make_mnmajor_desc(a_addr + k * 16 * 128, WG_BKP * 128, 1024, 2u);
+              const uint64_t bdesc = make_mnmajor_desc(b_addr + k * 16 * C::B_ROW, WG_BKP * C::B_ROW, 8 * C::B_ROW, C::B_SWZ);
+              umma_f16(tmem_base + t * BNW, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);
           if (kb == kb1 - 1) umma_commit(done_bar);
@@ -159,18 +171,21 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(done_bar, 0);
       tcgen05_fence_after();
       const long ktot = (long)p.ksize * p.ksize * p.cin;
-      float* dst = p.dw + (long)co * ktot + (long)tap * p.cin + ci0;
 #pragma unroll 1
-      for (int ch = 0; ch < BNW / 32; ++ch) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + ch * 32, r);
-        tmem_ld_wait();
-        if (co < p.cout) {
+      for (int t = 0; t < TP; ++t) {
+        float* dst = p.dw + (long)co * ktot + (long)(tap0 + t) * p.cin + ci0;
+#pragma unroll 1
+        for (int ch = 0; ch < BNW / 32; ++ch) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + t * BNW + ch * 32, r);
+          tmem_ld_wait();
+          if (co < p.cout) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-            atomicAdd(reinterpret_cast<float4*>(dst + ch * 32 + 4 * j), v);
+            for (int j = 0; j < 8; ++j) {
+              float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                     __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+              atomicAdd(reinterpret_cast<float4*>(dst + ch * 32 + 4 * j), v);
+            }
           }
         }
       }
@@ -184,11 +199,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
-template <typename T, int BNW>
+template <typename T, int BNW, int TP>
 static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, const WgradParams& p, dim3 grid, cudaStream_t st) {
-  using C = WCfg<BNW>;
+  using C = WCfg<BNW, TP>;
   static bool attr_done = false;
-  auto kern = conv_wgrad_kernel<T, BNW>;
+  auto kern = conv_wgrad_kernel<T, BNW, TP>;
   if (!attr_done) {
     YB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_done = true;
@@ -257,8 +272,12 @@ extern "C" int yb_conv2d_wgrad(const yb_conv_desc* d, const void* x, const void*
   p.n_chunks = d->cin / bnw;
   p.dw = dw;
   const int taps = d->ksize * d->ksize;
+  // taps accumulated per CTA: all 9 for cin = 32 (288 TMEM columns), one kernel row otherwise; 1x1 convs have one tap
+  const char* tpf = getenv("YB_WGRAD_TP");     // "1": one tap per CTA (the first version; A/B testing)
+  const int tp = (taps == 1 || (tpf && tpf[0] == '1')) ? 1 : (bnw == 32 ? 9 : 3);
+  const int tap_groups = taps / tp;
   const int co_tiles = ceil_div(d->cout, WG_BM);
-  const long tiles = (long)taps * p.n_chunks * co_tiles;
+  const long tiles = (long)tap_groups * p.n_chunks * co_tiles;
   long splits = ((long)num_sms() * 2 + tiles - 1) / tiles;
   if (splits > p.num_kb) splits = p.num_kb;
   if (splits < 1) splits = 1;
@@ -277,12 +296,14 @@ extern "C" int yb_conv2d_wgrad(const yb_conv_desc* d, const void* x, const void*
   rc = make_tmap_im2col_px(&tmB, x, d->dtype, d->n, d->h, d->w, d->cin, d->in_ld, d->ksize, d->stride, p.pad,
                            bnw < 64 ? bnw : 64, WG_BKP);
   if (rc) return rc;
-  dim3 grid((unsigned)splits, (unsigned)(taps * p.n_chunks), (unsigned)co_tiles);
+  dim3 grid((unsigned)splits, (unsigned)(tap_groups * p.n_chunks), (unsigned)co_tiles);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define YB_WG(T)                                                         \
-  if (bnw == 128) return launch_wgrad<T, 128>(tmA, tmB, p, grid, st);   \
-  if (bnw == 64) return launch_wgrad<T, 64>(tmA, tmB, p, grid, st);     \
-  return launch_wgrad<T, 32>(tmA, tmB, p, grid, st);
+#define YB_WG(T)                                                                       \
+  if (bnw == 128) return tp == 3 ? launch_wgrad<T, 128, 3>(tmA, tmB, p, grid, st)     \
+                                 : launch_wgrad<T, 128, 1>(tmA, tmB, p, grid, st);   \
+  if (bnw == 64) return tp == 3 ? launch_wgrad<T, 64, 3>(tmA, tmB, p, grid, st)       \
+                                : launch_wgrad<T, 64, 1>(tmA, tmB, p, grid, st);     \
+  return tp == 9 ? launch_wgrad<T, 32, 9>(tmA, tmB, p, grid, st) : launch_wgrad<T, 32, 1>(tmA, tmB, p, grid, st);
   if (d->dtype == YB_F16) { YB_WG(__half) }
   YB_WG(__nv_bfloat16)
 #undef YB_WG
