@@ -115,6 +115,9 @@ int yb_conv2d_wgrad(const yb_conv_desc* d, const void* x, const void* dz, int dz
                     void* stream);
 /* wgrad of the 3-channel stem: x float32 [n,h,w,3], dz [n*h*w, 32] 16-bit -> dw [32,3,3,3] accumulated. */
 int yb_stem_conv_wgrad(const float* x, const void* dz, int dtype, int n, int h, int w, float* dw, void* stream);
+/* Same contract on the warp-level tensor path (image split into 16-bit head + remainder: float32-exact to ~1e-5);
+ * yb_stem_conv_wgrad dispatches to it by default. */
+int yb_stem_conv_wgrad_tc(const float* x, const void* dz, int dtype, int n, int h, int w, float* dw, void* stream);
 /* dgrad weights: dst[ci][r][s][co] = w_ohwi[co][k-1-r][k-1-s][ci] (k_cout >= cout, cin_pad >= cin zero-padded):
  * the data gradient of a stride-1 conv is yb_conv2d_fwd(dz, dst) (stride-2: on the zero-inserted dz). */
 int yb_pack_dgrad_weights(const float* w_ohwi, int cout, int cin, int ksize, int k_cout, int cin_pad, int dtype,

@@ -181,3 +181,13 @@ def test_col_sum_and_stem_wgrad():
     wt = torch.zeros((32, 3, 3, 3), device="cuda", requires_grad=True)
     F.conv2d(img.permute(0, 3, 1, 2), wt, None, padding=1).backward(dz.float().permute(0, 3, 1, 2))
     assert _rel(dw, wt.grad.permute(0, 2, 3, 1)) < 1e-4
+    # tensor-path kernel explicitly, fp16 gradients, a size that is not a multiple of the 8x16 tile
+    n, h, w = 3, 20, 28
+    img = torch.rand((n, h, w, 3), generator=g).cuda()
+    for dt, code in ((torch.float16, L.YB_F16), (torch.bfloat16, L.YB_BF16)):
+        dz = (torch.randn((n, h, w, 32), generator=g) * 0.1).to(dt).cuda()
+        dw = torch.zeros((32, 3, 3, 3), device="cuda")
+        L.check(L.lib.yb_stem_conv_wgrad_tc(L.ptr(img), L.ptr(dz), code, n, h, w, L.ptr(dw), L.stream_handle()), "stem_wgrad_tc")
+        wt = torch.zeros((32, 3, 3, 3), device="cuda", requires_grad=True)
+        F.conv2d(img.permute(0, 3, 1, 2), wt, None, padding=1).backward(dz.float().permute(0, 3, 1, 2))
+        assert _rel(dw, wt.grad.permute(0, 2, 3, 1)) < 1e-4

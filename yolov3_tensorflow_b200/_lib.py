@@ -52,6 +52,7 @@ _SIGS = {
     "yb_bn_fold": ([vp, vp, vp, vp, i32, f32, vp, vp, vp], i32),
     "yb_conv2d_wgrad": ([C.POINTER(ConvDesc), vp, vp, i32, i32, vp, vp], i32),
     "yb_stem_conv_wgrad": ([vp, vp, i32, i32, i32, i32, vp, vp], i32),
+    "yb_stem_conv_wgrad_tc": ([vp, vp, i32, i32, i32, i32, vp, vp], i32),
     "yb_pack_dgrad_weights": ([vp, i32, i32, i32, i32, i32, i32, vp, vp], i32),
     "yb_bn_finalize": ([vp, vp, C.c_long, i32, vp, vp, f32, f32, vp, vp, vp, vp, vp, vp, vp], i32),
     "yb_bn_act_apply": ([vp, C.c_long, vp, vp, vp, C.c_long, vp, C.c_long, i32, i32, i32, i32, i32, i32, i32, vp], i32),

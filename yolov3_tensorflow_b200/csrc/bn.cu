@@ -147,9 +147,12 @@ bn_act_apply_kernel(const T* __restrict__ z, long z_ld, const float* __restrict_
   }
 }
 
-// Stage 1: every block reduces its row slab to per-channel partial sums.  With a workspace the partials go to
-// [grid][2][c] and the LAST block to finish (ticket counter) adds them up in a fixed order (deterministic, and free of
-// the ~600-deep same-address atomics that dominated the first version); without one they are added atomically.
+// Stage 1: every block reduces its row slab to per-channel partial sums.  With a (zero-initialised) workspace the
+// partials are added into one of BN_SLOTS rows [slot][2][c] and the LAST block to finish (ticket counter) sums the
+// rows, writes dgamma/dbeta and zeroes the rows again; without one they are added atomically to dgamma/dbeta
+// (~600-deep same-address atomics: slow, kept for callers without a workspace).
+static constexpr int BN_SLOTS = 16;
+
 template <typename T>
 __global__ void __launch_bounds__(256, 3)
 bn_bwd_reduce_kernel(const T* __restrict__ dA, long dA_ld, const T* __restrict__ z, long z_ld,
@@ -200,9 +203,11 @@ bn_bwd_reduce_kernel(const T* __restrict__ dA, long dA_ld, const T* __restrict__
 #pragma unroll
       for (int j = 0; j < 8; ++j) { atomicAdd(dgamma + c0 + j, ag[j]); atomicAdd(dbeta + c0 + j, ab[j]); }
     } else {
-      float* pg = partial + (long)blockIdx.x * 2 * g.c;
+      // BN_SLOTS partial rows (zero on entry): ~grid/BN_SLOTS-deep atomics per address instead of grid-deep, and the
+      // final pass reads BN_SLOTS x 2c floats instead of grid x 2c (which made one SM stream megabytes: r01_i)
+      float* pg = partial + (long)(blockIdx.x % BN_SLOTS) * 2 * g.c;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { pg[c0 + j] = ag[j]; pg[g.c + c0 + j] = ab[j]; }
+      for (int j = 0; j < 8; ++j) { atomicAdd(pg + c0 + j, ag[j]); atomicAdd(pg + g.c + c0 + j, ab[j]); }
     }
   }
   if (partial == nullptr) return;
@@ -212,14 +217,14 @@ bn_bwd_reduce_kernel(const T* __restrict__ dA, long dA_ld, const T* __restrict__
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  for (int c = threadIdx.x; c < g.c; c += 256) {
-    float sg_ = 0.f, sb_ = 0.f;
-    for (unsigned int bk = 0; bk < gridDim.x; ++bk) {
-      sg_ += partial[(long)bk * 2 * g.c + c];
-      sb_ += partial[(long)bk * 2 * g.c + g.c + c];
-    }
-    dgamma[c] = sg_;
-    dbeta[c] = sb_;
+  for (int c = threadIdx.x; c < 2 * g.c; c += 256) {
+    float v[BN_SLOTS];
+#pragma unroll
+    for (int sl = 0; sl < BN_SLOTS; ++sl) v[sl] = __ldcg(partial + (long)sl * 2 * g.c + c);
+    float acc = 0.f;
+#pragma unroll
+    for (int sl = 0; sl < BN_SLOTS; ++sl) { acc += v[sl]; partial[(long)sl * 2 * g.c + c] = 0.f; }   // re-armed
+    if (c < g.c) dgamma[c] = acc; else dbeta[c - g.c] = acc;
   }
   if (threadIdx.x == 0) *ticket = 0u;   // ready for the next launch
 }
@@ -358,7 +363,7 @@ extern "C" int yb_bn_act_apply(const void* z, long z_ld, const float* scale, con
 
 extern "C" int yb_bn_bwd_reduce_workspace_bytes(size_t* bytes) {
   YB_REQUIRE(bytes, "bn_bwd_reduce_workspace_bytes: null pointer");
-  *bytes = 256 + (size_t)num_sms() * 4 * 2 * 2048 * sizeof(float);
+  *bytes = 256 + (size_t)16 * 2 * 2048 * sizeof(float);   // ticket + BN_SLOTS x [2][c <= 2048]
   return YB_OK;
 }
 

@@ -231,6 +231,126 @@ conv_thin_kernel(const ThinParams p) {
   cp_async_wait_all();
 }
 
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+
+// Weight gradient of the stem (float32 image, 3 -> 32 channels, utils/layer_utils.py:35):
+//   dW[co, k] = sum_p dz[p, co] * patch[p, k],   k = (r*3+s)*3+c  (27, padded to 32)
+// on the warp-level tensor path: D[32 co x 32 k] += dz^T[32 x 128 px] * patch[128 px x 32] per 8x16-pixel tile.  Both
+// operands are stored pixel-major in shared memory and read with ldmatrix.trans.  The image stays float32-exact:
+// every patch value is split into a 16-bit head and a 16-bit remainder (x = hi + lo) and both products are
+// accumulated, so the result matches a float32 convolution-backward to ~1e-5.
+// Each of the 4 warps reduces 32 of the tile's 128 pixels; accumulators live in registers across all tiles of the
+// persistent CTA and are combined through shared memory at the end (864 global atomics per CTA).
+template <typename T>
+__global__ void __launch_bounds__(THIN_THREADS)
+stem_wgrad_tc_kernel(const float* __restrict__ x, const T* __restrict__ dz, int n, int h, int w, int tiles_y,
+                     int tiles_x, int num_tiles, float* __restrict__ dw) {
+  constexpr int HH = TH + 2, HW = TW + 2;
+  constexpr int PITCH = 32 * 2 + 16;                      // bytes per pixel row of the 16-bit tiles
+  __shared__ __align__(16) float s_halo[HH * HW * 3];
+  __shared__ __align__(16) uint8_t s_hi[128 * PITCH], s_lo[128 * PITCH], s_dz[128 * PITCH];
+  __shared__ float s_acc[32 * 32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 32 * 32; i += THIN_THREADS) s_acc[i] = 0.f;
+  float acc[2][4][4];
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int nj = 0; nj < 4; ++nj)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[mi][nj][q] = 0.f;
+
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int tx = tile % tiles_x;
+    const int ty = (tile / tiles_x) % tiles_y;
+    const int img = tile / (tiles_x * tiles_y);
+    const int oy0 = ty * TH, ox0 = tx * TW;
+    __syncthreads();                                      // previous tile's fragments are consumed
+    // dz tile: 128 pixels x 64 bytes (zero outside the image)
+    for (int i = tid; i < 128 * 4; i += THIN_THREADS) {
+      const int px = i >> 2, ch = i & 3;
+      const int oy = oy0 + px / TW, ox = ox0 + px % TW;
+      const bool ok = oy < h && ox < w;
+      const T* src = ok ? dz + (((long)img * h + oy) * w + ox) * 32 + ch * 8 : dz;
+      cp_async16(s_dz + px * PITCH + ch * 16, src, ok ? 16 : 0);
+    }
+    const float* xin = x + (long)img * h * w * 3;
+    for (int i = tid; i < HH * HW * 3; i += THIN_THREADS) {
+      const int c = i % 3, px = (i / 3) % HW, py = i / (3 * HW);
+      const int gy = oy0 - 1 + py, gx = ox0 - 1 + px;
+      s_halo[i] = (gy >= 0 && gy < h && gx >= 0 && gx < w) ? xin[((long)gy * w + gx) * 3 + c] : 0.f;
+    }
+    __syncthreads();
+    {   // im2col of the thread's pixel, split into head + remainder
+      const int py = tid / TW, px = tid % TW;
+      uint32_t* hi = reinterpret_cast<uint32_t*>(s_hi + tid * PITCH);
+      uint32_t* lo = reinterpret_cast<uint32_t*>(s_lo + tid * PITCH);
+      float v[32];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s2 = 0; s2 < 3; ++s2)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) v[(r * 3 + s2) * 3 + c] = s_halo[((py + r) * HW + (px + s2)) * 3 + c];
+#pragma unroll
+      for (int k = 27; k < 32; ++k) v[k] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 32; k += 2) {
+        const uint32_t hq = Pack2<T>::pack(v[k], v[k + 1]);
+        const float2 hf = Pack2<T>::unpack(hq);
+        hi[k >> 1] = hq;
+        lo[k >> 1] = Pack2<T>::pack(v[k] - hf.x, v[k + 1] - hf.y);
+      }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    // warp `warp` reduces pixels [32*warp, 32*warp + 32): two k16 steps
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const int p0 = warp * 32 + ks * 16;
+      const int mi_ = lane >> 3, rr = lane & 7;
+      uint32_t a[2][4];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)   // matrices: (co 0-7, px 0-7), (co 8-15, px 0-7), (co 0-7, px 8-15), (co 8-15, px 8-15)
+        ldmatrix_x4_trans(a[mi], s_dz + (p0 + (mi_ >> 1) * 8 + rr) * PITCH + (mi * 16 + (mi_ & 1) * 8) * 2);
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {
+        const uint8_t* bt = part == 0 ? s_hi : s_lo;
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {   // matrices: (px 0-7, k 0-7), (px 8-15, k 0-7), (px 0-7, k 8-15), (px 8-15, k 8-15)
+          uint32_t b[4];
+          ldmatrix_x4_trans(b, bt + (p0 + (mi_ & 1) * 8 + rr) * PITCH + (nb * 16 + (mi_ >> 1) * 8) * 2);
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi) {
+            mma16816<T>(acc[mi][2 * nb], a[mi], b[0], b[1]);
+            mma16816<T>(acc[mi][2 * nb + 1], a[mi], b[2], b[3]);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int nj = 0; nj < 4; ++nj)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int co = mi * 16 + (lane >> 2) + (q >> 1) * 8;
+        const int k = nj * 8 + (lane & 3) * 2 + (q & 1);
+        atomicAdd(&s_acc[co * 32 + k], acc[mi][nj][q]);
+      }
+  __syncthreads();
+  for (int i = tid; i < 32 * 27; i += THIN_THREADS) {
+    const int co = i / 27, k = i - co * 27;
+    atomicAdd(dw + i, s_acc[co * 32 + k]);
+  }
+}
+
 template <typename T, int COUT, int STRIDE, bool STEM>
 static int launch_thin(const ThinParams& p, cudaStream_t st) {
   using C = ThinCfg<T, COUT, STRIDE, STEM>;
@@ -296,4 +416,23 @@ extern "C" int yb_stem_conv_fwd_tc(const float* x, const float* w_ohwi, const fl
   if (dtype == YB_BF16) return launch_thin<__nv_bfloat16, 32, 1, true>(p, st);
   set_error("stem_tc: dtype must be f16 or bf16");
   return YB_ERR_UNSUPPORTED;
+}
+
+// Stem weight gradient on the warp-level tensor path (float32 image split into 16-bit head + remainder).
+extern "C" int yb_stem_conv_wgrad_tc(const float* x, const void* dz, int dtype, int n, int h, int w, float* dw,
+                                     void* stream) {
+  YB_REQUIRE(x && dz && dw && n > 0 && h > 0 && w > 0, "stem_wgrad_tc: bad argument");
+  YB_REQUIRE(dtype == YB_F16 || dtype == YB_BF16, "stem_wgrad_tc: dtype must be f16 or bf16");
+  const int tiles_y = ceil_div(h, TH), tiles_x = ceil_div(w, TW);
+  const int num_tiles = tiles_x * tiles_y * n;
+  const int grid = num_tiles < num_sms() * 4 ? num_tiles : num_sms() * 4;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == YB_F16)
+    stem_wgrad_tc_kernel<__half><<<grid, THIN_THREADS, 0, st>>>(x, static_cast<const __half*>(dz), n, h, w, tiles_y,
+                                                               tiles_x, num_tiles, dw);
+  else
+    stem_wgrad_tc_kernel<__nv_bfloat16><<<grid, THIN_THREADS, 0, st>>>(x, static_cast<const __nv_bfloat16*>(dz), n, h,
+                                                                      w, tiles_y, tiles_x, num_tiles, dw);
+  YB_CUDA(cudaGetLastError());
+  return YB_OK;
 }

@@ -309,10 +309,16 @@ extern "C" int yb_conv2d_wgrad(const yb_conv_desc* d, const void* x, const void*
 #undef YB_WG
 }
 
+extern "C" int yb_stem_conv_wgrad_tc(const float* x, const void* dz, int dtype, int n, int h, int w, float* dw,
+                                     void* stream);
 extern "C" int yb_stem_conv_wgrad(const float* x, const void* dz, int dtype, int n, int h, int w, float* dw,
                                   void* stream) {
   YB_REQUIRE(x && dz && dw && n > 0 && h > 0 && w > 0, "stem_wgrad: bad argument");
   YB_REQUIRE(dtype == YB_F16 || dtype == YB_BF16, "stem_wgrad: dtype must be f16 or bf16");
+  {
+    const char* sw = getenv("YB_STEM_WGRAD");   // "cuda": the CUDA-core kernel below (A/B testing)
+    if (!(sw && sw[0] == 'c')) return yb_stem_conv_wgrad_tc(x, dz, dtype, n, h, w, dw, stream);
+  }
   const long P = (long)n * h * w;
   long blocks = (P + 7) / 8;
   const long cap = (long)num_sms() * 8;
