@@ -42,7 +42,8 @@ def _worker(rank, world, port, q):
     assert scale == 1.0 / world
     ref = gs[0] + gs[1]
     err = float((plan.grad_flat() - ref).abs().max() / ref.abs().max())
-    check(lib.yb_net_train_update(plan.handle, 1e-3, scale, 0.9, 5e-4, 100.0, stream_handle()), "update")
+    # momentum 0: the lr-0 local step above left each rank's LOCAL gradient in its velocity buffers
+    check(lib.yb_net_train_update(plan.handle, 1e-3, scale, 0.0, 5e-4, 100.0, stream_handle()), "update")
     w = torch.cat([plan.conv_params(i)["w"].reshape(-1) for i in (0, 30, 74)])
     ws = [torch.empty_like(w) for _ in range(world)]
     dist.all_gather(ws, w)
