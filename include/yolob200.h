@@ -122,6 +122,15 @@ int yb_stem_conv_wgrad_tc(const float* x, const void* dz, int dtype, int n, int 
  * the data gradient of a stride-1 conv is yb_conv2d_fwd(dz, dst) (stride-2: on the zero-inserted dz). */
 int yb_pack_dgrad_weights(const float* w_ohwi, int cout, int cin, int ksize, int k_cout, int cin_pad, int dtype,
                           void* dst, void* stream);
+/* Data gradient of a 3x3 STRIDE-2 conv (pad 1 + VALID, utils/layer_utils.py:17-27) without zero insertion: the input
+ * pixels are split by parity (a, b) = (row & 1, col & 1); class (a, b) is a (1+a) x (1+b)-tap conv over the plain
+ * dz [n, h/2, w/2, dz_ld] whose result is stored at (2i + a, 2j + b) of dx [n, h, w, dx_ld] (+ res at the same pixel,
+ * res nullable, may alias dx).  yb_pack_dgrad_weights_s2 lays the four weight matrices [cin_pad][(1+a)(1+b)*k_cout]
+ * out back to back (9 * cin_pad * k_cout elements).  `fwd` is the FORWARD conv's descriptor (n, h, w, cin, cout, dtype). */
+int yb_pack_dgrad_weights_s2(const float* w_ohwi, int cout, int cin, int k_cout, int cin_pad, int dtype, void* dst,
+                             void* stream);
+int yb_conv2d_dgrad_s2(const yb_conv_desc* fwd, const void* dz, int dz_ld, int k_cout, const void* w_dgrad_s2,
+                       const void* res, int res_ld, void* dx, int dx_ld, void* stream);
 /* BN batch statistics -> scale/shift for bn_act_apply, saved mean/invstd for the backward, moving-stat update
  * (biased variance normalises, unbiased variance feeds the moving average; moving_* nullable). */
 int yb_bn_finalize(const float* sum, const float* sqsum, long count, int c, const float* gamma, const float* beta,

@@ -106,6 +106,34 @@ def test_dgrad_via_forward_kernel(k, s, cin, cout):
     assert torch.all(err <= 2.0 ** -6 * torch.clamp(ref.abs(), min=0.05)), float(err.max())
 
 
+@pytest.mark.parametrize("cin,cout,with_res", [(32, 64, True), (64, 128, False), (256, 512, True)])
+def test_dgrad_stride2_parity_classes(cin, cout, with_res):
+    """dX of a 3x3 stride-2 conv as four parity-class convs over the plain dz (no zero insertion)."""
+    L = _L()
+    g = torch.Generator().manual_seed(8)
+    n, h, w = 2, 24, 20
+    ho, wo = h // 2, w // 2
+    wt = (torch.randn((cout, 3, 3, cin), generator=g) * 0.05).cuda()
+    kco = (cout + 31) // 32 * 32
+    cin_pad = L.lib.yb_conv_cout_pad(cin)
+    wd = torch.empty(9 * cin_pad * kco, dtype=torch.bfloat16, device="cuda")
+    L.check(L.lib.yb_pack_dgrad_weights_s2(L.ptr(wt), cout, cin, kco, cin_pad, L.YB_BF16, L.ptr(wd), L.stream_handle()), "packd_s2")
+    dz = (torch.randn((n, ho, wo, kco), generator=g) * 0.1).to(torch.bfloat16).cuda()
+    prev = (torch.randn((n, h, w, cin), generator=g) * 0.1).to(torch.bfloat16).cuda()
+    out = prev.clone() if with_res else torch.full((n, h, w, cin), 7.0, dtype=torch.bfloat16, device="cuda")
+    d = L.ConvDesc(n=n, h=h, w=w, cin=cin, cout=cout, ksize=3, stride=2, in_ld=cin, out_ld=cout, res_ld=0,
+                   dtype=L.YB_BF16, out_fp32=0, leaky=0, upsample2x=0)
+    L.check(L.lib.yb_conv2d_dgrad_s2(C.byref(d), L.ptr(dz), kco, kco, L.ptr(wd), L.ptr(out) if with_res else None, cin,
+                                     L.ptr(out), cin, L.stream_handle()), "dgrad_s2")
+    x = torch.zeros((n, cin, h, w), device="cuda", requires_grad=True)
+    wq = wt.to(torch.bfloat16).float()                    # the packer rounds the master weights to 16 bits
+    F.conv2d(x, wq.permute(0, 3, 1, 2).contiguous(), None, stride=2, padding=1).backward(
+        dz[..., :cout].float().permute(0, 3, 1, 2))
+    ref = x.grad.permute(0, 2, 3, 1) + (prev.float() if with_res else 0)
+    err = (out.float() - ref).abs()
+    assert torch.all(err <= 2.0 ** -6 * torch.clamp(ref.abs(), min=0.05)), float(err.max())
+
+
 @pytest.mark.parametrize("upsample,res,c", [(False, True, 64), (True, False, 128), (False, False, 32)])
 def test_bn_train_forward_backward(upsample, res, c):
     L = _L()

@@ -9,6 +9,8 @@ struct ConvParams {
   int cout;               // valid output channels
   int cin;                // input channels (K per filter tap)
   int ksize, stride, pad;
+  int kh, kw;             // filter window (ksize x ksize for the forward convs; 1x1 .. 2x2 for the stride-2 dgrad classes)
+  int scatter;            // 0, or 1 + 2a + b: output pixel (p, q) is stored at (2p + a, 2q + b) of a [n, 2P, 2Q] grid
   int im2col;             // 1: A via im2col TMA, 0: A via 2D tiled TMA
   int two_cta;            // 1: cta_group::2 kernel (256-row tiles per CTA pair)
   int b_resident;         // 1-CTA kernel: the whole [BN, K] weight tile stays in shared memory (single n-tile, fits)
@@ -29,6 +31,12 @@ struct ConvParams {
 int conv_prepare(const yb_conv_desc* d, const void* x, const void* w_packed, const float* scale, const float* shift,
                  const void* res, void* out, float* stat_sum, float* stat_sqsum, CUtensorMap* tmA, CUtensorMap* tmB,
                  ConvParams* p, int* cout_pad_out);
+// Window variant used by the stride-2 dgrad: a kh x kw window whose taps sit at offsets (0..kh-1, 0..kw-1) from the
+// output pixel (zero-filled past the border), stride 1, output scattered to parity class `scatter`.
+// w_packed is [cout_pad][kh*kw*cin].
+int conv_prepare_win(const yb_conv_desc* d, int kh, int kw, int scatter, const void* x, const void* w_packed,
+                     const float* scale, const float* shift, const void* res, void* out, CUtensorMap* tmA,
+                     CUtensorMap* tmB, ConvParams* p, int* cout_pad_out);
 int conv_launch(int dtype, int cout_pad, const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p,
                 cudaStream_t st);
 

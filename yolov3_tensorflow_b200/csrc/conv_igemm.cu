@@ -80,14 +80,18 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const int row
   // output row(s)
   long orow[4];
   int nrep = 1;
-  if (p.upsample) {
+  if (p.upsample || p.scatter) {
     const int q = row % p.Q;
     const int pp = (row / p.Q) % p.P;
     const int img = row / (p.Q * p.P);
     const long W2 = 2L * p.Q;
     const long base = ((long)img * 2 * p.P + 2 * pp) * W2 + 2 * q;
-    orow[0] = base; orow[1] = base + 1; orow[2] = base + W2; orow[3] = base + W2 + 1;
-    nrep = 4;
+    if (p.scatter) {
+      orow[0] = base + ((p.scatter - 1) >> 1) * W2 + ((p.scatter - 1) & 1);
+    } else {
+      orow[0] = base; orow[1] = base + 1; orow[2] = base + W2; orow[3] = base + W2 + 1;
+      nrep = 4;
+    }
   } else {
     orow[0] = row;
   }
@@ -134,7 +138,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const int row
         for (int j = 0; j < 32; ++j) v[j] = leaky01(v[j]);
       }
       if (p.res != nullptr) {
-        const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const T*>(p.res) + (long)row * p.res_ld + col0);
+        const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const T*>(p.res) +
+                                                         (p.scatter ? orow[0] : (long)row) * p.res_ld + col0);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint4 u = __ldg(rp + j);
@@ -199,7 +204,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int kb_per_tap_ = p.cin / BK;
-  const int num_kb_ = p.ksize * p.ksize * kb_per_tap_;
+  const int num_kb_ = p.kh * p.kw * kb_per_tap_;
   // operand ring: [nst x A][nst x B], or with resident weights [nst x A][num_kb x B] (B loaded once per CTA)
   int nst = C::STAGES;
   if (p.b_resident) {
@@ -222,7 +227,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int kb_per_tap = p.cin / BK;
-  const int num_kb = p.ksize * p.ksize * kb_per_tap;
+  const int num_kb = p.kh * p.kw * kb_per_tap;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -277,7 +282,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (ld_a) {
             if (p.im2col) {
               tma_load_im2col_4d(sA + stage * C::A_BYTES, &tmA, &full_bar[stage], c0, w_base, h_base, img,
-                                 (uint16_t)(tap % p.ksize), (uint16_t)(tap / p.ksize));
+                                 (uint16_t)(tap % p.kw), (uint16_t)(tap / p.kw));
             } else {
               tma_load_2d(sA + stage * C::A_BYTES, &tmA, &full_bar[stage], c0, m0);
             }
@@ -408,7 +413,7 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const int num_clusters = gridDim.x >> 1;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;   // m tiles are 256 rows here
   const int kb_per_tap = p.cin / BK;
-  const int num_kb = p.ksize * p.ksize * kb_per_tap;
+  const int num_kb = p.kh * p.kw * kb_per_tap;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -454,7 +459,7 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           if (!(p.dbg & 1)) {
             if (p.im2col) {
               tma_load_im2col_4d_2sm(sA + stage * C::A_BYTES, &tmA, &full_bar[stage], c0, w_base, h_base, img,
-                                     (uint16_t)(tap % p.ksize), (uint16_t)(tap / p.ksize));
+                                     (uint16_t)(tap % p.kw), (uint16_t)(tap / p.kw));
             } else {
               tma_load_2d_2sm(sA + stage * C::A_BYTES, &tmA, &full_bar[stage], c0, m0);
             }
@@ -577,7 +582,7 @@ conv_igemm_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int SM_T = (p.num_m_tiles + CM - 1) / CM, SN_T = p.num_n_tiles / CN;   // super-tiles
   const int num_tiles = SM_T * SN_T;
   const int kb_per_tap = p.cin / BK;
-  const int num_kb = p.ksize * p.ksize * kb_per_tap;
+  const int num_kb = p.kh * p.kw * kb_per_tap;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -630,8 +635,8 @@ conv_igemm_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           uint8_t* adst = sA + stage * C::A_BYTES + pn * A_ROWS * (BK * 2);
           uint8_t* bdst = sB + stage * C::B_BYTES + pm * B_ROWS * (BK * 2);
           if (p.im2col) {
-            tma_load_im2col_4d_2sm_mc(adst, &tmA, &full_bar[stage], c0, w_base, h_base, img, (uint16_t)(tap % p.ksize),
-                                      (uint16_t)(tap / p.ksize), maskA);
+            tma_load_im2col_4d_2sm_mc(adst, &tmA, &full_bar[stage], c0, w_base, h_base, img, (uint16_t)(tap % p.kw),
+                                      (uint16_t)(tap / p.kw), maskA);
           } else {
             tma_load_2d_2sm_mc(adst, &tmA, &full_bar[stage], c0, m0, maskA);
           }
@@ -920,10 +925,12 @@ int conv_launch(int dtype, int cout_pad, const CUtensorMap& tmA, const CUtensorM
 }
 
 // Build maps + params for one conv.  x/w/out pointers are baked into maps/params.
-int conv_prepare(const yb_conv_desc* d, const void* x, const void* w_packed, const float* scale, const float* shift,
-                 const void* res, void* out, float* stat_sum, float* stat_sqsum, CUtensorMap* tmA, CUtensorMap* tmB,
-                 ConvParams* p, int* cout_pad_out) {
-  YB_REQUIRE(d->ksize == 1 || d->ksize == 3, "conv: ksize must be 1 or 3 (got %d)", d->ksize);
+// win = 0: the forward rule (ksize x ksize, symmetric padding ksize/2); win = 1: kh x kw window at offsets >= 0.
+static int conv_prepare_core(const yb_conv_desc* d, int win, int kh, int kw, int scatter, const void* x,
+                             const void* w_packed, const float* scale, const float* shift, const void* res, void* out,
+                             float* stat_sum, float* stat_sqsum, CUtensorMap* tmA, CUtensorMap* tmB, ConvParams* p,
+                             int* cout_pad_out) {
+  YB_REQUIRE(win || d->ksize == 1 || d->ksize == 3, "conv: ksize must be 1 or 3 (got %d)", d->ksize);
   YB_REQUIRE(d->stride == 1 || d->stride == 2, "conv: stride must be 1 or 2 (got %d)", d->stride);
   YB_REQUIRE(!(d->ksize == 1 && d->stride != 1), "conv: 1x1 stride-2 is not on the YOLOv3 path");
   YB_REQUIRE(d->cin % 32 == 0 && d->cin >= 32, "conv: cin must be a multiple of 32 (got %d); use yb_stem_conv_fwd", d->cin);
@@ -945,7 +952,8 @@ int conv_prepare(const yb_conv_desc* d, const void* x, const void* w_packed, con
   YB_REQUIRE((stat_sum == nullptr) == (stat_sqsum == nullptr), "conv: stat_sum/stat_sqsum must both be given");
   const int P = d->h / d->stride, Q = d->w / d->stride;
   const int bk = conv_block_k(d->cin);
-  const int pad = d->ksize / 2;
+  if (!win) { kh = d->ksize; kw = d->ksize; }
+  const int pad = win ? 0 : d->ksize / 2;
   p->M = d->n * P * Q; p->P = P; p->Q = Q;
   // a CTA pair per 256-row tile once there are enough tiles to occupy the 74 SM pairs
   const char* force = getenv("YB_CONV_MODE");   // "1cta" / "2cta": testing override
@@ -970,12 +978,13 @@ int conv_prepare(const yb_conv_desc* d, const void* x, const void* w_packed, con
   const int bn = two ? conv_block_n2(cout_pad) : conv_block_n(cout_pad);
   {
     // resident weights (1-CTA kernel): one n-tile, and the [BN, K] tile leaves room for >= 3 A stages
-    const long b_bytes = (long)d->ksize * d->ksize * d->cin * bn * 2;
+    const long b_bytes = (long)kh * kw * d->cin * bn * 2;
     const char* br = getenv("YB_CONV_BRES");
     p->b_resident = (!two && cout_pad == bn && SMEM_BUDGET - b_bytes >= 3L * BLOCK_M * bk * 2 && (br && br[0] == '1')) ? 1 : 0;   // opt-in: measured no gain (profiles/r01_i)
   }
   p->cout = d->cout; p->cin = d->cin; p->ksize = d->ksize; p->stride = d->stride; p->pad = pad;
-  p->im2col = d->ksize == 3;
+  p->kh = kh; p->kw = kw; p->scatter = scatter;
+  p->im2col = kh * kw > 1;
   p->num_m_tiles = ceil_div(p->M, two ? 2 * BLOCK_M : BLOCK_M);
   p->num_n_tiles = cout_pad / bn;
   p->scale = scale; p->shift = shift;
@@ -984,17 +993,32 @@ int conv_prepare(const yb_conv_desc* d, const void* x, const void* w_packed, con
   p->stat_sum = stat_sum; p->stat_sqsum = stat_sqsum;
   int rc;
   if (p->im2col) {
-    rc = make_tmap_im2col_px(tmA, x, d->dtype, d->n, d->h, d->w, d->cin, d->in_ld, d->ksize, d->stride, pad, bk,
+    rc = make_tmap_im2col_px(tmA, x, d->dtype, d->n, d->h, d->w, d->cin, d->in_ld, win ? 1 : d->ksize, d->stride, pad, bk,
                              BLOCK_M / mc_n);
   } else {
     rc = make_tmap_2d(tmA, x, d->dtype, (long)d->n * d->h * d->w, d->cin, d->in_ld, BLOCK_M / mc_n, bk, 0);
   }
   if (rc) return rc;
-  rc = make_tmap_2d(tmB, w_packed, d->dtype, cout_pad, (long)d->ksize * d->ksize * d->cin,
-                    (long)d->ksize * d->ksize * d->cin, (two ? bn / 2 : bn) / mc_m, bk, 1);
+  rc = make_tmap_2d(tmB, w_packed, d->dtype, cout_pad, (long)kh * kw * d->cin, (long)kh * kw * d->cin, (two ? bn / 2 : bn) / mc_m, bk, 1);
   if (rc) return rc;
   *cout_pad_out = cout_pad;
   return YB_OK;
+}
+
+int conv_prepare(const yb_conv_desc* d, const void* x, const void* w_packed, const float* scale, const float* shift,
+                 const void* res, void* out, float* stat_sum, float* stat_sqsum, CUtensorMap* tmA, CUtensorMap* tmB,
+                 ConvParams* p, int* cout_pad_out) {
+  return conv_prepare_core(d, 0, 0, 0, 0, x, w_packed, scale, shift, res, out, stat_sum, stat_sqsum, tmA, tmB, p,
+                           cout_pad_out);
+}
+
+int conv_prepare_win(const yb_conv_desc* d, int kh, int kw, int scatter, const void* x, const void* w_packed,
+                     const float* scale, const float* shift, const void* res, void* out, CUtensorMap* tmA,
+                     CUtensorMap* tmB, ConvParams* p, int* cout_pad_out) {
+  YB_REQUIRE(kh >= 1 && kh <= 2 && kw >= 1 && kw <= 2 && scatter >= 0 && scatter <= 4, "conv_prepare_win: bad window");
+  YB_REQUIRE(d->stride == 1 && !d->out_fp32 && !d->upsample2x, "conv_prepare_win: stride-1, 16-bit, non-upsampled only");
+  return conv_prepare_core(d, 1, kh, kw, scatter, x, w_packed, scale, shift, res, out, nullptr, nullptr, tmA, tmB, p,
+                           cout_pad_out);
 }
 
 }  // namespace yb
@@ -1011,4 +1035,36 @@ extern "C" int yb_conv2d_fwd(const yb_conv_desc* d, const void* x, const void* w
   int rc = yb::conv_prepare(d, x, w_packed, scale, shift, res, out, stat_sum, stat_sqsum, &tmA, &tmB, &p, &cout_pad);
   if (rc) return rc;
   return yb::conv_launch(d->dtype, cout_pad, tmA, tmB, p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int yb_conv2d_dgrad_s2(const yb_conv_desc* fwd, const void* dz, int dz_ld, int k_cout, const void* w_dgrad_s2,
+                                  const void* res, int res_ld, void* dx, int dx_ld, void* stream) {
+  YB_REQUIRE(fwd && dz && w_dgrad_s2 && dx, "dgrad_s2: null pointer");
+  YB_REQUIRE(fwd->ksize == 3 && fwd->stride == 2 && fwd->h % 2 == 0 && fwd->w % 2 == 0, "dgrad_s2: 3x3 stride-2 convs only");
+  YB_REQUIRE(k_cout >= fwd->cout && k_cout % 32 == 0 && dz_ld >= k_cout, "dgrad_s2: dz must hold k_cout (multiple of 32) channels");
+  static float* unit = nullptr;                  // scale = 1 / shift = 0 vectors (2 x 1024 floats, created once)
+  if (!unit) {
+    float h_unit[2048];
+    for (int i = 0; i < 1024; ++i) { h_unit[i] = 1.f; h_unit[1024 + i] = 0.f; }
+    YB_CUDA(cudaMalloc(&unit, sizeof(h_unit)));
+    YB_CUDA(cudaMemcpy(unit, h_unit, sizeof(h_unit), cudaMemcpyHostToDevice));
+  }
+  YB_REQUIRE(fwd->cin <= 1024, "dgrad_s2: cin > 1024");
+  yb_conv_desc d = *fwd;
+  d.h = fwd->h / 2; d.w = fwd->w / 2; d.cin = k_cout; d.cout = fwd->cin; d.ksize = 1; d.stride = 1;
+  d.in_ld = dz_ld; d.out_ld = dx_ld; d.res_ld = res_ld; d.out_fp32 = 0; d.leaky = 0; d.upsample2x = 0;
+  const size_t per = (size_t)yb_conv_cout_pad(fwd->cin) * k_cout;
+  const size_t woff[4] = {0, per, 3 * per, 5 * per};
+  for (int c = 0; c < 4; ++c) {
+    CUtensorMap tmA, tmB;
+    yb::ConvParams p;
+    int cout_pad = 0;
+    int rc = yb::conv_prepare_win(&d, 1 + (c >> 1), 1 + (c & 1), 1 + c, dz,
+                                  static_cast<const uint8_t*>(w_dgrad_s2) + woff[c] * 2, unit, unit + 1024, res, dx, &tmA,
+                                  &tmB, &p, &cout_pad);
+    if (rc) return rc;
+    rc = yb::conv_launch(d.dtype, cout_pad, tmA, tmB, p, static_cast<cudaStream_t>(stream));
+    if (rc) return rc;
+  }
+  return YB_OK;
 }

@@ -34,6 +34,10 @@ struct Layer {
   // ---- training plan (net_train.cu) ----
   size_t z_off = 0, dz_off = 0;      // raw conv output z / its gradient (activation arena); dz is zero-inserted for stride 2
   int dz_ld = 0, dz_dilated = 0, k_cout = 0;
+  int dgrad_parity = 0;              // stride-2 layer whose dgrad runs as 4 parity-class convs on the plain dz
+  CUtensorMap d4_tmA[4], d4_tmB[4];
+  ConvParams d4_params[4];
+  int d4_cout_pad[4] = {0, 0, 0, 0};
   size_t st_sum = 0, st_sqsum = 0, st_mean = 0, st_invstd = 0, st_scale = 0, st_shift = 0;   // fp32 [cout_pad] each
   size_t w_dgrad = 0;                // [cin_pad, k, k, k_cout] 16-bit (param arena)
   long g_w = -1, g_gamma = -1, g_beta = -1, g_bias = -1;   // float offsets into the flat gradient / velocity buffers

@@ -40,7 +40,11 @@ void train_layout(yb_net* net) {
     if (L.info.has_bn) {
       L.z_off = o; o = al256(o + out_rows * L.info.cout * esz);
       L.dz_ld = L.info.cout;
-      L.dz_dilated = L.info.stride == 2;
+      // stride-2 layers: the input gradient is computed per parity class on the plain dz (4 small convs, no zeros);
+      // YB_DGRAD_S2=dilated selects the first version (one 3x3 conv over a zero-inserted dz: 4x the MMA work)
+      const char* s2 = getenv("YB_DGRAD_S2");
+      L.dgrad_parity = (L.info.stride == 2 && !(s2 && s2[0] == 'd')) ? 1 : 0;
+      L.dz_dilated = L.info.stride == 2 && !L.dgrad_parity;
       const size_t dz_rows = L.dz_dilated ? (size_t)net->n * L.info.in_h * L.info.in_w : out_rows;
       L.dz_off = o; o = al256(o + dz_rows * L.dz_ld * esz);
     } else {
@@ -189,8 +193,19 @@ int train_bind(yb_net* net) {
     if (cov && pit != pending.end()) { set_error("train plan: tensor with both a written gradient and a pending residual"); return YB_ERR_UNSUPPORTED; }
     if (cov) { res = gten_ptr(net, L.in); d.res_ld = d.out_ld; }
     else if (pit != pending.end()) { res = pit->second.ptr; d.res_ld = (int)pit->second.ld; pending.erase(pit); }
-    int rc = conv_prepare(&d, net->act + L.dz_off, net->par + L.w_dgrad, ones, zeros, res, gten_ptr(net, L.in), nullptr,
-                          nullptr, &L.d_tmA, &L.d_tmB, &L.dparams, &L.d_cout_pad);
+    int rc = YB_OK;
+    if (L.dgrad_parity) {
+      d.h = L.info.out_h; d.w = L.info.out_w;                // plain dz at the OUTPUT resolution
+      const size_t esz = 2, per = (size_t)yb_conv_cout_pad(L.info.cin) * L.k_cout;
+      const size_t woff[4] = {0, per, 3 * per, 5 * per};
+      for (int c = 0; c < 4 && rc == YB_OK; ++c)
+        rc = conv_prepare_win(&d, 1 + (c >> 1), 1 + (c & 1), 1 + c, net->act + L.dz_off, net->par + L.w_dgrad + woff[c] * esz,
+                              ones, zeros, res, gten_ptr(net, L.in), &L.d4_tmA[c], &L.d4_tmB[c], &L.d4_params[c],
+                              &L.d4_cout_pad[c]);
+    } else {
+      rc = conv_prepare(&d, net->act + L.dz_off, net->par + L.w_dgrad, ones, zeros, res, gten_ptr(net, L.in), nullptr,
+                        nullptr, &L.d_tmA, &L.d_tmB, &L.dparams, &L.d_cout_pad);
+    }
     if (rc) return rc;
     written[L.in.buf].push_back({L.in.off, L.in.c});
   }
@@ -226,6 +241,9 @@ int train_bind(yb_net* net) {
 int train_refresh_dgrad_weights(yb_net* net, int layer, void* stream) {
   Layer& L = net->layers[layer];
   if (layer == 0) return YB_OK;
+  if (L.dgrad_parity)
+    return yb_pack_dgrad_weights_s2(fpar(net, L.w_master), L.info.cout, L.info.cin, L.k_cout, yb_conv_cout_pad(L.info.cin),
+                                    net->dtype, net->par + L.w_dgrad, stream);
   return yb_pack_dgrad_weights(fpar(net, L.w_master), L.info.cout, L.info.cin, L.info.ksize, L.k_cout,
                                yb_conv_cout_pad(L.info.cin), net->dtype, net->par + L.w_dgrad, stream);
 }
@@ -329,8 +347,15 @@ extern "C" int yb_net_train_fwd_bwd(yb_net* net, const float* images, const floa
     d.ksize = L.info.ksize; d.stride = L.info.stride; d.in_ld = net->bufs[L.in.buf].ld; d.dtype = dt;
     rc = yb_conv2d_wgrad(&d, ten_ptr2(net, L.in), net->act + L.dz_off, L.dz_ld, L.dz_dilated, gradp(net, L.g_w), stream);
     if (rc) return rc;
-    rc = conv_launch(dt, L.d_cout_pad, L.d_tmA, L.d_tmB, L.dparams, st);
-    if (rc) return rc;
+    if (L.dgrad_parity) {
+      for (int c = 0; c < 4; ++c) {
+        rc = conv_launch(dt, L.d4_cout_pad[c], L.d4_tmA[c], L.d4_tmB[c], L.d4_params[c], st);
+        if (rc) return rc;
+      }
+    } else {
+      rc = conv_launch(dt, L.d_cout_pad, L.d_tmA, L.d_tmB, L.dparams, st);
+      if (rc) return rc;
+    }
   }
   return YB_OK;
 }

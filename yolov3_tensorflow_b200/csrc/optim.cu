@@ -89,9 +89,52 @@ __global__ void pack_dgrad_weights_kernel(const float* __restrict__ w, int cout,
   }
 }
 
+// dgrad weights of a 3x3 stride-2 conv (pad 1 + VALID, utils/layer_utils.py:17-27), split by the parity (a, b) of the
+// input-gradient pixel (2i + a, 2j + b):  dx[2i+a, 2j+b] = sum over the (1+a) x (1+b) window taps (th, tw) of
+//   dz[i + th, j + tw] * W[co][r][s][ci],   r = a ? (th ? 0 : 2) : 1,   s = b ? (tw ? 0 : 2) : 1.
+// Four matrices [cin_pad][(1+a)(1+b) * kco] are stored back to back (class c = 2a + b at element offset
+// cin_pad * kco * {0, 1, 3, 5}[c]); together they hold the 9 taps exactly once.
+template <typename T>
+__global__ void pack_dgrad_s2_kernel(const float* __restrict__ w, int cout, int cin, int kco, int cin_pad,
+                                     T* __restrict__ dst) {
+  const long per = (long)cin_pad * kco;
+  const long total = 9 * per;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int cls = i < per ? 0 : (i < 3 * per ? 1 : (i < 5 * per ? 2 : 3));
+    const long base = cls == 0 ? 0 : (cls == 1 ? per : (cls == 2 ? 3 * per : 5 * per));
+    const int a = cls >> 1, b = cls & 1;
+    const int kw = 1 + b, taps = (1 + a) * kw;
+    const long j = i - base;                       // index inside [cin_pad][taps][kco]
+    const int co = j % kco;
+    const int tap = (j / kco) % taps;
+    const int ci = j / ((long)kco * taps);
+    const int th = tap / kw, tw = tap - th * kw;
+    const int r = a ? (th ? 0 : 2) : 1;
+    const int s2 = b ? (tw ? 0 : 2) : 1;
+    float v = 0.f;
+    if (co < cout && ci < cin) v = w[(((long)co * 3 + r) * 3 + s2) * cin + ci];
+    dst[i] = static_cast<T>(v);
+  }
+}
+
 }  // namespace yb
 
 using namespace yb;
+
+extern "C" int yb_pack_dgrad_weights_s2(const float* w_ohwi, int cout, int cin, int k_cout, int cin_pad, int dtype,
+                                        void* dst, void* stream) {
+  YB_REQUIRE(w_ohwi && dst && cout > 0 && cin > 0 && k_cout >= cout && cin_pad >= cin, "pack_dgrad_s2: bad argument");
+  const long total = 9L * cin_pad * k_cout;
+  const int grid = (int)((total + 255) / 256 < 148L * 16 ? (total + 255) / 256 : 148L * 16);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == YB_F16)
+    pack_dgrad_s2_kernel<__half><<<grid, 256, 0, st>>>(w_ohwi, cout, cin, k_cout, cin_pad, (__half*)dst);
+  else if (dtype == YB_BF16)
+    pack_dgrad_s2_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(w_ohwi, cout, cin, k_cout, cin_pad, (__nv_bfloat16*)dst);
+  else { set_error("pack_dgrad_s2: bad dtype"); return YB_ERR_UNSUPPORTED; }
+  YB_CUDA(cudaGetLastError());
+  return YB_OK;
+}
 
 extern "C" int yb_pack_dgrad_weights(const float* w_ohwi, int cout, int cin, int ksize, int k_cout, int cin_pad,
                                      int dtype, void* dst, void* stream) {
