@@ -204,6 +204,27 @@ def synth_y_true(rng, n, size, anchors, class_num=CLASS_NUM, max_boxes=50):
 
 
 # --------------------------------------------------------------------------------------
+def latency_b1(pkg, S, iters=30):
+    """Single-image latency (the shape of BASELINE.json configs[0], on the GPU): forward + decode + NMS, one host
+    synchronisation per image, CUDA events."""
+    model = pkg.yolov3(CLASS_NUM, pkg.parse_anchors(os.path.join(ROOT, "yolov3_tensorflow_b200", "data", "yolo_anchors.txt")), dtype="fp16")
+    model.init_params(3)
+    x = torch.rand((1, S, S, 3), device="cuda")
+    ts = []
+    for i in range(iters + 5):
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        fms = model.forward(x, is_training=False)
+        boxes, scores = model.predict_scores(fms)
+        out = pkg.batched_gpu_nms(boxes, scores, CLASS_NUM, max_boxes=200, score_thresh=0.3, nms_thresh=0.45)
+        b.record(); torch.cuda.synchronize()
+        if i >= 5:
+            ts.append(a.elapsed_time(b))
+    ts.sort()
+    return {"ms_median": ts[len(ts) // 2], "ms_min": ts[0], "images_per_s": 1e3 / ts[len(ts) // 2],
+            "what": "batch 1, %dx%d, forward + decode + NMS, device-resident input, 81 launches" % (S, S)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -364,8 +385,16 @@ def main():
     conv_flop = (FWD_GFLOP_416 - STEM_GFLOP_416) * scale * 1e9 * B
     pk = peaks()
     achieved = conv_flop / conv_t / 1e12
-    roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel (74 launches/step, layers 1..74)", "achieved": achieved,
-                "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None,
+    traffic = None      # DRAM bytes of the same 74 launches, from the committed ncu table (profiles/, not measured here)
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "conv_traffic.json")))
+        if tj.get("batch") == B and tj.get("size") == S:
+            traffic = tj["dram_bytes_per_step"]
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "kernel": "conv layers 1..74 (72 tcgen05 conv_igemm launches + 2 mma.sync conv_thin launches per step)",
+                "achieved": achieved,
+                "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": traffic,
                 "peak_source": pk["src"], "ms_per_step_conv": conv_t * 1e3, "ms_per_step_stem": float(np.mean(stem_ms)),
                 "algorithmic_flop_per_step": conv_flop}
 
@@ -414,11 +443,14 @@ def main():
             "e2e": {"value": imgs / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": args.steps * (1 + 74 + 1 + 3),
-            "launches_per_step": {"stem_conv": 1, "conv_igemm(tcgen05)": 74, "predict": 1, "nms": 3},
+            "launches_per_step": {"stem(mma.sync)": 1, "conv_thin(mma.sync, layers 1 and 3)": 2,
+                                  "conv_igemm(tcgen05: 1-CTA + CTA-pair kernels)": 72, "predict": 1, "nms": 3},
             "detections_per_step": n_det, "clocks": clocks, "roofline": roofline,
             "fraction_of_conv_flop_roofline": (value / world) * FWD_GFLOP_416 * scale * 1e9 / (pk["tflops"] * 1e12)}
     if train is not None:
         line["train"] = train
+    if world == 1:
+        line["latency_batch1"] = latency_b1(pkg, S)
     if world == 1:
         line["nms_stress"] = nms_stress(pkg, with_cpu=not args.no_cpu_baseline)
     if world == 1 and not args.no_cpu_baseline:
