@@ -207,6 +207,7 @@ def synth_y_true(rng, n, size, anchors, class_num=CLASS_NUM, max_boxes=50):
 def latency_b1(pkg, S, iters=30):
     """Single-image latency (the shape of BASELINE.json configs[0], on the GPU): forward + decode + NMS, one host
     synchronisation per image, CUDA events."""
+    import torch
     model = pkg.yolov3(CLASS_NUM, pkg.parse_anchors(os.path.join(ROOT, "yolov3_tensorflow_b200", "data", "yolo_anchors.txt")), dtype="fp16")
     model.init_params(3)
     x = torch.rand((1, S, S, 3), device="cuda")

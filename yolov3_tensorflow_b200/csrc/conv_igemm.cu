@@ -260,60 +260,65 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tma_load_2d(sB + kb * C::B_BYTES, &tmB, bres_bar, tap * p.cin + (kb - tap * kb_per_tap) * BK, 0);
       }
     }
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      int m_idx, n_idx;
-      tile_coords(p, tile, m_idx, n_idx);
-      const int m0 = m_idx * BLOCK_M;
-      const int n0 = n_idx * BN;
-      // first output pixel of the tile -> (image, row, col); base input pixel of the 3x3 window
-      const int q = m0 % p.Q;
-      const int pp = (m0 / p.Q) % p.P;
-      const int img = m0 / (p.Q * p.P);
-      const int w_base = q * p.stride - p.pad;
-      const int h_base = pp * p.stride - p.pad;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int tap = kb / kb_per_tap;
-        const int c0 = (kb - tap * kb_per_tap) * BK;
-        if (lane == 0) {
+    // One lane runs the whole loop: a k-block costs one barrier wait, one expect_tx and two TMA issues.  The filter
+    // tap / channel-chunk coordinates are carried as counters — the first version recomputed them with three integer
+    // divisions per k-block and re-converged the warp every iteration, which (single thread, dependent instructions)
+    // cost about as much as the k-block's MMAs (profiles/r01_j).
+    if (lane == 0) {
+      const bool ld_a = !(p.dbg & 1), ld_b = !p.b_resident && !(p.dbg & 2);
+      const uint32_t tx_bytes = (ld_a ? C::A_BYTES : 0) + (ld_b ? C::B_BYTES : 0);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int m_idx, n_idx;
+        tile_coords(p, tile, m_idx, n_idx);
+        const int m0 = m_idx * BLOCK_M;
+        const int n0 = n_idx * BN;
+        // first output pixel of the tile -> (image, row, col); base input pixel of the filter window
+        const int q = m0 % p.Q;
+        const int pp = (m0 / p.Q) % p.P;
+        const int img = m0 / (p.Q * p.P);
+        const int w_base = q * p.stride - p.pad;
+        const int h_base = pp * p.stride - p.pad;
+        int c0 = 0, tw = 0, th = 0, kcol = 0;                  // channel chunk, tap (tw, th), column in the packed weights
+        for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          const bool ld_a = !(p.dbg & 1), ld_b = !p.b_resident && !(p.dbg & 2);
-          if (ld_a || ld_b) mbar_arrive_expect_tx(&full_bar[stage], (ld_a ? C::A_BYTES : 0) + (ld_b ? C::B_BYTES : 0));
+          if (tx_bytes) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
           else mbar_arrive(&full_bar[stage]);
           if (ld_a) {
             if (p.im2col) {
-              tma_load_im2col_4d(sA + stage * C::A_BYTES, &tmA, &full_bar[stage], c0, w_base, h_base, img,
-                                 (uint16_t)(tap % p.kw), (uint16_t)(tap / p.kw));
+              tma_load_im2col_4d(sA + stage * C::A_BYTES, &tmA, &full_bar[stage], c0, w_base, h_base, img, (uint16_t)tw,
+                                 (uint16_t)th);
             } else {
               tma_load_2d(sA + stage * C::A_BYTES, &tmA, &full_bar[stage], c0, m0);
             }
           }
-          if (ld_b) tma_load_2d(sB + stage * C::B_BYTES, &tmB, &full_bar[stage], tap * p.cin + c0, n0);
+          if (ld_b) tma_load_2d(sB + stage * C::B_BYTES, &tmB, &full_bar[stage], kcol, n0);
+          c0 += BK; kcol += BK;
+          if (c0 == p.cin) { c0 = 0; if (++tw == p.kw) { tw = 0; ++th; } }
+          if (++stage == nst) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == nst) { stage = 0; phase ^= 1; }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = make_idesc_f16(BLOCK_M, BN, sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    if (p.b_resident && lane == 0 && (int)blockIdx.x < num_tiles) mbar_wait(bres_bar, 0);
-    __syncwarp();
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      if (lane == 0) mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue drained this accumulator
-      __syncwarp();
-      tcgen05_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        if (lane == 0) {
+    if (lane == 0) {
+      if (p.b_resident && (int)blockIdx.x < num_tiles) mbar_wait(bres_bar, 0);
+      const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(sA + stage * C::A_BYTES);
-          const uint32_t b_addr = smem_u32(sB + (p.b_resident ? kb : stage) * C::B_BYTES);
+          const uint32_t a_addr = a_base + stage * C::A_BYTES;
+          const uint32_t b_addr = b_base + (p.b_resident ? kb : stage) * C::B_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adesc = make_kmajor_desc(a_addr + k * UMMA_K * 2, C::SBO, C::SWIZZLE);
@@ -322,11 +327,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           umma_commit(&empty_bar[stage]);                       // smem slot reusable once these MMAs retire
           if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
+          if (++stage == nst) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == nst) { stage = 0; phase ^= 1; }
       }
     }
+    __syncwarp();
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are this warp's
@@ -439,37 +444,39 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     // ===================== TMA producer (both CTAs) =====================
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      int m_idx, n_idx;
-      tile_coords(p, tile, m_idx, n_idx);
-      const int m0 = m_idx * (2 * BLOCK_M) + (int)rank * BLOCK_M;   // this CTA's 128 rows
-      const int n0 = n_idx * BN + (int)rank * (BN / 2);             // this CTA's half of B
-      const int q = m0 % p.Q;
-      const int pp = (m0 / p.Q) % p.P;
-      const int img = m0 / (p.Q * p.P);
-      const int w_base = q * p.stride - p.pad;
-      const int h_base = pp * p.stride - p.pad;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int tap = kb / kb_per_tap;
-        const int c0 = (kb - tap * kb_per_tap) * BK;
-        if (lane == 0) {
+    if (lane == 0) {   // single-lane loop, tap / chunk coordinates as counters (see the 1-CTA kernel)
+      const bool ld_a = !(p.dbg & 1), ld_b = !(p.dbg & 2);
+      const uint32_t tx_bytes = 2 * ((ld_a ? C::A_BYTES : 0) + (ld_b ? C::B_BYTES : 0));
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        int m_idx, n_idx;
+        tile_coords(p, tile, m_idx, n_idx);
+        const int m0 = m_idx * (2 * BLOCK_M) + (int)rank * BLOCK_M;   // this CTA's 128 rows
+        const int n0 = n_idx * BN + (int)rank * (BN / 2);             // this CTA's half of B
+        const int q = m0 % p.Q;
+        const int pp = (m0 / p.Q) % p.P;
+        const int img = m0 / (p.Q * p.P);
+        const int w_base = q * p.stride - p.pad;
+        const int h_base = pp * p.stride - p.pad;
+        int c0 = 0, tw = 0, th = 0, kcol = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (rank == 0)
-            mbar_arrive_expect_tx(&full_bar[stage], 2 * (((p.dbg & 1) ? 0 : C::A_BYTES) + ((p.dbg & 2) ? 0 : C::B_BYTES)));
-          if (!(p.dbg & 1)) {
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+          if (ld_a) {
             if (p.im2col) {
               tma_load_im2col_4d_2sm(sA + stage * C::A_BYTES, &tmA, &full_bar[stage], c0, w_base, h_base, img,
-                                     (uint16_t)(tap % p.kw), (uint16_t)(tap / p.kw));
+                                     (uint16_t)tw, (uint16_t)th);
             } else {
               tma_load_2d_2sm(sA + stage * C::A_BYTES, &tmA, &full_bar[stage], c0, m0);
             }
           }
-          if (!(p.dbg & 2)) tma_load_2d_2sm(sB + stage * C::B_BYTES, &tmB, &full_bar[stage], tap * p.cin + c0, n0);
+          if (ld_b) tma_load_2d_2sm(sB + stage * C::B_BYTES, &tmB, &full_bar[stage], kcol, n0);
+          c0 += BK; kcol += BK;
+          if (c0 == p.cin) { c0 = 0; if (++tw == p.kw) { tw = 0; ++th; } }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (rank == 0) {
@@ -477,19 +484,19 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        if (lane == 0) mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-        __syncwarp();
-        tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          if (lane == 0) {
+      if (lane == 0) {
+        const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+          const int acc = it & 1;
+          const uint32_t acc_phase = (it >> 1) & 1;
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+          tcgen05_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BN;
+          for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(&full_bar[stage], phase);
             tcgen05_fence_after();
-            const uint32_t a_addr = smem_u32(sA + stage * C::A_BYTES);
-            const uint32_t b_addr = smem_u32(sB + stage * C::B_BYTES);
+            const uint32_t a_addr = a_base + stage * C::A_BYTES;
+            const uint32_t b_addr = b_base + stage * C::B_BYTES;
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t adesc = make_kmajor_desc(a_addr + k * UMMA_K * 2, C::SBO, C::SWIZZLE);
@@ -498,11 +505,11 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             }
             umma_commit_2sm(&empty_bar[stage]);                       // frees the slot in BOTH CTAs
             if (kb == num_kb - 1) umma_commit_2sm(&tfull_bar[acc]);   // accumulator ready in BOTH CTAs
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
           }
-          __syncwarp();
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      __syncwarp();
     }
   } else {
     // ===================== epilogue (warps 2..5, both CTAs) =====================

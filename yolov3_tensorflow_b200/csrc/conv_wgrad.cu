@@ -110,13 +110,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (nkb > 0) {
     if (warp == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        if (lane == 0) {
+      if (lane == 0) {   // single-lane loop; the pixel coordinates of the 64-pixel block advance as counters
+        const long pstart = (long)kb0 * WG_BKP;
+        int q = (int)(pstart % p.wo), pp = (int)((pstart / p.wo) % p.ho), img = (int)(pstart / ((long)p.wo * p.ho));
+        const bool two_a = co0 + 64 < p.cout;   // second 64-channel block exists (else its rows are masked anyway)
+        const uint32_t tx_bytes = TP * C::B_BYTES + (two_a ? C::A_BYTES : C::A_BYTES / 2);
+        for (int kb = kb0; kb < kb1; ++kb) {
           const long p0 = (long)kb * WG_BKP;
-          const int q = (int)(p0 % p.wo), pp = (int)((p0 / p.wo) % p.ho), img = (int)(p0 / ((long)p.wo * p.ho));
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          const bool two_a = co0 + 64 < p.cout;   // second 64-channel block exists (else its rows are masked anyway)
-          mbar_arrive_expect_tx(&full_bar[stage], TP * C::B_BYTES + (two_a ? C::A_BYTES : C::A_BYTES / 2));
+          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
           uint8_t* a = sA + stage * C::A_BYTES;
           if (p.a_dilated) {
             tma_load_im2col_4d(a, &tmA, &full_bar[stage], co0, 2 * q, 2 * pp, img, 0, 0);
@@ -129,28 +131,32 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int t = 0; t < TP; ++t) {
             uint8_t* b = sB + (stage * TP + t) * C::B_BYTES;
             const int tap = tap0 + t;
+            const int th = TP == 9 ? t / 3 : (TP == 3 ? tap0 / 3 : tap / p.ksize);
+            const int tw = TP == 9 ? t % 3 : (TP == 3 ? t : tap % p.ksize);
 #pragma unroll
             for (int j = 0; j < C::NB; ++j)
               tma_load_im2col_4d(b + j * WG_BKP * C::B_ROW, &tmB, &full_bar[stage], ci0 + j * C::BCH,
-                                 q * p.stride - p.pad, pp * p.stride - p.pad, img, (uint16_t)(tap % p.ksize),
-                                 (uint16_t)(tap / p.ksize));
+                                 q * p.stride - p.pad, pp * p.stride - p.pad, img, (uint16_t)tw, (uint16_t)th);
           }
+          q += WG_BKP;
+          while (q >= p.wo) { q -= p.wo; if (++pp == p.ho) { pp = 0; ++img; } }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
     } else if (warp == 1) {
       // kind::f16, fp32 accumulate, A and B both MN-major (bits 15/16)
       constexpr uint32_t idesc = make_idesc_f16(WG_BM, BNW, std::is_same<T, __nv_bfloat16>::value) | (1u << 15) | (1u << 16);
       int stage = 0; uint32_t phase = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        if (lane == 0) {
+      if (lane == 0) {
+        const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(sA + stage * C::A_BYTES);
+          const uint32_t a_addr = a_base + stage * C::A_BYTES;
 #pragma unroll
           for (int t = 0; t < TP; ++t) {
-            const uint32_t b_addr = smem_u32(sB + (stage * TP + t) * C::B_BYTES);
+            const uint32_t b_addr = b_base + (stage * TP + t) * C::B_BYTES;
 #pragma unroll
             for (int k = 0; k < WG_BKP / 16; ++k) {
               const uint64_t adesc = make_mnmajor_desc(a_addr + k * 16 * 128, WG_BKP * 128, 1024, 2u);
@@ -160,10 +166,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           umma_commit(&empty_bar[stage]);
           if (kb == kb1 - 1) umma_commit(done_bar);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
     } else {
       // epilogue: rows = output channels, columns = input channels of this tap
       const int quarter = warp & 3;
