@@ -43,7 +43,7 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BN;  // power of two >= 32 for BN in {64,128,256}
-  static constexpr int SMEM_BYTES = SMEM_BUDGET + 1024 /*align*/ + 256 /*barriers*/ + 4 * STAGE_FLOATS * 4 + 2 * BN * 4;
+  static constexpr int SMEM_BYTES = SMEM_BUDGET + 1024 /*align*/ + 256 /*barriers*/ + 4 * STAGE_FLOATS * 4 + 4 * BN * 4;
   static constexpr uint32_t SWIZZLE = (BK == 64) ? 2u : 4u;   // UMMA layout_type: 128B / 64B
   static constexpr uint32_t SBO = 8 * BK * 2;                  // bytes between 8-row groups
 };
@@ -73,9 +73,20 @@ __device__ __forceinline__ void stat_flush(const ConvParams& p, float* s_stat, i
 // One epilogue pass of a warp over its 32 accumulator rows x BN columns:
 // TMEM -> registers -> scale/shift (+leaky) (+residual) -> 16-bit / fp32 global stores
 // (channel-slice and 2x-upsample aware), optional BN batch statistics.
+// executed by the 128 epilogue threads together: (re)load the n-tile's scale/shift into shared memory
+template <int BN>
+__device__ __forceinline__ void load_scale_shift(const ConvParams& p, float* s_ss, int n0, int et /*0..127*/) {
+  asm volatile("bar.sync 1, 128;" ::: "memory");          // nobody still reads the previous n-tile's values
+  for (int c = et; c < BN; c += 128) {
+    s_ss[c] = __ldg(p.scale + n0 + c);
+    s_ss[BN + c] = __ldg(p.shift + n0 + c);
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
 template <typename T, int BN>
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const int row, const int n0, const uint32_t t_row,
-                                              const int lane, float* stage, float* s_stat) {
+                                              const int lane, float* stage, float* s_stat, const float* s_ss) {
   const bool row_ok = row < p.M;
   // output row(s)
   long orow[4];
@@ -95,12 +106,19 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const int row
   } else {
     orow[0] = row;
   }
-#pragma unroll 1
-  for (int ch = 0; ch < BN / 32; ++ch) {
+  // The TMEM load of chunk c+1 is in flight while chunk c is processed (TMEM reads run at 64 B/clk per SM: a
+  // 128x128 fp32 tile alone is 1024 cycles), and scale/shift come from shared memory: the first version waited for
+  // each chunk's tcgen05.ld and for 16 L2-latency loads per chunk, 3.2-3.7 us per 128x128 tile, which bounded every
+  // short-K layer (profiles/r01_j).
+  constexpr int NCH = BN / 32;
+  uint32_t rbuf[2][32];
+  tmem_ld_32x32(t_row, rbuf[0]);
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
     if (n0 + ch * 32 >= p.cout) break;   // zero-padded weight rows (cout_pad > cout): nothing to store
-    uint32_t r[32];
-    tmem_ld_32x32(t_row + ch * 32, r);
     tmem_ld_wait();
+    uint32_t (&r)[32] = rbuf[ch & 1];
+    if (ch + 1 < NCH && n0 + (ch + 1) * 32 < p.cout) tmem_ld_32x32(t_row + (ch + 1) * 32, rbuf[(ch + 1) & 1]);
     const int col0 = n0 + ch * 32;
     if (p.stat_sum != nullptr) {
       // BN batch statistics of the raw conv output.  Transpose the warp's 32x32 block through its staging
@@ -122,12 +140,12 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const int row
     }
     if (row_ok) {
       float v[32];
-      const float4* sc4 = reinterpret_cast<const float4*>(p.scale + col0);
-      const float4* sh4 = reinterpret_cast<const float4*>(p.shift + col0);
+      const float4* sc4 = reinterpret_cast<const float4*>(s_ss + ch * 32);
+      const float4* sh4 = reinterpret_cast<const float4*>(s_ss + BN + ch * 32);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float4 sc = __ldg(sc4 + j);
-        const float4 sh = __ldg(sh4 + j);
+        const float4 sc = sc4[j];
+        const float4 sh = sh4[j];
         v[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), sc.x, sh.x);
         v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), sc.y, sh.y);
         v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), sc.z, sh.z);
@@ -135,7 +153,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const int row
       }
       if (p.leaky) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = leaky01(v[j]);
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.1f * v[j]);   // == v > 0 ? v : 0.1 v
       }
       if (p.res != nullptr) {
         const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const T*>(p.res) +
@@ -222,6 +240,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
   float* stage_base = reinterpret_cast<float*>(smem + SMEM_BUDGET + 256);
   float* s_stat = stage_base + 4 * STAGE_FLOATS;   // [2][BN] per-CTA column sums / sums of squares
+  float* s_ss = s_stat + 2 * BN;                   // [2][BN] scale / shift of the current n-tile
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -336,7 +355,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ===================== epilogue (warps 2..5) =====================
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are this warp's
     const int et = threadIdx.x - 64;
-    int cur_n0 = -1;
+    int cur_n0 = -1, ss_n0 = -1;
     if (p.stat_sum != nullptr) {
       for (int c = et; c < 2 * BN; c += 128) s_stat[c] = 0.f;
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -353,11 +372,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (cur_n0 >= 0) stat_flush<BN>(p, s_stat, cur_n0, et);
         cur_n0 = n0;
       }
+      if (n0 != ss_n0) { load_scale_shift<BN>(p, s_ss, n0, et); ss_n0 = n0; }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_fence_after();
       if (!(p.dbg & 8))
         epilogue_tile<T, BN>(p, m0 + quarter * 32 + lane, n0, tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN, lane,
-                             stage_base + (warp - 2) * STAGE_FLOATS, s_stat);
+                             stage_base + (warp - 2) * STAGE_FLOATS, s_stat, s_ss);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -388,7 +408,7 @@ struct Cfg2 {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 4 * STAGE_FLOATS * 4 + 2 * BN * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 4 * STAGE_FLOATS * 4 + 4 * BN * 4;
   static constexpr uint32_t SWIZZLE = (BK == 64) ? 2u : 4u;
   static constexpr uint32_t SBO = 8 * BK * 2;
 };
@@ -410,6 +430,7 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
   float* stage_base = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
   float* s_stat = stage_base + 4 * STAGE_FLOATS;
+  float* s_ss = s_stat + 2 * BN;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -515,7 +536,7 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     // ===================== epilogue (warps 2..5, both CTAs) =====================
     const int quarter = warp & 3;
     const int et = threadIdx.x - 64;
-    int cur_n0 = -1;
+    int cur_n0 = -1, ss_n0 = -1;
     if (p.stat_sum != nullptr) {
       for (int c = et; c < 2 * BN; c += 128) s_stat[c] = 0.f;
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -532,10 +553,11 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (cur_n0 >= 0) stat_flush<BN>(p, s_stat, cur_n0, et);
         cur_n0 = n0;
       }
+      if (n0 != ss_n0) { load_scale_shift<BN>(p, s_ss, n0, et); ss_n0 = n0; }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_fence_after();
       epilogue_tile<T, BN>(p, m0 + quarter * 32 + lane, n0, tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN, lane,
-                           stage_base + (warp - 2) * STAGE_FLOATS, s_stat);
+                           stage_base + (warp - 2) * STAGE_FLOATS, s_stat, s_ss);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);    // the leader's MMA warp waits for both CTAs
@@ -578,6 +600,7 @@ conv_igemm_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
   float* stage_base = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
   float* s_stat = stage_base + 4 * STAGE_FLOATS;
+  float* s_ss = s_stat + 2 * BN;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -691,7 +714,7 @@ conv_igemm_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // ===================== epilogue (warps 2..5, both CTAs) =====================
     const int quarter = warp & 3;
     const int et = threadIdx.x - 64;
-    int cur_n0 = -1;
+    int cur_n0 = -1, ss_n0 = -1;
     if (p.stat_sum != nullptr) {
       for (int c = et; c < 2 * BN; c += 128) s_stat[c] = 0.f;
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -708,10 +731,11 @@ conv_igemm_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (cur_n0 >= 0) stat_flush<BN>(p, s_stat, cur_n0, et);
         cur_n0 = n0;
       }
+      if (n0 != ss_n0) { load_scale_shift<BN>(p, s_ss, n0, et); ss_n0 = n0; }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_fence_after();
       epilogue_tile<T, BN>(p, m0 + quarter * 32 + lane, n0, tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN, lane,
-                           stage_base + (warp - 2) * STAGE_FLOATS, s_stat);
+                           stage_base + (warp - 2) * STAGE_FLOATS, s_stat, s_ss);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], crank & ~1u);   // this pair's leader
