@@ -393,7 +393,7 @@ def main():
             traffic = tj["dram_bytes_per_step"]
     except Exception:
         pass
-    roofline = {"bound": "tensor", "kernel": "conv layers 1..74 (72 tcgen05 conv_igemm launches + 2 mma.sync conv_thin launches per step)",
+    roofline = {"bound": "tensor", "kernel": "conv_igemm (74 tcgen05 launches per step: layers 1..74, 1-CTA and CTA-pair kernels)",
                 "achieved": achieved,
                 "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": traffic,
                 "peak_source": pk["src"], "ms_per_step_conv": conv_t * 1e3, "ms_per_step_stem": float(np.mean(stem_ms)),
@@ -444,8 +444,8 @@ def main():
             "e2e": {"value": imgs / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": args.steps * (1 + 74 + 1 + 3),
-            "launches_per_step": {"stem(mma.sync)": 1, "conv_thin(mma.sync, layers 1 and 3)": 2,
-                                  "conv_igemm(tcgen05: 1-CTA + CTA-pair kernels)": 72, "predict": 1, "nms": 3},
+            "launches_per_step": {"stem(mma.sync)": 1, "conv_igemm(tcgen05: 1-CTA + CTA-pair kernels)": 74, "predict": 1,
+                                  "nms": 3},
             "detections_per_step": n_det, "clocks": clocks, "roofline": roofline,
             "fraction_of_conv_flop_roofline": (value / world) * FWD_GFLOP_416 * scale * 1e9 / (pk["tflops"] * 1e12)}
     if train is not None:

@@ -133,16 +133,23 @@ conv_thin_kernel(const ThinParams p) {
       // im2col of the thread's pixel: 27 taps -> one 32-wide fp16 row
       const float* hf = reinterpret_cast<const float*>(s_halo);
       const int py = tid / TW, px = tid % TW;
-      T* arow = reinterpret_cast<T*>(s_a + tid * C::A_PITCH);
+      float pv[32];
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
         for (int s = 0; s < 3; ++s)
 #pragma unroll
-          for (int c = 0; c < 3; ++c)
-            arow[(r * 3 + s) * 3 + c] = static_cast<T>(hf[((py + r) * C::HW + (px + s)) * 3 + c]);
+          for (int c = 0; c < 3; ++c) pv[(r * 3 + s) * 3 + c] = hf[((py + r) * C::HW + (px + s)) * 3 + c];
 #pragma unroll
-      for (int k = 27; k < 32; ++k) arow[k] = static_cast<T>(0.f);
+      for (int k = 27; k < 32; ++k) pv[k] = 0.f;
+      uint4* arow = reinterpret_cast<uint4*>(s_a + tid * C::A_PITCH);   // 80-byte pitch: 16-byte aligned rows
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {                                     // four 128-bit stores instead of 32 16-bit ones
+        uint4 u;
+        u.x = Pack2<T>::pack(pv[8 * j + 0], pv[8 * j + 1]); u.y = Pack2<T>::pack(pv[8 * j + 2], pv[8 * j + 3]);
+        u.z = Pack2<T>::pack(pv[8 * j + 4], pv[8 * j + 5]); u.w = Pack2<T>::pack(pv[8 * j + 6], pv[8 * j + 7]);
+        arow[j] = u;
+      }
       __syncthreads();
     }
     // ---- main loop: each warp computes 2 output rows (2 x m16) x COUT ----
@@ -299,11 +306,17 @@ stem_wgrad_tc_kernel(const float* __restrict__ x, const T* __restrict__ dz, int 
 #pragma unroll
       for (int k = 27; k < 32; ++k) v[k] = 0.f;
 #pragma unroll
-      for (int k = 0; k < 32; k += 2) {
-        const uint32_t hq = Pack2<T>::pack(v[k], v[k + 1]);
-        const float2 hf = Pack2<T>::unpack(hq);
-        hi[k >> 1] = hq;
-        lo[k >> 1] = Pack2<T>::pack(v[k] - hf.x, v[k + 1] - hf.y);
+      for (int j = 0; j < 4; ++j) {                       // 128-bit stores (80-byte row pitch keeps 16-byte alignment)
+        uint32_t hq[4], lq[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k = 8 * j + 2 * e;
+          hq[e] = Pack2<T>::pack(v[k], v[k + 1]);
+          const float2 hf = Pack2<T>::unpack(hq[e]);
+          lq[e] = Pack2<T>::pack(v[k] - hf.x, v[k + 1] - hf.y);
+        }
+        reinterpret_cast<uint4*>(hi)[j] = make_uint4(hq[0], hq[1], hq[2], hq[3]);
+        reinterpret_cast<uint4*>(lo)[j] = make_uint4(lq[0], lq[1], lq[2], lq[3]);
       }
     }
     cp_async_wait_all();

@@ -292,7 +292,10 @@ extern "C" int yb_net_forward_layers(yb_net* net, const float* images, float* fm
   }
   for (size_t i = first > 1 ? first : 1; i < net->layers.size() && (int)i <= last; ++i) {
     Layer& L = net->layers[i];
-    if (thin && L.info.ksize == 3 && L.info.cin == 32 && L.info.has_bn && !L.upsample) {
+    // (after the r01_j pipeline-loop fixes the tcgen05 kernel runs these two layers in ~455 us against ~500-550 us for
+    //  the mma.sync halo kernel, so the latter is now opt-in: YB_THIN=2)
+    static const bool thin_cin32 = getenv("YB_THIN") && getenv("YB_THIN")[0] == '2';
+    if (thin_cin32 && L.info.ksize == 3 && L.info.cin == 32 && L.info.has_bn && !L.upsample) {
       // Cin = 32: 64-byte im2col rows halve the TMA line rate -> direct halo-tile kernel (csrc/conv_thin.cu)
       yb_conv_desc d;
       memset(&d, 0, sizeof(d));
