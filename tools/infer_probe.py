@@ -12,9 +12,10 @@ m = pkg.yolov3(80, anchors, dtype="fp16")
 m.init_params(3)
 rng = np.random.default_rng(3)
 x = torch.from_numpy(rng.random((b, size, size, 3), dtype=np.float32)).cuda()
+torch.cuda.synchronize(); torch.cuda.profiler.start()   # ncu --profile-from-start off: only the steps are captured
 for _ in range(steps):
     fms = m.forward(x, is_training=False)
     boxes, scores = m.predict_scores(fms)
     out = batched_gpu_nms(boxes, scores, 80, max_boxes=200, score_thresh=0.3, nms_thresh=0.45)
-torch.cuda.synchronize()
+torch.cuda.synchronize(); torch.cuda.profiler.stop()
 print("detections", sum(int(o[0].shape[0]) for o in out))

@@ -29,6 +29,7 @@ struct ThinParams {
   int ho, wo;           // output spatial size
   int tiles_y, tiles_x, num_tiles;
   int leaky;
+  int dbg;              // timing experiments (YB_STEM_DBG bitmask): 1 no halo load, 2 no im2col, 4 no MMA, 8 no stores
 };
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
@@ -101,6 +102,28 @@ conv_thin_kernel(const ThinParams p) {
     }
   }
 
+  // stem: the NEXT tile's halo (float32 image) is fetched into registers while the current tile is processed — a
+  // tile's 540 scalar loads were issued and awaited serially before, 43 % of the kernel (profiles/r01_j: 665 -> 379 us
+  // with the loads removed)
+  constexpr int HN = STEM ? C::HH * C::HW * 3 : 1;
+  constexpr int NL = (HN + THIN_THREADS - 1) / THIN_THREADS;
+  float pre[NL];
+  auto fetch_halo = [&](int tile) {
+    const int tx = tile % p.tiles_x;
+    const int ty = (tile / p.tiles_x) % p.tiles_y;
+    const int img = tile / (p.tiles_x * p.tiles_y);
+    const int iy0 = ty * TH * STRIDE - 1, ix0 = tx * TW * STRIDE - 1;
+    const float* xin = static_cast<const float*>(p.x) + (long)img * p.h * p.w * 3;
+#pragma unroll
+    for (int k = 0; k < NL; ++k) {
+      const int i = tid + k * THIN_THREADS;
+      const int c = i % 3, px = (i / 3) % C::HW, py = i / (3 * C::HW);
+      const int gy = iy0 + py, gx = ix0 + px;
+      pre[k] = (i < HN && gy >= 0 && gy < p.h && gx >= 0 && gx < p.w) ? __ldg(xin + ((long)gy * p.w + gx) * 3 + c) : 0.f;
+    }
+  };
+  if (STEM && (int)blockIdx.x < p.num_tiles && !(p.dbg & 1)) fetch_halo(blockIdx.x);
+
   for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
     const int tx = tile % p.tiles_x;
     const int ty = (tile / p.tiles_x) % p.tiles_y;
@@ -110,12 +133,14 @@ conv_thin_kernel(const ThinParams p) {
     __syncthreads();                                            // previous tile done with s_halo / s_o
     // ---- halo tile ----
     if (STEM) {
-      const float* xin = static_cast<const float*>(p.x) + (long)img * p.h * p.w * 3;
       float* hf = reinterpret_cast<float*>(s_halo);
-      for (int i = tid; i < C::HH * C::HW * 3; i += THIN_THREADS) {
-        const int c = i % 3, px = (i / 3) % C::HW, py = i / (3 * C::HW);
-        const int gy = iy0 + py, gx = ix0 + px;
-        hf[i] = (gy >= 0 && gy < p.h && gx >= 0 && gx < p.w) ? xin[((long)gy * p.w + gx) * 3 + c] : 0.f;
+      if (!(p.dbg & 1)) {
+#pragma unroll
+        for (int k = 0; k < NL; ++k) {
+          const int i = tid + k * THIN_THREADS;
+          if (i < HN) hf[i] = pre[k];
+        }
+        if (tile + (int)gridDim.x < p.num_tiles) fetch_halo(tile + gridDim.x);
       }
     } else {
       const T* xin = static_cast<const T*>(p.x) + (long)img * p.h * p.w * p.x_ld;
@@ -129,7 +154,7 @@ conv_thin_kernel(const ThinParams p) {
     }
     cp_async_wait_all();
     __syncthreads();
-    if (STEM) {
+    if (STEM && !(p.dbg & 2)) {
       // im2col of the thread's pixel: 27 taps -> one 32-wide fp16 row
       const float* hf = reinterpret_cast<const float*>(s_halo);
       const int py = tid / TW, px = tid % TW;
@@ -150,8 +175,8 @@ conv_thin_kernel(const ThinParams p) {
         u.z = Pack2<T>::pack(pv[8 * j + 4], pv[8 * j + 5]); u.w = Pack2<T>::pack(pv[8 * j + 6], pv[8 * j + 7]);
         arow[j] = u;
       }
-      __syncthreads();
     }
+    if (STEM) __syncthreads();
     // ---- main loop: each warp computes 2 output rows (2 x m16) x COUT ----
     constexpr int NT = COUT / 8;                                // n8 tiles
     float acc[2][NT][4];
@@ -163,7 +188,7 @@ conv_thin_kernel(const ThinParams p) {
         for (int q = 0; q < 4; ++q) acc[mi][nj][q] = 0.f;
     constexpr int KSTEPS = C::K / 16;
 #pragma unroll 1
-    for (int ks = 0; ks < KSTEPS; ++ks) {
+    for (int ks = 0; ks < ((STEM && (p.dbg & 4)) ? 0 : KSTEPS); ++ks) {
       uint32_t a[2][4];
 #pragma unroll
       for (int mi = 0; mi < 2; ++mi) {
@@ -229,7 +254,7 @@ conv_thin_kernel(const ThinParams p) {
     for (int i = tid; i < 128 * OCH; i += THIN_THREADS) {
       const int px = i / OCH, ch = i - px * OCH;
       const int oy = oy0 + px / TW, ox = ox0 + px % TW;
-      if (oy < p.ho && ox < p.wo) {
+      if (oy < p.ho && ox < p.wo && !(STEM && (p.dbg & 8))) {
         const uint4 v = *reinterpret_cast<const uint4*>(s_o + px * C::O_PITCH + ch * 16);
         *reinterpret_cast<uint4*>(static_cast<T*>(p.out) + (((long)img * p.ho + oy) * p.wo + ox) * p.out_ld + ch * 8) = v;
       }
@@ -271,6 +296,24 @@ stem_wgrad_tc_kernel(const float* __restrict__ x, const T* __restrict__ dz, int 
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc[mi][nj][q] = 0.f;
 
+  constexpr int HN = HH * HW * 3;
+  constexpr int NL = (HN + THIN_THREADS - 1) / THIN_THREADS;
+  float pre[NL];
+  auto fetch_halo = [&](int tile) {
+    const int tx = tile % tiles_x;
+    const int ty = (tile / tiles_x) % tiles_y;
+    const int img = tile / (tiles_x * tiles_y);
+    const float* xin = x + (long)img * h * w * 3;
+#pragma unroll
+    for (int k = 0; k < NL; ++k) {
+      const int i = tid + k * THIN_THREADS;
+      const int c = i % 3, px = (i / 3) % HW, py = i / (3 * HW);
+      const int gy = ty * TH - 1 + py, gx = tx * TW - 1 + px;
+      pre[k] = (i < HN && gy >= 0 && gy < h && gx >= 0 && gx < w) ? __ldg(xin + ((long)gy * w + gx) * 3 + c) : 0.f;
+    }
+  };
+  if ((int)blockIdx.x < num_tiles) fetch_halo(blockIdx.x);
+
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const int tx = tile % tiles_x;
     const int ty = (tile / tiles_x) % tiles_y;
@@ -285,12 +328,12 @@ stem_wgrad_tc_kernel(const float* __restrict__ x, const T* __restrict__ dz, int 
       const T* src = ok ? dz + (((long)img * h + oy) * w + ox) * 32 + ch * 8 : dz;
       cp_async16(s_dz + px * PITCH + ch * 16, src, ok ? 16 : 0);
     }
-    const float* xin = x + (long)img * h * w * 3;
-    for (int i = tid; i < HH * HW * 3; i += THIN_THREADS) {
-      const int c = i % 3, px = (i / 3) % HW, py = i / (3 * HW);
-      const int gy = oy0 - 1 + py, gx = ox0 - 1 + px;
-      s_halo[i] = (gy >= 0 && gy < h && gx >= 0 && gx < w) ? xin[((long)gy * w + gx) * 3 + c] : 0.f;
+#pragma unroll
+    for (int k = 0; k < NL; ++k) {
+      const int i = tid + k * THIN_THREADS;
+      if (i < HN) s_halo[i] = pre[k];
     }
+    if (tile + (int)gridDim.x < num_tiles) fetch_halo(tile + gridDim.x);   // next tile's image halo, in flight during this tile
     __syncthreads();
     {   // im2col of the thread's pixel, split into head + remainder
       const int py = tid / TW, px = tid % TW;
@@ -402,7 +445,7 @@ extern "C" int yb_conv3x3_thin_fwd(const yb_conv_desc* d, const void* x, const v
   p.ho = d->h / d->stride; p.wo = d->w / d->stride;
   p.tiles_y = ceil_div(p.ho, TH); p.tiles_x = ceil_div(p.wo, TW);
   p.num_tiles = p.tiles_x * p.tiles_y * d->n;
-  p.leaky = d->leaky;
+  p.leaky = d->leaky; p.dbg = 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define YB_THIN(T)                                                                         \
   if (d->cout == 64 && d->stride == 1) return launch_thin<T, 64, 1, false>(p, st);        \
@@ -424,6 +467,7 @@ extern "C" int yb_stem_conv_fwd_tc(const float* x, const float* w_ohwi, const fl
   p.tiles_y = ceil_div(h, TH); p.tiles_x = ceil_div(w, TW);
   p.num_tiles = p.tiles_x * p.tiles_y * n;
   p.leaky = leaky;
+  { const char* dbg = getenv("YB_STEM_DBG"); p.dbg = dbg ? atoi(dbg) : 0; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == YB_F16) return launch_thin<__half, 32, 1, true>(p, st);
   if (dtype == YB_BF16) return launch_thin<__nv_bfloat16, 32, 1, true>(p, st);
