@@ -12,6 +12,7 @@ m.init_params(3)
 rng = np.random.default_rng(3)
 x = torch.from_numpy(rng.random((tb, ts, ts, 3), dtype=np.float32)).cuda()
 y = bench.synth_y_true(rng, tb, ts, anchors)
+m.train_step(x, y, 1e-4)   # warm-up: builds the plan, packs weights
 torch.cuda.synchronize(); torch.cuda.profiler.start()   # ncu --profile-from-start off: only the steps are captured
 for _ in range(steps):
     l = m.train_step(x, y, 1e-4)

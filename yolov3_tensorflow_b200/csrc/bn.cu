@@ -164,6 +164,12 @@ bn_bwd_reduce_kernel(const T* __restrict__ dA, long dA_ld, const T* __restrict__
   __shared__ unsigned int s_last;
   const int cvi = threadIdx.x % sg.cv, lane_r = threadIdx.x / sg.cv;
   const int c0 = cvi * 8;
+  // per-channel coefficients live in registers (the first version re-loaded four of them per ELEMENT through the LSU,
+  // which made this kernel 2x slower than bn_bwd_apply on the same data: profiles/r01_k).  The invstd factor of
+  // zhat = (z - mean) * invstd is folded in once per block at the end.
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; }
   float ag[8], ab[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) ag[j] = ab[j] = 0.f;
@@ -184,13 +190,16 @@ bn_bwd_reduce_kernel(const T* __restrict__ dA, long dA_ld, const T* __restrict__
       else load_dA(dA, dA_ld, rb + (long)u * sg.lanes, c0, g, 1, dv);   // fp32 sum of the 4 upsampled copies
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float y = fmaf(zv[j], __ldg(scale + c0 + j), __ldg(shift + c0 + j));
+        const float y = fmaf(zv[j], sc[j], sh[j]);
         const float da = (leaky && y <= 0.f) ? 0.1f * dv[j] : dv[j];
         ab[j] += da;
-        ag[j] = fmaf(da, (zv[j] - __ldg(save_mean + c0 + j)) * __ldg(save_invstd + c0 + j), ag[j]);
+        ag[j] = fmaf(da, zv[j], ag[j]);        // sum(da * z); centred and scaled below
       }
     }
   }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)   // sum(da * zhat) = invstd * (sum(da * z) - mean * sum(da))   (linear: exact per block)
+    ag[j] = (ag[j] - __ldg(save_mean + c0 + j) * ab[j]) * __ldg(save_invstd + c0 + j);
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s_g[threadIdx.x][j] = ag[j]; s_b[threadIdx.x][j] = ab[j]; }
   __syncthreads();
