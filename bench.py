@@ -121,10 +121,23 @@ def cpu_step(O, x, params, anchors):
 def run_cpu(size, steps, warmup, sample_images):
     import torch
     from oracle import yolov3_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    ncpu = os.cpu_count() or 1
     params = make_bench_params()
     x = np.random.default_rng(2).random((sample_images, size, size, 3), dtype=np.float32)
+    # give the CPU port its best thread count: all cores is NOT the fastest on a 128-core host for a 2-image sample
+    # (0.07-0.5 img/s with 128 threads against several img/s with 16-32), so calibrate on one image first
+    cands = sorted({ncpu, min(ncpu, 64), min(ncpu, 32), min(ncpu, 16)}, reverse=True)
+    best_t, cores = None, ncpu
+    if len(cands) > 1:
+        for t in cands:
+            torch.set_num_threads(t)
+            cpu_step(O, x[:1], params, O.COCO_ANCHORS)
+            t0 = time.perf_counter()
+            cpu_step(O, x[:1], params, O.COCO_ANCHORS)
+            dt = time.perf_counter() - t0
+            if best_t is None or dt < best_t:
+                best_t, cores = dt, t
+    torch.set_num_threads(cores)
     for _ in range(warmup):
         cpu_step(O, x, params, O.COCO_ANCHORS)
     t0 = time.perf_counter()
@@ -141,7 +154,8 @@ def run_cpu(size, steps, warmup, sample_images):
         pass
     return dict(value=sample_images * steps / dt, unit="images/s", cores=cores, kind="port", cpu_model=model,
                 sample=f"{steps} passes over {sample_images} image(s) {size}x{size} (forward+decode+NMS, fp32, torch-CPU conv2d "
-                       f"restatement of the TF1 graph; TensorFlow not installable in this image)"), dt / steps
+                       f"restatement of the TF1 graph; TensorFlow not installable in this image; "
+                       f"{cores} of {ncpu} host threads, the fastest of {cands} on a 1-image calibration)"), dt / steps
 
 
 def nms_stress(pkg, with_cpu):
