@@ -159,13 +159,14 @@ def run_cpu(size, steps, warmup, sample_images):
                 best, threads = dt, t
         del params
     workers = max(1, ncpu // threads)
-    if workers == 1:
-        images, dt = _cpu_worker(size, steps, warmup, sample_images, threads)
-        per_step = dt / steps
-    else:
+    images, dt = _cpu_worker(size, steps, warmup, sample_images, threads)      # one process, calibrated thread count
+    per_step = dt / steps
+    single = (images, dt)
+    if workers > 1:
         cmd = [sys.executable, os.path.abspath(__file__), "--cpu-worker",
                f"{size},{steps},{warmup},{sample_images},{threads}"]
         env = dict(os.environ, OMP_NUM_THREADS=str(threads), MKL_NUM_THREADS=str(threads), CUDA_VISIBLE_DEVICES="")
+        procs = []
         try:
             procs = [subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env) for _ in range(workers)]
             images, dt = 0, 0.0
@@ -178,8 +179,12 @@ def run_cpu(size, steps, warmup, sample_images):
             for pr in procs:
                 if pr.poll() is None:
                     pr.kill()
+            images, dt = 0, 1.0
+        # measured on the 128-core GPU box: 8 workers x 16 threads reach 5.3 img/s together, ONE 16-thread process 7.7 —
+        # the workers contend (memory bandwidth / thread placement), so report whichever configuration is faster
+        if images / dt <= single[0] / single[1]:
+            images, dt = single
             workers = 1
-            images, dt = _cpu_worker(size, steps, warmup, sample_images, threads)
         per_step = dt / steps
     model = ""
     try:
@@ -190,7 +195,8 @@ def run_cpu(size, steps, warmup, sample_images):
     except Exception:
         pass
     return dict(value=images / dt, unit="images/s", cores=workers * threads, kind="port", cpu_model=model,
-                sample=f"{workers} worker process(es) x {threads} threads, each {steps} passes over {sample_images} image(s) "
+                sample=f"{workers} worker process(es) x {threads} threads (the faster of 1 process and {max(1, ncpu // threads)} "
+                       f"concurrent processes), each {steps} passes over {sample_images} image(s) "
                        f"{size}x{size} (forward+decode+NMS, fp32, torch-CPU conv2d restatement of the TF1 graph; TensorFlow "
                        f"not installable in this image; threads per process = fastest of {cands} on a 1-image calibration)"), per_step
 
