@@ -14,6 +14,7 @@ struct ConvParams {
   int im2col;             // 1: A via im2col TMA, 0: A via 2D tiled TMA
   int two_cta;            // 1: cta_group::2 kernel (256-row tiles per CTA pair)
   int b_resident;         // 1-CTA kernel: the whole [BN, K] weight tile stays in shared memory (single n-tile, fits)
+  int kps;                // 1-CTA kernel: k-blocks per barrier phase (one empty/full handshake per kps k-blocks)
   int dbg;                // timing experiments only (YB_CONV_DBG bitmask: 1 skip A loads, 2 skip B loads, 4 skip MMAs)
   int mc_m, mc_n;         // cluster of mc_m x mc_n pairs with TMA multicast (1,1: plain pair kernel)
   int num_m_tiles, num_n_tiles;

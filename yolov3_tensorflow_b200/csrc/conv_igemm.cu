@@ -225,12 +225,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int num_kb_ = p.kh * p.kw * kb_per_tap_;
   // operand ring: [nst x A][nst x B], or with resident weights [nst x A][num_kb x B] (B loaded once per CTA)
   int nst = C::STAGES;
+  const int kps = p.kps;                 // slots per barrier group (1: one handshake per k-block)
+  if (kps > 1) nst = (C::STAGES / kps);  // number of groups; slot index = group * kps + j
   if (p.b_resident) {
     nst = (SMEM_BUDGET - num_kb_ * C::B_BYTES) / C::A_BYTES;
     if (nst > 8) nst = 8;
   }
   uint8_t* sA = smem;
-  uint8_t* sB = smem + nst * C::A_BYTES;
+  uint8_t* sB = smem + nst * (kps > 1 ? kps : 1) * C::A_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BUDGET);
   uint64_t* full_bar = bars;                       // [<=8] TMA -> MMA
   uint64_t* empty_bar = bars + 8;                  // [<=8] MMA -> TMA
@@ -298,21 +300,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int w_base = q * p.stride - p.pad;
         const int h_base = pp * p.stride - p.pad;
         int c0 = 0, tw = 0, th = 0, kcol = 0;                  // channel chunk, tap (tw, th), column in the packed weights
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = 0; kb < num_kb; kb += kps) {
+          // one handshake per group of kps k-blocks: the short-K-block layers (Cin = 32: two 32-cycle MMAs per
+          // k-block) were bound by ~230-440 ns of barrier round trip per k-block (profiles/r01_k_layers_infer.md)
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (tx_bytes) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+          if (tx_bytes) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes * kps);
           else mbar_arrive(&full_bar[stage]);
-          if (ld_a) {
-            if (p.im2col) {
-              tma_load_im2col_4d(sA + stage * C::A_BYTES, &tmA, &full_bar[stage], c0, w_base, h_base, img, (uint16_t)tw,
-                                 (uint16_t)th);
-            } else {
-              tma_load_2d(sA + stage * C::A_BYTES, &tmA, &full_bar[stage], c0, m0);
+          for (int j = 0; j < kps; ++j) {
+            const int slot = stage * kps + j;
+            if (ld_a) {
+              if (p.im2col) {
+                tma_load_im2col_4d(sA + slot * C::A_BYTES, &tmA, &full_bar[stage], c0, w_base, h_base, img, (uint16_t)tw,
+                                   (uint16_t)th);
+              } else {
+                tma_load_2d(sA + slot * C::A_BYTES, &tmA, &full_bar[stage], c0, m0);
+              }
             }
+            if (ld_b) tma_load_2d(sB + slot * C::B_BYTES, &tmB, &full_bar[stage], kcol, n0);
+            c0 += BK; kcol += BK;
+            if (c0 == p.cin) { c0 = 0; if (++tw == p.kw) { tw = 0; ++th; } }
           }
-          if (ld_b) tma_load_2d(sB + stage * C::B_BYTES, &tmB, &full_bar[stage], kcol, n0);
-          c0 += BK; kcol += BK;
-          if (c0 == p.cin) { c0 = 0; if (++tw == p.kw) { tw = 0; ++th; } }
           if (++stage == nst) { stage = 0; phase ^= 1; }
         }
       }
@@ -333,19 +340,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue drained this accumulator
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = 0; kb < num_kb; kb += kps) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
-          const uint32_t a_addr = a_base + stage * C::A_BYTES;
-          const uint32_t b_addr = b_base + (p.b_resident ? kb : stage) * C::B_BYTES;
+          for (int j = 0; j < kps; ++j) {
+            const int slot = stage * kps + j;
+            const uint32_t a_addr = a_base + slot * C::A_BYTES;
+            const uint32_t b_addr = b_base + (p.b_resident ? kb : slot) * C::B_BYTES;
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t adesc = make_kmajor_desc(a_addr + k * UMMA_K * 2, C::SBO, C::SWIZZLE);
-            const uint64_t bdesc = make_kmajor_desc(b_addr + k * UMMA_K * 2, C::SBO, C::SWIZZLE);
-            if (!(p.dbg & 4)) umma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t adesc = make_kmajor_desc(a_addr + k * UMMA_K * 2, C::SBO, C::SWIZZLE);
+              const uint64_t bdesc = make_kmajor_desc(b_addr + k * UMMA_K * 2, C::SBO, C::SWIZZLE);
+              if (!(p.dbg & 4)) umma_f16(d_tmem, adesc, bdesc, idesc, (kb | j | k) != 0);
+            }
           }
-          umma_commit(&empty_bar[stage]);                       // smem slot reusable once these MMAs retire
-          if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
+          umma_commit(&empty_bar[stage]);                             // smem slots reusable once these MMAs retire
+          if (kb + kps >= num_kb) umma_commit(&tfull_bar[acc]);       // accumulator complete
           if (++stage == nst) { stage = 0; phase ^= 1; }
         }
       }
@@ -1006,12 +1016,26 @@ static int conv_prepare_core(const yb_conv_desc* d, int win, int kh, int kw, int
   }
   p->mc_m = mc_m; p->mc_n = mc_n;
   { const char* dbg = getenv("YB_CONV_DBG"); p->dbg = dbg ? atoi(dbg) : 0; }
+  p->kps = 1;   // set below once the tile shape is known
   const int bn = two ? conv_block_n2(cout_pad) : conv_block_n(cout_pad);
   {
     // resident weights (1-CTA kernel): one n-tile, and the [BN, K] tile leaves room for >= 3 A stages
     const long b_bytes = (long)kh * kw * d->cin * bn * 2;
     const char* br = getenv("YB_CONV_BRES");
     p->b_resident = (!two && cout_pad == bn && SMEM_BUDGET - b_bytes >= 3L * BLOCK_M * bk * 2 && (br && br[0] == '1')) ? 1 : 0;   // opt-in: measured no gain (profiles/r01_i)
+  }
+  if (!two && !p->b_resident) {
+    // k-blocks per barrier phase in the 1-CTA kernel: the largest of {4, 3, 2} that divides the k-block count and still
+    // leaves two groups in the ring.  YB_CONV_KPS=0 restores one handshake per k-block.
+    const char* ke = getenv("YB_CONV_KPS");
+    const bool on = !(ke && ke[0] == '0');
+    const int num_kb = kh * kw * (d->cin / bk);
+    const long stage_bytes = (long)(BLOCK_M + bn) * bk * 2;
+    int stages = (int)(SMEM_BUDGET / stage_bytes);
+    if (stages > 8) stages = 8;
+    if (on)
+      for (int c = 4; c >= 2; --c)
+        if (num_kb % c == 0 && stages / c >= 2) { p->kps = c; break; }
   }
   p->cout = d->cout; p->cin = d->cin; p->ksize = d->ksize; p->stride = d->stride; p->pad = pad;
   p->kh = kh; p->kw = kw; p->scatter = scatter;
