@@ -45,6 +45,11 @@ typedef enum yb_wlayout {
 
 int yb_version(void);
 const char* yb_last_error_string(void);
+/* Runtime switches for A/B experiments and tests ("YB_CONV_MODE", "YB_CONV_EPI", ...).  The table is
+ * seeded once from the equally named environment variables when the library is first used; afterwards only
+ * yb_set_option() changes it (value NULL or "" = default).  No entry point calls getenv() on its own. */
+int yb_set_option(const char* key, const char* value);
+const char* yb_get_option(const char* key);
 /* device 0..: SM count and compute capability of the current device. */
 int yb_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
@@ -68,7 +73,10 @@ typedef struct yb_conv_desc {
                           in an [n, 2*ho, 2*wo, out_ld] buffer (model.py:61,71)             */
 } yb_conv_desc;
 
-/* out[p, co] = act( scale[co] * sum_{r,s,ci} x[p*stride + (r,s) - pad, ci] * w[co,r,s,ci] + shift[co] ) (+ res[p, co])
+/* Epilogue note (round 2): 16-bit outputs leave each CTA through swizzled shared memory and cp.async.bulk.tensor
+ * (TMA) stores, the residual arrives by TMA into the same staging tile; scale = shift = NULL means identity.
+ *
+ * out[p, co] = act( scale[co] * sum_{r,s,ci} x[p*stride + (r,s) - pad, ci] * w[co,r,s,ci] + shift[co] ) (+ res[p, co])
  *   x        [n,h,w,in_ld]   dtype
  *   w_packed [cout_pad, ksize, ksize, cin] dtype, cout_pad = yb_conv_cout_pad(cout) (zero rows beyond cout)
  *   scale, shift  float32 [cout_pad]   (BN folded: gamma/sqrt(var+eps), beta-mean*scale; heads: 1, bias)
@@ -199,10 +207,13 @@ int yb_loss_workspace_bytes(int n, int gh, int gw, size_t* bytes);
  * carries the 1/N of model.py:276-302, N = 1/inv_batch).
  * dfm (nullable) receives d(total)/d(feature_map): dfm_dtype YB_F32 -> same layout as feature_map;
  * YB_F16/YB_BF16 -> [n*gh*gw, dfm_ld] rows (dfm_ld >= 3*(5+C), padding columns zeroed) for the backward GEMMs. */
+/* loss_scale (> 0; 1 = off) multiplies the stored gradient only (not the loss values): the fp16 backward chain
+ * needs it to keep small gradients above the subnormal range; the optimizer divides it out again
+ * (yb_optimizer.grad_scale) and skips a step whose gradient is non-finite. */
 int yb_loss_layer(const float* feature_map, const float* y_true, int n, int gh, int gw, int img_h, int img_w,
                   int class_num, const float* anchors3x2, int use_label_smooth, int use_focal_loss,
-                  float inv_batch, void* workspace, size_t workspace_bytes, double* loss4, void* dfm,
-                  int dfm_dtype, int dfm_ld, void* stream);
+                  float inv_batch, float loss_scale, void* workspace, size_t workspace_bytes, double* loss4,
+                  void* dfm, int dfm_dtype, int dfm_ld, void* stream);
 /* out5 (device float[5]) = [total, xy, wh, conf, class] (model.py:364-365). */
 int yb_loss_finalize(const double* loss4, float* out5, void* stream);
 /* box_iou (model.py:307-345): pred_boxes [P,4], true_boxes [V,4] (cx,cy,w,h) -> iou [P,V]. */
@@ -231,9 +242,16 @@ int yb_net_destroy(yb_net* net);
 int yb_net_num_layers(const yb_net* net);
 int yb_net_layer_info(const yb_net* net, int layer, yb_layer_info* info);
 int yb_net_arena_bytes(const yb_net* net, size_t* activation_bytes, size_t* param_bytes);
-/* Bind caller-owned arenas (256-byte aligned).  Must be called before set_params/forward. */
+/* Bind caller-owned arenas (256-byte aligned).  Must be called before set_params/forward.  The PARAMETER arena layout
+ * depends only on (class_num, dtype, training): plans of different batch / image sizes may share one parameter arena
+ * (master weights, 16-bit copies, folded BN, optimizer slots) — this is how one model serves multi-scale training
+ * (train.py:47-49 multi_scale_train) with a single set of weights and a single optimizer state.  Binding fills
+ * constants and this plan's activation-arena scratch on `stream`; it never touches weights or optimizer slots. */
 int yb_net_bind(yb_net* net, void* activation_arena, size_t activation_bytes, void* param_arena,
-                size_t param_bytes);
+                size_t param_bytes, void* stream);
+/* Re-fold every BN layer's (gamma, beta, moving mean, moving variance) into the inference scale/shift (needed after
+ * training steps made through ANOTHER plan that shares the parameter arena; a plan refolds by itself after its own). */
+int yb_net_refold_bn(yb_net* net, void* stream);
 /* Upload one conv's parameters (device float32 pointers).  BN layers: gamma,beta,mean,var (bias NULL);
  * detection convs: bias (others NULL).  Repacks/folds on `stream`. */
 int yb_net_set_conv_params(yb_net* net, int layer, const float* w, int layout, const float* gamma,
@@ -250,20 +268,54 @@ int yb_net_forward_layers(yb_net* net, const float* images, float* fm1, float* f
  *      yb_net_train_fwd_bwd -> [all-reduce of yb_net_grad_buffer across ranks] -> yb_net_train_update ---- */
 /* forward with BN batch statistics (updating the moving statistics with `bn_decay`, train.py:108-109) ->
  * compute_loss (model.py:348-365; loss4 = device double[4] xy,wh,conf,class, overwritten) -> backward into the
- * flat gradient buffer (data term only).  forward_only=1 stops after the forward (y_true*, loss4 may be NULL).
+ * flat gradient buffer (data term only).  YB_TRAIN_FORWARD_ONLY stops after the forward (y_true*, loss4 may be NULL).
  * y_true_k: [n, g_k, g_k, 3, 5+C+1] float32 for the /32, /16, /8 maps; anchors9x2 host float[18].
  * fm1..3 nullable (then the arena-owned float32 outputs are used). */
+/* flags: YB_TRAIN_FORWARD_ONLY stops after the forward; YB_TRAIN_BN_FROZEN normalises with the moving statistics
+ * (forward(is_training=False) inside the training graph: fine-tuning with frozen BN; statistics are constants of the
+ * backward pass and are not updated) — per-image results then do not depend on the rest of the batch, which is what
+ * makes an N-rank data-parallel step bit-comparable with a 1-rank step on the concatenated batch. */
+enum { YB_TRAIN_FORWARD_ONLY = 1, YB_TRAIN_BN_FROZEN = 2 };
 int yb_net_train_fwd_bwd(yb_net* net, const float* images, const float* y_true_1, const float* y_true_2,
                          const float* y_true_3, const float* anchors9x2, int use_label_smooth, int use_focal_loss,
-                         float bn_decay, float* fm1, float* fm2, float* fm3, double* loss4, int forward_only,
-                         void* stream);
+                         float bn_decay, float loss_scale, float* fm1, float* fm2, float* fm3, double* loss4,
+                         int flags, void* stream);
 /* the flat float32 gradient of all 222 trainable tensors (creation order: per conv w [OHWI], then gamma, beta
  * | bias; each padded to 4 floats) — the buffer a data-parallel wrapper all-reduces. */
 int yb_net_grad_buffer(yb_net* net, float** ptr, size_t* count);
-/* g = grad_scale*grad + weight_decay*w (conv weights only); per-tensor clip_by_norm(g, clip_norm) (<=0: off);
- * v = momentum*v + g; w -= lr*v; refresh the 16-bit compute copies (train.py:78,113-115, misc_utils.py:151-153). */
-int yb_net_train_update(yb_net* net, float lr, float grad_scale, float momentum, float weight_decay,
-                        float clip_norm, void* stream);
+/* The optimizers of utils/misc_utils.py:151-161 (config_optimizer) with TensorFlow 1.x update rules. */
+typedef enum yb_opt_kind {
+  YB_OPT_SGD = 0,      /* GradientDescentOptimizer: w -= lr*g                                                    */
+  YB_OPT_MOMENTUM = 1, /* MomentumOptimizer(momentum): v = m*v + g; w -= lr*v  (the reference's default)         */
+  YB_OPT_RMSPROP = 2,  /* RMSPropOptimizer(decay, momentum, epsilon=1e-10): ms = d*ms + (1-d)g^2 (ms starts at 1);
+                          mom = m*mom + lr*g/sqrt(ms+eps); w -= mom                                              */
+  YB_OPT_ADAM = 3      /* AdamOptimizer(beta1=.9, beta2=.999, epsilon=1e-8): lr_t = lr*sqrt(1-b2^t)/(1-b1^t);
+                          m = b1*m + (1-b1)g; v = b2*v + (1-b2)g^2; w -= lr_t*m/(sqrt(v)+eps)                    */
+} yb_opt_kind;
+typedef struct yb_optimizer {
+  int kind;            /* yb_opt_kind                                                                            */
+  float lr;            /* THIS step's learning rate: the host evaluates the schedule (utils/misc_utils.py:129-148,
+                          warm-up train.py:93-99; Python: utils.misc_utils.config_learning_rate)                 */
+  float grad_scale;    /* multiplies the raw gradient buffer: 1/world_size (data-parallel mean) x 1/loss_scale   */
+  float momentum, decay, beta1, beta2, epsilon;
+  float weight_decay;  /* slim.l2_regularizer on conv weights only (model.py:49, train.py:78)                    */
+  float clip_norm;     /* per-tensor tf.clip_by_norm (train.py:113-114); <= 0: off                               */
+} yb_optimizer;
+/* g = grad_scale*grad + weight_decay*w (conv weights only); per-tensor clip_by_norm; the optimizer's rule on the fp32
+ * master weights and its slots; refresh of the 16-bit compute copies and dgrad weights.  A step whose gradient holds
+ * a non-finite value is skipped entirely (yb_net_opt_state: ctrl[2] counts skipped steps, ctrl[1] applied ones). */
+int yb_net_train_update(yb_net* net, const yb_optimizer* opt, void* stream);
+/* Zero the optimizer slots (rmsprop: mean-square slot = 1 like TF), the gradient buffer and the step counters.
+ * Call once when a parameter arena starts training (or the optimizer changes); binding a plan never does this. */
+int yb_net_train_reset_state(yb_net* net, int optimizer_kind, void* stream);
+/* The optimizer slots: num_slots x count_per_slot floats laid out like the gradient buffer, and int ctrl[3] =
+ * {non-finite flag of the running step, updates applied, steps skipped} (checkpoint save/restore of save_optimizer,
+ * train.py:101-104,118-121). */
+int yb_net_opt_state(yb_net* net, float** slots, size_t* count_per_slot, int* num_slots, int** ctrl);
+/* train.py:81 update_part: exclude a conv (weights + gamma/beta | bias) from / include it in the update. */
+int yb_net_set_trainable(yb_net* net, int layer, int trainable, void* stream);
+/* Re-derive the dgrad weight layouts from the fp32 master weights (after the arena's weights were replaced). */
+int yb_net_train_refresh_dgrad(yb_net* net, void* stream);
 /* device pointers of one conv's float32 master parameters (w is OHWI [cout,k,k,cin]) / of its gradients. */
 int yb_net_get_conv_params(yb_net* net, int layer, float** w_ohwi, float** gamma, float** beta, float** mean,
                            float** var, float** bias);

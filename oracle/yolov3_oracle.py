@@ -607,12 +607,24 @@ def synth_gt(rng, img_w, img_h, class_num=80, max_boxes=50):
 # --------------------------------------------------------------------------------------
 def train_step(x_nhwc, y_true, params, velocity, lr, anchors, class_num=80, use_label_smooth=False,
                use_focal_loss=False, bn_decay=0.99, weight_decay=5e-4, momentum=0.9, clip=100.0,
-               emulate=None, dtype=torch.float32):
-    """One reference training step on CPU.  Returns (losses, grads, new_params, new_velocity).
+               emulate=None, dtype=torch.float32, optimizer="momentum", decay=0.9, beta1=0.9, beta2=0.999,
+               epsilon=None, slot2=None, step=0, freeze_bn=False, trainable=None):
+    """One reference training step on CPU.  Returns (losses, grads, new_params, new_velocity) — for rmsprop / adam
+    new_velocity is a pair (slot1, slot2) of per-layer dicts.
 
     grads are d(total + l2)/d(param) *before* clipping, keyed like params
     ('w','gamma','beta','b'); L2 = wd * sum(w^2)/2 on conv weights only (model.py:49).
+    optimizer (utils/misc_utils.py:151-161, [TF] TensorFlow 1.x update rules):
+      momentum  v = m*v + g; w -= lr*v                                  (MomentumOptimizer, no Nesterov)
+      sgd       w -= lr*g                                               (GradientDescentOptimizer)
+      rmsprop   ms = d*ms + (1-d)g^2 (ms starts at 1); mom = m*mom + lr*g/sqrt(ms+1e-10); w -= mom
+      adam      t = step+1; lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m = b1*m+(1-b1)g; v = b2*v+(1-b2)g^2; w -= lr_t*m/(sqrt(v)+1e-8)
+    `velocity` is slot 1 (momentum / rmsprop mom / adam m), `slot2` the rmsprop ms / adam v (None: TF's initial value).
+    freeze_bn: the graph built with is_training=False (train.py:72): BN uses and keeps its moving statistics.
+    trainable: optional set of conv indices in update_vars (train.py:81); others are left untouched.
     """
+    if epsilon is None:
+        epsilon = 1e-10 if optimizer == "rmsprop" else 1e-8
     tp = []
     for p in params:
         q = {}
@@ -623,29 +635,90 @@ def train_step(x_nhwc, y_true, params, velocity, lr, anchors, class_num=80, use_
             q[k] = t
         tp.append(q)
     H, W = x_nhwc.shape[1:3]
-    fms, new_stats = forward(torch.tensor(x_nhwc, dtype=dtype), tp, class_num, True, emulate, bn_decay,
+    fms, new_stats = forward(torch.tensor(x_nhwc, dtype=dtype), tp, class_num, not freeze_bn, emulate, bn_decay,
                              dtype, as_torch=True)
     losses = compute_loss(list(fms), y_true, anchors, (H, W), class_num, use_label_smooth, use_focal_loss)
     l2 = sum((q["w"] ** 2).sum() for q in tp) * (weight_decay / 2.0)        # train.py:78
     (losses[0] + l2).backward()                                              # train.py:112
-    grads, new_params, new_vel = [], [], []
+    grads, new_params, new_vel, new_s2 = [], [], [], []
     si = 0
-    for q, p, v in zip(tp, params, velocity):
-        g, npar, nv = {}, {}, {}
+    for li, (q, p, v) in enumerate(zip(tp, params, velocity)):
+        g, npar, nv, n2 = {}, {}, {}, {}
         for k in q:
             if q[k].requires_grad:
                 gk = q[k].grad
                 g[k] = gk.numpy().copy()
+                if trainable is not None and li not in trainable:
+                    continue
                 nrm = torch.sqrt((gk * gk).sum())
                 gc = gk * clip / torch.clamp(nrm, min=clip)                  # train.py:113-114 clip_by_norm
-                vk = momentum * torch.as_tensor(v[k], dtype=dtype) + gc      # [TF] MomentumOptimizer
-                nv[k] = vk.numpy()
-                npar[k] = (q[k].detach() - lr * vk).numpy()
-        if "gamma" in q:
+                s1 = torch.as_tensor(v[k], dtype=dtype)
+                if optimizer == "momentum":                                  # utils/misc_utils.py:153
+                    vk = momentum * s1 + gc
+                    nv[k] = vk.numpy()
+                    npar[k] = (q[k].detach() - lr * vk).numpy()
+                elif optimizer == "sgd":                                     # :159
+                    nv[k] = s1.numpy()
+                    npar[k] = (q[k].detach() - lr * gc).numpy()
+                elif optimizer == "rmsprop":                                 # :155
+                    ms0 = torch.ones_like(gc) if slot2 is None else torch.as_tensor(slot2[li][k], dtype=dtype)
+                    ms = decay * ms0 + (1 - decay) * gc * gc
+                    mom = momentum * s1 + lr * gc / torch.sqrt(ms + epsilon)
+                    nv[k], n2[k] = mom.numpy(), ms.numpy()
+                    npar[k] = (q[k].detach() - mom).numpy()
+                elif optimizer == "adam":                                    # :157
+                    v0 = torch.zeros_like(gc) if slot2 is None else torch.as_tensor(slot2[li][k], dtype=dtype)
+                    t = step + 1
+                    lr_t = lr * math.sqrt(1 - beta2 ** t) / (1 - beta1 ** t)
+                    m1 = beta1 * s1 + (1 - beta1) * gc
+                    v1 = beta2 * v0 + (1 - beta2) * gc * gc
+                    nv[k], n2[k] = m1.numpy(), v1.numpy()
+                    npar[k] = (q[k].detach() - lr_t * m1 / (torch.sqrt(v1) + epsilon)).numpy()
+                else:
+                    raise ValueError("Unsupported optimizer type!")          # :161
+        if "gamma" in q and not freeze_bn:
             mm, mv = new_stats[si]; si += 1
             npar["mean"], npar["var"] = mm.numpy(), mv.numpy()
-        grads.append(g); new_params.append(npar); new_vel.append(nv)
-    return [float(l.detach()) for l in losses] + [float(l2.detach())], grads, new_params, new_vel
+        grads.append(g); new_params.append(npar); new_vel.append(nv); new_s2.append(n2)
+    out_vel = new_vel if optimizer in ("momentum", "sgd") else (new_vel, new_s2)
+    return [float(l.detach()) for l in losses] + [float(l2.detach())], grads, new_params, out_vel
+
+
+# --------------------------------------------------------------------------------------
+# Learning-rate schedules (utils/misc_utils.py:129-148, warm-up train.py:93-99)
+# --------------------------------------------------------------------------------------
+def learning_rate(args, global_step):
+    """The value of train.py:93-99's `learning_rate` tensor at float `global_step`.  `args` carries the fields of
+    args.py (lr_type, learning_rate_init, lr_decay_freq, lr_decay_factor, lr_lower_bound, total_epoches,
+    use_warm_up, warm_up_epoch, train_batch_num, pw_boundaries, pw_values).  [TF] semantics restated:
+      exponential_decay(staircase): lr0 * factor ** floor(step / freq), then max(., lower bound)
+      cosine_decay_restarts(t_mul=2, m_mul=1, alpha=0): first period = freq, each next one twice as long
+      piecewise_constant: values[i] for boundaries[i-1] < step <= boundaries[i]  (x <= b[0] -> v[0])"""
+    gs = float(global_step)
+    if args.use_warm_up:
+        wu = args.train_batch_num * args.warm_up_epoch
+        if gs < wu:
+            return args.learning_rate_init * gs / wu                         # train.py:95
+        gs = gs - wu                                                         # train.py:96
+    t = args.lr_type
+    if t == "exponential":
+        return max(args.learning_rate_init * args.lr_decay_factor ** math.floor(gs / args.lr_decay_freq), args.lr_lower_bound)
+    if t == "cosine_decay":
+        train_steps = (args.total_epoches - float(args.use_warm_up) * args.warm_up_epoch) * args.train_batch_num
+        return args.lr_lower_bound + 0.5 * (args.learning_rate_init - args.lr_lower_bound) * (1 + math.cos(gs / train_steps * math.pi))
+    if t == "cosine_decay_restart":
+        frac = gs / args.lr_decay_freq
+        i = math.floor(math.log(1.0 - frac * (1.0 - 2.0)) / math.log(2.0))  # [TF] compute_step, t_mul = 2
+        frac = (frac - (1.0 - 2.0 ** i) / (1.0 - 2.0)) / 2.0 ** i
+        return args.learning_rate_init * 0.5 * (1.0 + math.cos(math.pi * frac))
+    if t == "fixed":
+        return args.learning_rate_init
+    if t == "piecewise":
+        for b, v in zip(args.pw_boundaries, args.pw_values):
+            if gs <= b:
+                return v
+        return args.pw_values[-1]
+    raise ValueError("Unsupported learning rate type!")
 
 
 # --------------------------------------------------------------------------------------

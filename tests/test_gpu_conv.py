@@ -12,14 +12,21 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["1cta", "2cta", "mc"], autouse=True)
-def conv_mode(request, monkeypatch):
+@pytest.fixture(params=["1cta", "2cta", "mc", "1cta-reg", "2cta-reg"], autouse=True)
+def conv_mode(request):
     """Every conv test runs against the three tcgen05 kernels: cta_group::1 (128-row tiles), cta_group::2 (a CTA
     pair per 256-row tile) and the cluster-multicast pair kernel (2x2 / 2x1 pairs; only 256-wide tiles take it,
-    the other shapes fall back to the plain pair kernel).  YB_CONV_MODE / YB_CONV_MC override the heuristics."""
-    monkeypatch.setenv("YB_CONV_MODE", "2cta" if request.param == "mc" else request.param)
-    monkeypatch.setenv("YB_CONV_MC", "1" if request.param == "mc" else "0")
-    return request.param
+    the other shapes fall back to the plain pair kernel), and — for the first two — against both epilogues: the
+    shared-memory + TMA-store one (default) and the register-store one of round 1 ("-reg").  The library's option
+    table (yb_set_option) overrides the heuristics; it is restored after each test."""
+    L = _lib()
+    mode, _, epi = request.param.partition("-")
+    L.set_option("YB_CONV_MODE", "2cta" if mode == "mc" else mode)
+    L.set_option("YB_CONV_MC", "1" if mode == "mc" else "0")
+    L.set_option("YB_CONV_EPI", "reg" if epi == "reg" else None)
+    yield request.param
+    for k in ("YB_CONV_MODE", "YB_CONV_MC", "YB_CONV_EPI"):
+        L.set_option(k, None)
 
 
 def _lib():
@@ -170,6 +177,18 @@ def test_conv3x3_s2_wide():
 
 def test_conv1x1_wide_1024_bf16_stats():
     _run_conv(4, 13, 13, 512, 1024, 1, 1, dtype=torch.bfloat16, stats=True)   # 4 n-tiles, statistics epilogue
+
+
+def test_conv1x1_residual_tail_rows_many_chunks():
+    _run_conv(3, 13, 13, 128, 256, 1, 1, residual=True, out_extra=64)   # 507 rows: tail tile; 8 chunks/tile + TMA residual
+
+
+def test_conv3x3_many_tiles_per_cta_residual():
+    _run_conv(8, 52, 52, 64, 128, 3, 1, residual=True)                  # 169 m-tiles on <= 148 CTAs: residual prefetch across tiles
+
+
+def test_conv1x1_cout32_single_chunk():
+    _run_conv(2, 26, 26, 64, 32, 1, 1, residual=True)                   # cout 32: one valid chunk of a 64-wide tile
 
 
 def test_conv_rejects_bad_arguments():

@@ -1,6 +1,12 @@
 """2-GPU NCCL test of the data-parallel training step (needs >= 2 devices: `gpurun --gpus 2`; skipped on a
-single-GPU box): the all-reduced flat gradient equals the sum of the per-rank gradients, and both ranks hold
-bit-identical parameters after the update."""
+single-GPU box).
+
+DP-equivalence: every loss term is a mean over the local batch (model.py:276-302), so the
+N-rank step — local backward, NCCL all-reduce (sum) of the flat gradient, 1/world folded into the optimizer kernel —
+must equal the 1-rank step on the concatenated batch.  BN is frozen (train_step(freeze_bn=True): the graph of
+forward(is_training=False)) so that an image's activations do not depend on which other images share its rank.
+Checked on the ENGINE: the parameter update of the 2-rank run against a 1-rank run of all 4 images, on layers at
+the bottom, middle and top of the network, plus bit-identical parameters on both ranks."""
 import os
 import socket
 import sys
@@ -11,6 +17,16 @@ import torch
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LAYERS = (0, 1, 30, 57, 58, 66, 73, 74)
+
+
+def _flat(m, keys=("w", "gamma", "beta", "b")):
+    plan = m._last_plan
+    out = []
+    for i in LAYERS:
+        ps = plan.conv_params(i)
+        out += [ps[k].reshape(-1).clone() for k in keys if k in ps]
+    return out
 
 
 def _worker(rank, world, port, q):
@@ -26,44 +42,43 @@ def _worker(rank, world, port, q):
     lo, hi = parallel.shard_batch(4, rank, world)
     xs = torch.from_numpy(x[lo:hi]).cuda()
     ys = [torch.from_numpy(y[lo:hi]).cuda() for y in y_true]
-    # local backward (lr 0, no collective), then the data-parallel tail exactly as train_step runs it:
-    # ONE all-reduce of the flat gradient buffer, mean factor folded into the fused optimizer kernel.
-    # (Two separate backward runs are not comparable bit-for-bit: the BN statistics are accumulated with
-    #  fp32 atomics, and at random init this network's BN backward amplifies that last-bit noise.)
-    from yolov3_tensorflow_b200._lib import lib, check, stream_handle
-    m = pkg.yolov3(80, O.COCO_ANCHORS, dtype="bf16")
-    m.set_params(params, "HWIO")
-    m.train_step(xs, ys, 0.0, data_parallel=False)
-    plan = m._last_plan
-    g_local = plan.grad_flat().clone()
-    gs = [torch.empty_like(g_local) for _ in range(world)]
-    dist.all_gather(gs, g_local)
-    scale = parallel.allreduce_gradients(plan.grad_flat())
-    assert scale == 1.0 / world
-    ref = gs[0] + gs[1]
-    err = float((plan.grad_flat() - ref).abs().max() / ref.abs().max())
-    # momentum 0: the lr-0 local step above left each rank's LOCAL gradient in its velocity buffers
-    check(lib.yb_net_train_update(plan.handle, 1e-3, scale, 0.0, 5e-4, 100.0, stream_handle()), "update")
-    w = torch.cat([plan.conv_params(i)["w"].reshape(-1) for i in (0, 30, 74)])
-    ws = [torch.empty_like(w) for _ in range(world)]
-    dist.all_gather(ws, w)
-    same = bool(torch.equal(ws[0], ws[1])) and not bool(torch.equal(w, torch.cat([torch.from_numpy(
-        np.ascontiguousarray(np.transpose(params[i]["w"], (3, 0, 1, 2)))).reshape(-1) for i in (0, 30, 74)]).cuda()))
-    # and the public API end to end: a DP train_step leaves both ranks with identical parameters
-    m2 = pkg.yolov3(80, O.COCO_ANCHORS, dtype="bf16")
-    m2.set_params(params, "HWIO")
-    m2.train_step(xs, ys, 1e-3)
-    w2 = torch.cat([m2._last_plan.conv_params(i)["w"].reshape(-1) for i in (0, 30, 74)])
-    ws2 = [torch.empty_like(w2) for _ in range(world)]
-    dist.all_gather(ws2, w2)
-    same = same and bool(torch.equal(ws2[0], ws2[1]))
+    lr = 1e-2
+
+    def fresh():
+        m = pkg.yolov3(80, O.COCO_ANCHORS, use_label_smooth=True, use_focal_loss=True, dtype="bf16")
+        m.set_params(params, "HWIO")
+        return m
+
+    # ---- 2-rank data-parallel step through the public API (NCCL all-reduce inside train_step)
+    m_dp = fresh()
+    m_dp.train_step(xs, ys, lr, freeze_bn=True)
+    dp = _flat(m_dp)
+    gathered = []
+    for t in dp:
+        ws = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(ws, t)
+        gathered.append(ws)
+    same = all(torch.equal(ws[0], ws[1]) for ws in gathered)
+    # ---- 1-rank step on the concatenated batch (no collective), same engine, same parameters
+    m_1 = fresh()
+    m_1.train_step(torch.from_numpy(x).cuda(), [torch.from_numpy(y).cuda() for y in y_true], lr, freeze_bn=True,
+                   data_parallel=False)
+    one = _flat(m_1)
+    m_0 = fresh()
+    m_0.forward(xs)                                   # uploads the parameters: the "before" values in arena layout
+    before = _flat(m_0)
+    errs = []
+    for a, b, w0 in zip(dp, one, before):
+        da, db = (a - w0).double(), (b - w0).double()
+        errs.append(float((da - db).norm() / db.norm().clamp(min=1e-30)))
+    moved = all(float((b - w0).abs().max()) > 0 for b, w0 in zip(one, before))
     dist.barrier()
     dist.destroy_process_group()
-    q.put((rank, err, same))
+    q.put((rank, max(errs), same, moved))
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_dp_train_step_nccl_world2():
+def test_dp_train_step_equals_single_rank_on_concatenated_batch():
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -72,9 +87,12 @@ def test_dp_train_step_nccl_world2():
     for p in procs:
         p.start()
     for p in procs:
-        p.join(timeout=600)
+        p.join(timeout=900)
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     res = sorted(q.get(timeout=5) for _ in range(2))
-    for rank, err, same in res:
-        assert err < 1e-5, f"rank {rank}: all-reduced gradient differs from the sum of rank gradients ({err})"   # wgrad atomics: order noise only
+    for rank, err, same, moved in res:
+        print(f"rank {rank}: max relative L2 error of the parameter update, 2-rank DP vs 1-rank on 4 images: {err:.3g}")
+        assert moved, "the 1-rank reference step did not move the parameters"
+        # fp32 atomic-accumulation order in wgrad / BN reductions is the only difference (1/N is a power of two)
+        assert err < 1e-3, f"rank {rank}: DP update differs from the single-rank update on the concatenated batch ({err})"
         assert same, "ranks hold different parameters after the data-parallel update"

@@ -459,3 +459,264 @@ def test_nms_stress_shape_small_sample():
         ob, os_, ol, oi = O.gpu_nms_c(boxes[None], scores[None], 4, 200, 0.3, 0.45)
         assert np.array_equal(gi.cpu().numpy(), oi) and np.array_equal(gl.cpu().numpy(), ol)
         assert np.array_equal(gs.cpu().numpy(), os_) and np.array_equal(gb.cpu().numpy(), ob)
+
+
+# ------------------------------------------------------------------------- parity at the BASELINE sizes (recorded)
+def _record(name, payload):
+    """Measured parity numbers go to gpurun_out/r02_parity.json (copied to profiles/ by the builder)."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "gpurun_out", "r02_parity.json")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    data = {}
+    if os.path.exists(path):
+        try:
+            data = json.load(open(path))
+        except Exception:
+            data = {}
+    data[name] = payload
+    json.dump(data, open(path, "w"), indent=1, sort_keys=True)
+
+
+def _err_stats(a, b, floor):
+    """Per-element relative error |a-b| / max(|b|, floor): max, 99.9th percentile and mean."""
+    e = np.abs(a.astype(np.float64) - b.astype(np.float64)) / np.maximum(np.abs(b.astype(np.float64)), floor)
+    return {"max": float(e.max()), "p999": float(np.quantile(e, 0.999)), "mean": float(e.mean())}
+
+
+@pytest.mark.parametrize("size,batch", [(416, 2), (608, 2)])
+def test_forward_parity_at_baseline_sizes(size, batch):
+    """BASELINE.json configs[0..2] image sizes, cfg-2 weights (detection heads x8, conf bias -2): the engine's
+    logits, decoded boxes, confidences and class probabilities against the CPU oracle run (a) with the engine's
+    storage model (fp16 activations/weights, fp32 accumulate) and (b) in plain fp32 (the reference's arithmetic).
+    north_star asks for 1e-3 relative on box coords / obj / class logits: (a) isolates the kernels from the storage
+    format, (b) is what a user of the reference sees.  Numbers are recorded; bars are 2x the values measured on B200
+    (profiles/r02_parity.json) — where fp16 storage through 75 layers makes 1e-3 unreachable the bar says so."""
+    params = O.make_params(80, seed=7, random_bn=True, det_scale=8.0, conf_bias=-2.0)
+    x = gen_inputs(11 + size, batch, size, size)
+    m = _model(80, "fp16")
+    m.set_params(params, "HWIO")
+    fms = m.forward(torch.from_numpy(x).cuda())
+    b, c, p = m.predict(fms)
+    got_f = [f.cpu().numpy() for f in fms]
+    got = {"boxes": b.cpu().numpy(), "confs": c.cpu().numpy(), "probs": p.cpu().numpy()}
+    rec = {"size": size, "batch": batch, "dtype": "fp16 storage, fp32 accumulate"}
+    for tag, emu in (("vs_oracle_fp16_storage", "fp16"), ("vs_oracle_fp32", None)):
+        ref_f = O.forward(x, params, emulate=emu)
+        rb, rc, rp = O.predict(ref_f, O.COCO_ANCHORS, (size, size), 80)
+        r = {}
+        for name, a, ref in zip(("fm1", "fm2", "fm3"), got_f, ref_f):
+            r[name + "_logits"] = _err_stats(a, ref, 1.0)                       # logits: relative above 1, absolute below
+            r[name + "_maxnorm"] = _rel_err(a, ref)
+        r["boxes"] = _err_stats(got["boxes"], rb, 16.0)                         # pixels; 16 px floor (stride of the finest map x2)
+        r["confs"] = _err_stats(got["confs"], rc, 1e-2)
+        r["probs"] = _err_stats(got["probs"], rp, 1e-2)
+        rec[tag] = r
+    _record(f"forward_{size}", rec)
+    print(rec)
+    a = rec["vs_oracle_fp16_storage"]
+    # kernels vs the same-storage oracle (measured on B200, bars = 2x): logits ~1e-3-class, boxes/conf/prob tighter
+    assert max(a[k]["max"] for k in ("fm1_logits", "fm2_logits", "fm3_logits")) < 2e-2
+    assert a["boxes"]["p999"] < 5e-3 and a["confs"]["p999"] < 2e-2 and a["probs"]["p999"] < 2e-2
+    f = rec["vs_oracle_fp32"]
+    assert max(f[k] for k in ("fm1_maxnorm", "fm2_maxnorm", "fm3_maxnorm")) < 2e-2
+
+
+def _grad_errs(plan, params, og, layers=range(75)):
+    out = {}
+    for i in layers:
+        gr = plan.layer_grads(i)
+        for k in ("w", "gamma", "beta", "b"):
+            if k not in gr:
+                continue
+            a = gr[k].cpu().numpy().astype(np.float64)
+            if k == "w":
+                a = np.transpose(a, (1, 2, 3, 0))
+            l2 = 5e-4 * params[i]["w"] if k == "w" else 0.0
+            ref = (og[i][k] - l2).astype(np.float64)
+            out[(i, k)] = float(np.linalg.norm(a - ref) / max(np.linalg.norm(ref), 1e-30))
+    return out
+
+
+@pytest.mark.parametrize("dt", ["fp16", "bf16"])
+def test_train_step_frozen_bn_fixed_bar(dt):
+    """Training parity with a FIXED bar.  With batch-statistic BN at random init the BN backward is a near-cancellation
+    and the reference's own 16-bit-vs-fp32 spread is ~10 % (test_train_step_matches_oracle uses a noise-relative bar
+    for that reason).  With BN frozen (forward(is_training=False) under the gradient tape) nothing cancels, so the
+    engine's gradients must agree with the same-storage oracle tensor by tensor."""
+    params, x, y_true = _train_case()
+    lr = 1e-3
+    m = _pkg().yolov3(80, O.COCO_ANCHORS, use_label_smooth=True, use_focal_loss=True, dtype=dt)
+    m.set_params(params, "HWIO")
+    losses = m.train_step(torch.from_numpy(x).cuda(), [torch.from_numpy(y).cuda() for y in y_true], lr, freeze_bn=True)
+    scale = 1.0 / m.loss_scale
+    plan = m._last_plan
+    vel0 = [{k: np.zeros_like(v) for k, v in p.items() if k in ("w", "gamma", "beta", "b")} for p in params]
+    ol, og, op, _ = O.train_step(x, y_true, params, vel0, lr, O.COCO_ANCHORS, 80, True, True, emulate=dt, freeze_bn=True)
+    ol32, og32, _, _ = O.train_step(x, y_true, params, vel0, lr, O.COCO_ANCHORS, 80, True, True, emulate=None, freeze_bn=True)
+    errs = {}
+    for i in range(75):
+        gr = plan.layer_grads(i)
+        for k in ("w", "gamma", "beta", "b"):
+            if k not in gr:
+                continue
+            a = gr[k].cpu().numpy().astype(np.float64) * scale            # the buffer holds loss_scale x gradient
+            if k == "w":
+                a = np.transpose(a, (1, 2, 3, 0))
+            l2 = 5e-4 * params[i]["w"] if k == "w" else 0.0
+            ref = (og[i][k] - l2).astype(np.float64)
+            ref32 = (og32[i][k] - l2).astype(np.float64)
+            errs[(i, k)] = (float(np.linalg.norm(a - ref) / max(np.linalg.norm(ref), 1e-30)),
+                            float(np.linalg.norm(a - ref32) / max(np.linalg.norm(ref32), 1e-30)))
+    worst16 = max(v[0] for v in errs.values()); worst32 = max(v[1] for v in errs.values())
+    wk16 = max(errs, key=lambda k: errs[k][0]); wk32 = max(errs, key=lambda k: errs[k][1])
+    got = np.array([float(v) for v in losses])
+    lerr = float(np.max(np.abs(got - np.array(ol[:5])) / np.abs(np.array(ol[:5]))))
+    _record(f"train_frozen_bn_{dt}", {"worst_grad_rel_l2_vs_same_storage_oracle": worst16, "at": list(map(str, wk16)),
+                                      "worst_grad_rel_l2_vs_fp32_oracle": worst32, "at32": list(map(str, wk32)),
+                                      "loss_rel_err": lerr, "shape": [2, 128, 160]})
+    print(f"{dt}: worst grad err vs same-storage oracle {worst16:.3g} at {wk16}; vs fp32 oracle {worst32:.3g} at {wk32}; loss {lerr:.3g}")
+    bar = 3e-2 if dt == "fp16" else 1.5e-1      # 16-bit storage of activations AND gradients through 75 layers (2x measured)
+    assert worst16 < bar, (wk16, worst16)
+    assert lerr < (5e-3 if dt == "fp16" else 3e-2)
+
+
+@pytest.mark.parametrize("opt", ["sgd", "rmsprop", "adam", "momentum"])
+def test_optimizer_zoo_matches_oracle(opt):
+    """utils/misc_utils.py:151-161: two consecutive steps of each optimizer (TF1 rules: rmsprop's mean-square slot
+    starts at 1, adam's bias correction uses t = step count) against the oracle fed the ENGINE's gradients — isolates
+    the update kernel from the backward's storage noise.  Exact to fp32 rounding."""
+    params, x, y_true = _train_case()
+    lr = 1e-3
+    m = _pkg().yolov3(80, O.COCO_ANCHORS, dtype="bf16")
+    m.set_params(params, "HWIO")
+    xs, ys = torch.from_numpy(x).cuda(), [torch.from_numpy(y).cuda() for y in y_true]
+    layers = (0, 1, 30, 58, 74)
+    import math
+    state1 = {}; state2 = {}
+    for step in range(2):
+        before = {i: {k: v.clone() for k, v in m._plan(2, 128, 160, True).conv_params(i).items()} for i in layers} if step else None
+        m.train_step(xs, ys, lr, optimizer=opt, freeze_bn=True)
+        plan = m._last_plan
+        if before is None:
+            before = {i: {k: torch.from_numpy(np.transpose(params[i][k], (3, 0, 1, 2)).copy() if k == "w" else params[i][k]).cuda()
+                          for k in params[i]} for i in layers}
+        for i in layers:
+            gr = plan.layer_grads(i)
+            after = plan.conv_params(i)
+            for k in gr:
+                w0 = before[i][k].double()
+                g = gr[k].double() / m.loss_scale
+                if k == "w":
+                    g = g + 5e-4 * w0
+                nrm = g.norm()
+                g = g * 100.0 / torch.clamp(nrm, min=100.0)
+                s1 = state1.get((i, k), torch.zeros_like(g)); s2 = state2.get((i, k))
+                if opt == "sgd":
+                    w1 = w0 - lr * g
+                elif opt == "momentum":
+                    s1 = 0.9 * s1 + g; w1 = w0 - lr * s1
+                elif opt == "rmsprop":
+                    s2 = torch.ones_like(g) if s2 is None else s2
+                    s2 = 0.9 * s2 + 0.1 * g * g
+                    s1 = 0.9 * s1 + lr * g / torch.sqrt(s2 + 1e-10); w1 = w0 - s1
+                else:
+                    s2 = torch.zeros_like(g) if s2 is None else s2
+                    t = step + 1
+                    lr_t = lr * math.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t)
+                    s1 = 0.9 * s1 + 0.1 * g; s2 = 0.999 * s2 + 0.001 * g * g
+                    w1 = w0 - lr_t * s1 / (torch.sqrt(s2) + 1e-8)
+                state1[(i, k)] = s1; state2[(i, k)] = s2
+                got = after[k].double()
+                step_ref = (w1 - w0)
+                err = float((got - w1).norm() / step_ref.norm().clamp(min=1e-30))
+                assert err < 2e-4, f"{opt} step {step} layer {i} {k}: update rel err {err:.3g}"
+    slots, ctrl = m.optimizer_state()
+    assert ctrl.tolist()[:3] == [0, 2, 0]          # no non-finite flag, 2 updates applied, none skipped
+
+
+def test_multi_scale_training_shares_weights_and_optimizer_state():
+    """args.py multi_scale_train: steps at different resolutions / batch sizes run through different plans but ONE
+    parameter arena — the momentum accumulator carries over (the reference has a single MomentumOptimizer), the
+    weights trained at one size drive inference at another, update_part freezes tensors, and a non-finite gradient
+    skips the step."""
+    params, x, y_true = _train_case()
+    m = _pkg().yolov3(80, O.COCO_ANCHORS, dtype="bf16")
+    m.set_params(params, "HWIO")
+    xs, ys = torch.from_numpy(x).cuda(), [torch.from_numpy(y).cuda() for y in y_true]
+    m.train_step(xs, ys, 1e-3, freeze_bn=True)
+    slots, ctrl = m.optimizer_state()
+    v_after_1 = slots[0].clone()
+    assert float(v_after_1.abs().max()) > 0
+    # second step at another resolution and batch size (new plan, same arena)
+    rng = np.random.default_rng(5)
+    x2 = gen_inputs(77, 1, 96, 96)
+    yb = [[], [], []]
+    boxes, labels = O.synth_gt(rng, 96, 96, 80, 4)
+    y = O.process_box(boxes, labels, [96, 96], 80, O.COCO_ANCHORS)
+    y2 = [torch.from_numpy(t[None]).cuda() for t in y]
+    w_before = m._last_plan.conv_params(74)["w"].clone()
+    m.train_step(torch.from_numpy(x2).cuda(), y2, 1e-3, freeze_bn=True)
+    plan2 = m._last_plan
+    assert (plan2.n, plan2.h, plan2.w) == (1, 96, 96) and len(m._plans) == 2
+    slots2, ctrl2 = m.optimizer_state()
+    g2 = plan2.grad_flat() / m.loss_scale
+    # momentum: v2 = 0.9 * v1 + clip(g2 + wd*w): check on the bias of the last head conv (no L2, norm << clip)
+    gb = plan2.layer_grads(74)["b"] / m.loss_scale
+    off = gb.data_ptr() - plan2.grad_flat().data_ptr()
+    idx = off // 4
+    v1b = v_after_1[idx: idx + gb.numel()]
+    v2b = slots2[0][idx: idx + gb.numel()]
+    torch.testing.assert_close(v2b, 0.9 * v1b + gb, rtol=1e-5, atol=1e-9)
+    assert ctrl2.tolist()[1] == 2
+    assert not torch.equal(plan2.conv_params(74)["w"], w_before)
+    # inference at a third size sees the trained weights (BN refold included)
+    fms = m.forward(torch.from_numpy(gen_inputs(3, 1, 64, 64)).cuda())
+    ref = O.forward(gen_inputs(3, 1, 64, 64), m.get_params(), emulate="bf16")
+    for a, r in zip(fms, ref):
+        assert _rel_err(a.cpu().numpy(), r) < 0.1
+    # update_part: freeze the backbone (convs 0..51): only head tensors move
+    m.set_trainable(range(52), False)
+    wb = m._last_plan.conv_params(10)["w"].clone(); wh = plan2.conv_params(60)["w"].clone()
+    m.train_step(torch.from_numpy(x2).cuda(), y2, 1e-3, freeze_bn=True)
+    assert torch.equal(plan2.conv_params(10)["w"], wb) and not torch.equal(plan2.conv_params(60)["w"], wh)
+    # non-finite gradient -> the step is skipped, parameters untouched, counter incremented
+    m.set_trainable(range(52), True)
+    bad = torch.from_numpy(x2).cuda().clone(); bad[0, 0, 0, 0] = float("nan")
+    wq = plan2.conv_params(60)["w"].clone()
+    m.train_step(bad, y2, 1e-3, freeze_bn=True)
+    _, ctrl3 = m.optimizer_state()
+    assert torch.equal(plan2.conv_params(60)["w"], wq) and ctrl3.tolist()[2] == 1
+
+
+def test_checkpoint_roundtrip_with_tf_names(tmp_path):
+    """N2: .npz checkpoint keyed by the TF variable names (convert_weight.py:28-32 / train.py:101-104), partial restore
+    with get_variables_to_restore(include, exclude) semantics (args.py:50-58), optimizer slots carried over."""
+    pkg = _pkg()
+    from yolov3_tensorflow_b200.utils import misc_utils as M
+    params, x, y_true = _train_case()
+    m = pkg.yolov3(80, O.COCO_ANCHORS, dtype="bf16")
+    m.set_params(params, "HWIO")
+    xs, ys = torch.from_numpy(x).cuda(), [torch.from_numpy(y).cuda() for y in y_true]
+    m.train_step(xs, ys, 1e-3, freeze_bn=True)
+    path = str(tmp_path / "ckpt.npz")
+    M.save_checkpoint(m, path, global_step=7)
+    ck = np.load(path)
+    assert "yolov3/darknet53_body/Conv/weights:0" in ck.files and "yolov3/yolov3_head/Conv_22/biases:0" in ck.files
+    assert ck["yolov3/darknet53_body/Conv_1/weights:0"].shape == (3, 3, 32, 64)
+    m2 = pkg.yolov3(80, O.COCO_ANCHORS, dtype="bf16")
+    m2.init_params(5)
+    keep = m2.get_params()[74]["w"].copy()
+    gs = M.restore_checkpoint(m2, path, restore_exclude=["yolov3/yolov3_head/Conv_22"])
+    assert gs == 7.0
+    p1, p2 = m.get_params(), m2.get_params()
+    assert np.array_equal(p1[10]["w"], p2[10]["w"]) and np.array_equal(p1[73]["var"], p2[73]["var"])
+    assert np.array_equal(p2[74]["w"], keep)                                   # excluded scope keeps its own values
+    # full restore into a third model: the momentum slots come back too (save_optimizer=True, args.py:37)
+    m3 = pkg.yolov3(80, O.COCO_ANCHORS, dtype="bf16")
+    assert M.restore_checkpoint(m3, path) == 7.0
+    m3.train_step(xs, ys, 1e-3, freeze_bn=True)                                # restores the slots, then steps
+    m.train_step(xs, ys, 1e-3, freeze_bn=True)
+    s1, c1 = m.optimizer_state(); s3, c3 = m3.optimizer_state()
+    assert c1.tolist()[1] == 2 and c3.tolist()[1] == 2                         # the step counter was restored as well
+    torch.testing.assert_close(s1[0][:864], s3[0][:864], rtol=1e-3, atol=1e-7)  # layer-0 momentum: same slot + same step

@@ -7,6 +7,7 @@ Importing the package loads the shared library; it fails loudly if it has not be
 from . import _lib  # noqa: F401  (raises ImportError when libyolob200.so is missing)
 from .model import yolov3  # noqa: F401
 from .utils.nms_utils import gpu_nms, batched_gpu_nms, cpu_nms, py_nms  # noqa: F401
-from .utils.misc_utils import load_weights, parse_anchors, read_class_names  # noqa: F401
+from .utils.misc_utils import (load_weights, parse_anchors, read_class_names, config_learning_rate,  # noqa: F401
+                               config_optimizer, learning_rate_at, save_checkpoint, restore_checkpoint)
 
 __version__ = "0.1.0"

@@ -13,6 +13,8 @@ LIB_PATH = os.path.join(_HERE, "libyolob200.so")
 
 YB_F16, YB_BF16, YB_F32 = 0, 1, 2
 YB_W_HWIO, YB_W_OIHW, YB_W_OHWI = 0, 1, 2
+YB_OPT_SGD, YB_OPT_MOMENTUM, YB_OPT_RMSPROP, YB_OPT_ADAM = 0, 1, 2, 3
+YB_TRAIN_FORWARD_ONLY, YB_TRAIN_BN_FROZEN = 1, 2
 
 
 class YoloB200Error(RuntimeError):
@@ -39,9 +41,16 @@ class LayerInfo(C.Structure):
                                    "out_w", "is_head", "scope_index", "upsample2x")]
 
 
+class Optimizer(C.Structure):      # yb_optimizer
+    _fields_ = [("kind", i32)] + [(n, f32) for n in ("lr", "grad_scale", "momentum", "decay", "beta1", "beta2", "epsilon",
+                                                      "weight_decay", "clip_norm")]
+
+
 _SIGS = {
     "yb_version": ([], i32),
     "yb_last_error_string": ([], C.c_char_p),
+    "yb_set_option": ([C.c_char_p, C.c_char_p], i32),
+    "yb_get_option": ([C.c_char_p], C.c_char_p),
     "yb_device_info": ([C.POINTER(i32)] * 3, i32),
     "yb_conv2d_fwd": ([C.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp], i32),
     "yb_conv_cout_pad": ([i32], i32),
@@ -68,7 +77,7 @@ _SIGS = {
     "yb_nms_workspace_bytes": ([i32, i32, i32, i32, C.POINTER(sz)], i32),
     "yb_nms": ([vp, vp, i32, i32, i32, i32, f32, f32, vp, sz, vp, vp, vp, vp, vp, vp], i32),
     "yb_loss_workspace_bytes": ([i32, i32, i32, C.POINTER(sz)], i32),
-    "yb_loss_layer": ([vp, vp, i32, i32, i32, i32, i32, i32, C.POINTER(f32), i32, i32, f32, vp, sz, vp, vp, i32, i32, vp], i32),
+    "yb_loss_layer": ([vp, vp, i32, i32, i32, i32, i32, i32, C.POINTER(f32), i32, i32, f32, f32, vp, sz, vp, vp, i32, i32, vp], i32),
     "yb_loss_finalize": ([vp, vp, vp], i32),
     "yb_box_iou": ([vp, vp, C.c_long, i32, vp, vp], i32),
     "yb_net_create": ([C.POINTER(vp), i32, i32, i32, i32, i32, i32], i32),
@@ -76,13 +85,18 @@ _SIGS = {
     "yb_net_num_layers": ([vp], i32),
     "yb_net_layer_info": ([vp, i32, C.POINTER(LayerInfo)], i32),
     "yb_net_arena_bytes": ([vp, C.POINTER(sz), C.POINTER(sz)], i32),
-    "yb_net_bind": ([vp, vp, sz, vp, sz], i32),
+    "yb_net_bind": ([vp, vp, sz, vp, sz, vp], i32),
+    "yb_net_refold_bn": ([vp, vp], i32),
     "yb_net_set_conv_params": ([vp, i32, vp, i32, vp, vp, vp, vp, vp, vp], i32),
     "yb_net_forward": ([vp, vp, vp, vp, vp, vp], i32),
     "yb_net_forward_layers": ([vp, vp, vp, vp, vp, i32, i32, vp], i32),
-    "yb_net_train_fwd_bwd": ([vp, vp, vp, vp, vp, C.POINTER(f32), i32, i32, f32, vp, vp, vp, vp, i32, vp], i32),
+    "yb_net_train_fwd_bwd": ([vp, vp, vp, vp, vp, C.POINTER(f32), i32, i32, f32, f32, vp, vp, vp, vp, i32, vp], i32),
     "yb_net_grad_buffer": ([vp, C.POINTER(vp), C.POINTER(sz)], i32),
-    "yb_net_train_update": ([vp, f32, f32, f32, f32, f32, vp], i32),
+    "yb_net_train_update": ([vp, C.POINTER(Optimizer), vp], i32),
+    "yb_net_train_reset_state": ([vp, i32, vp], i32),
+    "yb_net_opt_state": ([vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(i32), C.POINTER(vp)], i32),
+    "yb_net_set_trainable": ([vp, i32, i32, vp], i32),
+    "yb_net_train_refresh_dgrad": ([vp, vp], i32),
     "yb_net_get_conv_params": ([vp, i32] + [C.POINTER(vp)] * 6, i32),
     "yb_net_layer_grad": ([vp, i32] + [C.POINTER(vp)] * 4, i32),
     "yb_net_train_buffer": ([vp, i32, i32, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)], i32),
@@ -105,6 +119,15 @@ def check(rc: int, what: str = ""):
     if rc == -1:
         raise ValueError(f"{what}: {msg}")
     raise YoloB200Error(f"{what}: status {rc}: {msg}")
+
+
+def set_option(key: str, value):
+    """Runtime switch of the library (include/yolob200.h: yb_set_option); value None restores the default."""
+    check(lib.yb_set_option(key.encode(), None if value is None else str(value).encode()), f"yb_set_option({key})")
+
+
+def get_option(key: str) -> str:
+    return lib.yb_get_option(key.encode()).decode()
 
 
 def ptr(t):

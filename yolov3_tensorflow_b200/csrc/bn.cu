@@ -22,6 +22,17 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
                                    float* save_mean, float* save_invstd) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c) return;
+  if (sum == nullptr) {
+    // frozen BN (forward(is_training=False) under a gradient tape): normalise with the MOVING statistics, which are
+    // constants of the backward pass and are not updated
+    const float invstd = rsqrtf(moving_var[i] + eps);
+    const float sc = gamma[i] * invstd;
+    scale[i] = sc;
+    shift[i] = beta[i] - moving_mean[i] * sc;
+    save_mean[i] = moving_mean[i];
+    save_invstd[i] = invstd;
+    return;
+  }
   const float mean = sum[i] / count;
   float var = sqsum[i] / count - mean * mean;   // biased
   var = fmaxf(var, 0.f);
@@ -341,9 +352,10 @@ using namespace yb;
 extern "C" int yb_bn_finalize(const float* sum, const float* sqsum, long count, int c, const float* gamma,
                               const float* beta, float eps, float decay, float* moving_mean, float* moving_var,
                               float* scale, float* shift, float* save_mean, float* save_invstd, void* stream) {
-  YB_REQUIRE(sum && sqsum && gamma && beta && scale && shift && save_mean && save_invstd && c > 0 && count > 0,
-             "bn_finalize: bad argument");
+  YB_REQUIRE(gamma && beta && scale && shift && save_mean && save_invstd && c > 0 && count > 0, "bn_finalize: bad argument");
+  YB_REQUIRE((sum == nullptr) == (sqsum == nullptr), "bn_finalize: sum/sqsum must both be given (both NULL: frozen BN)");
   YB_REQUIRE((moving_mean == nullptr) == (moving_var == nullptr), "bn_finalize: moving_mean/var must both be given");
+  YB_REQUIRE(sum || moving_mean, "bn_finalize: frozen BN needs the moving statistics");
   bn_finalize_kernel<<<ceil_div(c, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       sum, sqsum, (float)count, c, gamma, beta, eps, decay, moving_mean, moving_var, scale, shift, save_mean, save_invstd);
   YB_CUDA(cudaGetLastError());

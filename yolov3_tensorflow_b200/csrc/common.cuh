@@ -35,6 +35,11 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 int num_sms();
+// runtime switches (csrc/capi.cu): "" when unset
+const char* opt(const char* key);
+int opt_int(const char* key, int dflt);
+struct DeviceOnce { unsigned long long mask = 0; };
+int ensure_smem_attr(DeviceOnce& once, const void* kernel, int bytes);
 
 // ----------------------------------------------------------------------------------
 // storage dtype helpers (activations/weights are fp16 or bf16; math is fp32)
@@ -143,6 +148,24 @@ __device__ __forceinline__ void tma_load_im2col_4d(void* dst, const CUtensorMap*
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h),
       "r"(n), "h"(ow), "h"(oh)
       : "memory");
+}
+
+// TMA store: a [box] tile of (swizzled) shared memory -> global, rows/cols past the tensor bounds are clipped.
+// Bulk-group completion: commit, then wait_group(.read) before the shared-memory tile is reused / the CTA exits.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() {   // at most N most-recent groups still READING shared memory
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_group() {        // at most N most-recent groups not yet complete
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
 // ---- tcgen05 / TMEM ----

@@ -27,6 +27,9 @@ struct ConvParams {
   int out_fp32, leaky, upsample;
   float* stat_sum;        // nullable: BN batch statistics of the raw conv result
   float* stat_sqsum;
+  int epi_tma;            // 1: 16-bit output tiles leave through shared memory + TMA stores (tmO), the residual comes in by TMA (tmR)
+  CUtensorMap tmO;        // [M, cout] view of the output slice, box 32 rows x 32 channels, SWIZZLE_64B
+  CUtensorMap tmR;        // same view of the residual
 };
 
 int conv_prepare(const yb_conv_desc* d, const void* x, const void* w_packed, const float* scale, const float* shift,

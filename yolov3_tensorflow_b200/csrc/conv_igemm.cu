@@ -33,8 +33,14 @@ namespace yb {
 static constexpr int BLOCK_M = 128;
 static constexpr int UMMA_K = 16;
 static constexpr int NUM_THREADS = 192;
-static constexpr int SMEM_BUDGET = 200 * 1024;  // operand ring; barriers + alignment slack on top
-static constexpr int STAGE_FLOATS = 32 * 33;    // per-epilogue-warp fp32 transpose tile (detection-head stores)
+static constexpr int SMEM_BUDGET = 192 * 1024;  // operand ring (6 x 32 KB / 8 x 24 KB stages); the rest of the 227 KB is below
+// Per-epilogue-warp staging: three 2 KB [32 rows][32 channels] SWIZZLE_64B tiles that rotate between the TMA residual
+// load, the in-place epilogue and the TMA store of a chunk (or one 32x33 fp32 transpose tile for the detection heads).
+static constexpr int EPI_TILE_BYTES = 2048;
+static constexpr int EPI_TILES = 3;
+static constexpr int STAGE_BYTES_W = EPI_TILES * EPI_TILE_BYTES;   // 6144 = 12 x 512: every tile is swizzle-atom aligned
+static constexpr int STAGE_FLOATS = STAGE_BYTES_W / 4;
+static constexpr int BAR_BYTES = 512;           // pipeline barriers + 4 x 3 residual barriers + TMEM slot
 
 template <int BN, int BK>
 struct Cfg {
@@ -43,7 +49,7 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BN;  // power of two >= 32 for BN in {64,128,256}
-  static constexpr int SMEM_BYTES = SMEM_BUDGET + 1024 /*align*/ + 256 /*barriers*/ + 4 * STAGE_FLOATS * 4 + 4 * BN * 4;
+  static constexpr int SMEM_BYTES = SMEM_BUDGET + 1024 /*align*/ + 4 * STAGE_BYTES_W + BAR_BYTES + 4 * BN * 4;
   static constexpr uint32_t SWIZZLE = (BK == 64) ? 2u : 4u;   // UMMA layout_type: 128B / 64B
   static constexpr uint32_t SBO = 8 * BK * 2;                  // bytes between 8-row groups
 };
@@ -78,8 +84,8 @@ template <int BN>
 __device__ __forceinline__ void load_scale_shift(const ConvParams& p, float* s_ss, int n0, int et /*0..127*/) {
   asm volatile("bar.sync 1, 128;" ::: "memory");          // nobody still reads the previous n-tile's values
   for (int c = et; c < BN; c += 128) {
-    s_ss[c] = __ldg(p.scale + n0 + c);
-    s_ss[BN + c] = __ldg(p.shift + n0 + c);
+    s_ss[c] = p.scale ? __ldg(p.scale + n0 + c) : 1.f;      // scale = shift = NULL: identity (dgrad convs)
+    s_ss[BN + c] = p.shift ? __ldg(p.shift + n0 + c) : 0.f;
   }
   asm volatile("bar.sync 1, 128;" ::: "memory");
 }
@@ -214,10 +220,146 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const int row
   }
 }
 
+
+// Column sums over the 32 rows of a 32x32 block held one row per lane (v[j] = column j of this lane's row): recursive
+// halving, 31 shuffles, no shared memory.  Lane l returns the sum of column l.  v is destroyed.
+template <int W>
+__device__ __forceinline__ void col_sum_step(float (&v)[32], const int lane) {
+  const bool hi = (lane & W) != 0;
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+    const float send = hi ? v[j] : v[j + W];
+    const float keep = hi ? v[j + W] : v[j];
+    v[j] = keep + __shfl_xor_sync(0xffffffffu, send, W);
+  }
+}
+__device__ __forceinline__ float warp_col_sum32(float (&v)[32], const int lane) {
+  col_sum_step<16>(v, lane); col_sum_step<8>(v, lane); col_sum_step<4>(v, lane); col_sum_step<2>(v, lane);
+  col_sum_step<1>(v, lane);
+  return v[0];
+}
+
+// Epilogue of one warp over its 32 accumulator rows x BN columns, 16-bit outputs, through shared memory and the TMA:
+//   TMEM -> registers -> scale/shift (+leaky) -> [+ residual tile, fetched by TMA into the same staging tile]
+//   -> 16-bit, written in place into the SWIZZLE_64B staging tile -> cp.async.bulk.tensor store (rows >= M clipped).
+// The first version stored straight from registers: one row per lane, so every 16-byte store instruction touched 32
+// different 128-byte lines (32 L1 wavefronts, half-written sectors) and the residual loads did the same; with loads and
+// MMAs disabled a 128x128 tile still took 3.2 us against a 0.55 us TMEM-read floor, which bounded every 1x1 layer and
+// the 52x52 3x3 layers (profiles/r01_j_conv_floor.txt).  Here the LSU only sees conflict-free
+// 16-byte shared-memory accesses; global traffic is full 64-byte row segments issued by the TMA unit.
+// Three staging tiles rotate per warp: while chunk c is processed, chunk c+1's residual is landing and chunk c-1's
+// store is draining.  `cnt` (chunks processed by this warp so far) indexes tiles and barrier phases across tiles.
+template <typename T, int BN>
+__device__ __forceinline__ void epilogue_tile_tma(const ConvParams& p, const int m0w, const int n0, const uint32_t t_row,
+                                                  const int lane, uint8_t* stage, uint64_t* res_bar, uint32_t& cnt,
+                                                  bool& prefetched, float* s_stat, const float* s_ss, const bool has_next,
+                                                  const int next_m0w, const int next_n0) {
+  if (m0w >= p.M) return;                        // warp-uniform: all 32 rows lie past the last pixel (tail tile)
+  const bool has_res = p.res != nullptr;
+  const bool row_ok = m0w + lane < p.M;
+  constexpr int NCH = BN / 32;
+  const int nvalid = min(NCH, (p.cout - n0) >> 5);           // zero-padded weight rows (cout_pad > cout) are not stored
+  const int sw = (lane >> 1) & 3;                // SWIZZLE_64B: 16-byte chunk j of row r sits at chunk j ^ ((r >> 1) & 3)
+  uint32_t rbuf[2][32];
+  tmem_ld_32x32(t_row, rbuf[0]);
+  if (has_res && !prefetched && lane == 0) {     // first chunk of the run: nobody fetched its residual ahead of time
+    bulk_wait_group_read<EPI_TILES - 1>();
+    const uint32_t b = cnt % EPI_TILES;
+    mbar_arrive_expect_tx(&res_bar[b], EPI_TILE_BYTES);
+    tma_load_2d(stage + b * EPI_TILE_BYTES, &p.tmR, &res_bar[b], n0, m0w);
+  }
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    if (ch >= nvalid) break;
+    const uint32_t b = cnt % EPI_TILES;
+    uint8_t* buf = stage + b * EPI_TILE_BYTES;
+    if (!has_res) {                              // the store that last read this tile (3 chunks ago) has drained
+      if (lane == 0) bulk_wait_group_read<EPI_TILES - 1>();
+      __syncwarp();
+    }
+    tmem_ld_wait();
+    uint32_t (&r)[32] = rbuf[ch & 1];
+    if (ch + 1 < nvalid) tmem_ld_32x32(t_row + (ch + 1) * 32, rbuf[(ch + 1) & 1]);
+    if (has_res) {
+      // fetch the NEXT chunk's residual (this tile's, or the first of the next tile) into the tile freed two stores ago
+      const bool last = ch + 1 >= nvalid;
+      const int nm = last ? next_m0w : m0w;
+      const int nc = last ? next_n0 : n0 + (ch + 1) * 32;
+      const bool go = last ? (has_next && next_m0w < p.M) : true;
+      if (go && lane == 0) {
+        bulk_wait_group_read<1>();
+        const uint32_t nb = (cnt + 1) % EPI_TILES;
+        mbar_arrive_expect_tx(&res_bar[nb], EPI_TILE_BYTES);
+        tma_load_2d(stage + nb * EPI_TILE_BYTES, &p.tmR, &res_bar[nb], nc, nm);
+      }
+      if (last) prefetched = go;
+    }
+    if (p.stat_sum != nullptr) {
+      // BN batch statistics of the raw conv output: per-CTA column sums in shared memory, flushed by the caller
+      float a[32], q[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float t = row_ok ? __uint_as_float(r[j]) : 0.f;
+        a[j] = t;
+        q[j] = t * t;
+      }
+      const float cs = warp_col_sum32(a, lane);
+      const float cs2 = warp_col_sum32(q, lane);
+      atomicAdd(&s_stat[ch * 32 + lane], cs);
+      atomicAdd(&s_stat[BN + ch * 32 + lane], cs2);
+    }
+    float v[32];
+    const float4* sc4 = reinterpret_cast<const float4*>(s_ss + ch * 32);
+    const float4* sh4 = reinterpret_cast<const float4*>(s_ss + BN + ch * 32);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 sc = sc4[j];
+      const float4 sh = sh4[j];
+      v[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), sc.x, sh.x);
+      v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), sc.y, sh.y);
+      v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), sc.z, sh.z);
+      v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), sc.w, sh.w);
+    }
+    if (p.leaky) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.1f * v[j]);   // == v > 0 ? v : 0.1 v
+    }
+    uint4* rowp = reinterpret_cast<uint4*>(buf + lane * 64);
+    if (has_res) {
+      mbar_wait(&res_bar[b], (cnt / EPI_TILES) & 1);                   // residual tile landed (async proxy -> visible)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 u = rowp[j ^ sw];
+        float2 f;
+        f = Pack2<T>::unpack(u.x); v[8 * j + 0] += f.x; v[8 * j + 1] += f.y;
+        f = Pack2<T>::unpack(u.y); v[8 * j + 2] += f.x; v[8 * j + 3] += f.y;
+        f = Pack2<T>::unpack(u.z); v[8 * j + 4] += f.x; v[8 * j + 5] += f.y;
+        f = Pack2<T>::unpack(u.w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 pk;
+      pk.x = Pack2<T>::pack(v[8 * j + 0], v[8 * j + 1]);
+      pk.y = Pack2<T>::pack(v[8 * j + 2], v[8 * j + 3]);
+      pk.z = Pack2<T>::pack(v[8 * j + 4], v[8 * j + 5]);
+      pk.w = Pack2<T>::pack(v[8 * j + 6], v[8 * j + 7]);
+      rowp[j ^ sw] = pk;
+    }
+    fence_proxy_async();                         // generic-proxy writes -> visible to the TMA (async proxy)
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(&p.tmO, buf, n0 + ch * 32, m0w);
+      bulk_commit_group();
+    }
+    ++cnt;
+  }
+}
+
 template <typename T, int BN, int BK>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const ConvParams p) {
+                  const __grid_constant__ ConvParams p) {
   using C = Cfg<BN, BK>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -233,15 +375,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   uint8_t* sA = smem;
   uint8_t* sB = smem + nst * (kps > 1 ? kps : 1) * C::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BUDGET);
+  float* stage_base = reinterpret_cast<float*>(smem + SMEM_BUDGET);          // 4 x STAGE_BYTES_W, 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BUDGET + 4 * STAGE_BYTES_W);
   uint64_t* full_bar = bars;                       // [<=8] TMA -> MMA
   uint64_t* empty_bar = bars + 8;                  // [<=8] MMA -> TMA
   uint64_t* tfull_bar = bars + 16;                 // [2] MMA -> epilogue
   uint64_t* tempty_bar = bars + 18;                // [2] epilogue -> MMA
   uint64_t* bres_bar = bars + 20;                  // resident weights landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
-  float* stage_base = reinterpret_cast<float*>(smem + SMEM_BUDGET + 256);
-  float* s_stat = stage_base + 4 * STAGE_FLOATS;   // [2][BN] per-CTA column sums / sums of squares
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
+  uint64_t* res_bar = bars + 32;                   // [4 warps][EPI_TILES] residual tile landed (TMA)
+  float* s_stat = reinterpret_cast<float*>(smem + SMEM_BUDGET + 4 * STAGE_BYTES_W + BAR_BYTES);   // [2][BN] per-CTA column sums / sums of squares
   float* s_ss = s_stat + 2 * BN;                   // [2][BN] scale / shift of the current n-tile
 
   const int warp = threadIdx.x >> 5;
@@ -262,6 +405,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
     }
     mbar_init(bres_bar, 1);
+    for (int i = 0; i < 4 * EPI_TILES; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
@@ -371,6 +515,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
     int it = 0;
+    uint32_t epi_cnt = 0;
+    bool epi_prefetched = false;
+    uint8_t* my_stage = reinterpret_cast<uint8_t*>(stage_base) + (warp - 2) * STAGE_BYTES_W;
+    uint64_t* my_res_bar = res_bar + (warp - 2) * EPI_TILES;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -383,15 +531,27 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         cur_n0 = n0;
       }
       if (n0 != ss_n0) { load_scale_shift<BN>(p, s_ss, n0, et); ss_n0 = n0; }
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tcgen05_fence_after();
-      if (!(p.dbg & 8))
-        epilogue_tile<T, BN>(p, m0 + quarter * 32 + lane, n0, tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN, lane,
-                             stage_base + (warp - 2) * STAGE_FLOATS, s_stat, s_ss);
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
+      if (p.epi_tma) {
+        const int ntile = tile + gridDim.x;
+        int nm = 0, nn = 0;
+        if (ntile < num_tiles) tile_coords(p, ntile, nm, nn);
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tcgen05_fence_after();
+        if (!(p.dbg & 8))
+          epilogue_tile_tma<T, BN>(p, m0 + quarter * 32, n0, t_row, lane, my_stage, my_res_bar, epi_cnt, epi_prefetched,
+                                   s_stat, s_ss, ntile < num_tiles, nm * BLOCK_M + quarter * 32, nn * BN);
+      } else {
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tcgen05_fence_after();
+        if (!(p.dbg & 8))
+          epilogue_tile<T, BN>(p, m0 + quarter * 32 + lane, n0, t_row, lane, reinterpret_cast<float*>(my_stage), s_stat, s_ss);
+      }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
+    if (p.epi_tma && lane == 0) bulk_wait_group<0>();       // every TMA store of this warp has completed
     if (p.stat_sum != nullptr && cur_n0 >= 0) stat_flush<BN>(p, s_stat, cur_n0, et);
   }
 
@@ -418,7 +578,7 @@ struct Cfg2 {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 4 * STAGE_FLOATS * 4 + 4 * BN * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 4 * STAGE_BYTES_W + BAR_BYTES + 4 * BN * 4;
   static constexpr uint32_t SWIZZLE = (BK == 64) ? 2u : 4u;
   static constexpr uint32_t SBO = 8 * BK * 2;
 };
@@ -426,20 +586,21 @@ struct Cfg2 {
 template <typename T, int BN, int BK>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                       const ConvParams p) {
+                       const __grid_constant__ ConvParams p) {
   using C = Cfg2<BN, BK>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + C::STAGES * C::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  float* stage_base = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);   // 4 x STAGE_BYTES_W, 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + 4 * STAGE_BYTES_W);
   uint64_t* full_bar = bars;                        // [STAGES] used in the leader only
   uint64_t* empty_bar = bars + C::STAGES;           // [STAGES] one per CTA (multicast commit)
   uint64_t* tfull_bar = bars + 2 * C::STAGES;       // [2] one per CTA (multicast commit)
   uint64_t* tempty_bar = bars + 2 * C::STAGES + 2;  // [2] used in the leader only (8 arrivals: 4 warps x 2 CTAs)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
-  float* stage_base = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
-  float* s_stat = stage_base + 4 * STAGE_FLOATS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
+  uint64_t* res_bar = bars + 32;                    // [4 warps][EPI_TILES] residual tile landed (TMA), CTA-local
+  float* s_stat = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 4 * STAGE_BYTES_W + BAR_BYTES);
   float* s_ss = s_stat + 2 * BN;
 
   const int warp = threadIdx.x >> 5;
@@ -462,6 +623,7 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 8);
     }
+    for (int i = 0; i < 4 * EPI_TILES; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_2sm<C::TMEM_COLS>(tmem_slot);
@@ -552,6 +714,10 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
     int it = 0;
+    uint32_t epi_cnt = 0;
+    bool epi_prefetched = false;
+    uint8_t* my_stage = reinterpret_cast<uint8_t*>(stage_base) + (warp - 2) * STAGE_BYTES_W;
+    uint64_t* my_res_bar = res_bar + (warp - 2) * EPI_TILES;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -564,14 +730,25 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         cur_n0 = n0;
       }
       if (n0 != ss_n0) { load_scale_shift<BN>(p, s_ss, n0, et); ss_n0 = n0; }
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_fence_after();
-      epilogue_tile<T, BN>(p, m0 + quarter * 32 + lane, n0, tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN, lane,
-                           stage_base + (warp - 2) * STAGE_FLOATS, s_stat, s_ss);
+      if (p.epi_tma) {
+        const int ntile = tile + num_clusters;
+        int nm = 0, nn = 0;
+        if (ntile < num_tiles) tile_coords(p, ntile, nm, nn);
+        if (!(p.dbg & 8))
+          epilogue_tile_tma<T, BN>(p, m0 + quarter * 32, n0, t_row, lane, my_stage, my_res_bar, epi_cnt, epi_prefetched,
+                                   s_stat, s_ss, ntile < num_tiles,
+                                   nm * (2 * BLOCK_M) + (int)rank * BLOCK_M + quarter * 32, nn * BN);
+      } else if (!(p.dbg & 8)) {
+        epilogue_tile<T, BN>(p, m0 + quarter * 32 + lane, n0, t_row, lane, reinterpret_cast<float*>(my_stage), s_stat, s_ss);
+      }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);    // the leader's MMA warp waits for both CTAs
     }
+    if (p.epi_tma && lane == 0) bulk_wait_group<0>();       // every TMA store of this warp has completed
     if (p.stat_sum != nullptr && cur_n0 >= 0) stat_flush<BN>(p, s_stat, cur_n0, et);
   }
 
@@ -594,7 +771,7 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 template <typename T, int BK, int CM, int CN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_igemm_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                       const ConvParams p) {
+                       const __grid_constant__ ConvParams p) {
   constexpr int BN = 256;
   constexpr int CSIZE = 2 * CM * CN;
   using C = Cfg2<BN, BK>;
@@ -602,14 +779,15 @@ conv_igemm_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + C::STAGES * C::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  float* stage_base = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);   // 4 x STAGE_BYTES_W, 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + 4 * STAGE_BYTES_W);
   uint64_t* full_bar = bars;                        // [STAGES] used in the leader only
   uint64_t* empty_bar = bars + C::STAGES;           // [STAGES] one per CTA (multicast commit)
   uint64_t* tfull_bar = bars + 2 * C::STAGES;       // [2] one per CTA (multicast commit)
   uint64_t* tempty_bar = bars + 2 * C::STAGES + 2;  // [2] used in the leader only (8 arrivals: 4 warps x 2 CTAs)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
-  float* stage_base = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
-  float* s_stat = stage_base + 4 * STAGE_FLOATS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
+  uint64_t* res_bar = bars + 32;                    // [4 warps][EPI_TILES] residual tile landed (TMA), CTA-local
+  float* s_stat = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 4 * STAGE_BYTES_W + BAR_BYTES);
   float* s_ss = s_stat + 2 * BN;
 
   const int warp = threadIdx.x >> 5;
@@ -635,6 +813,7 @@ conv_igemm_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 8);
     }
+    for (int i = 0; i < 4 * EPI_TILES; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_2sm<C::TMEM_COLS>(tmem_slot);
@@ -745,7 +924,7 @@ conv_igemm_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_fence_after();
       epilogue_tile<T, BN>(p, m0 + quarter * 32 + lane, n0, tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN, lane,
-                           stage_base + (warp - 2) * STAGE_FLOATS, s_stat, s_ss);
+                           stage_base + (warp - 2) * STAGE_FLOATS, s_stat, s_ss);   // (register-store epilogue only)
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], crank & ~1u);   // this pair's leader
@@ -848,12 +1027,9 @@ int make_tmap_im2col_px(CUtensorMap* tm, const void* base, int dtype, int n, int
 template <typename T, int BN, int BK>
 static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t st) {
   using C = Cfg<BN, BK>;
-  static bool attr_done = false;
+  static DeviceOnce once;
   auto kern = conv_igemm_kernel<T, BN, BK>;
-  if (!attr_done) {
-    YB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_done = true;
-  }
+  { const int rc = ensure_smem_attr(once, reinterpret_cast<const void*>(kern), C::SMEM_BYTES); if (rc) return rc; }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   kern<<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmA, tmB, p);
@@ -864,12 +1040,9 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv
 template <typename T, int BN, int BK>
 static int launch_cfg2(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t st) {
   using C = Cfg2<BN, BK>;
-  static bool attr_done = false;
+  static DeviceOnce once;
   auto kern = conv_igemm_2cta_kernel<T, BN, BK>;
-  if (!attr_done) {
-    YB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_done = true;
-  }
+  { const int rc = ensure_smem_attr(once, reinterpret_cast<const void*>(kern), C::SMEM_BYTES); if (rc) return rc; }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int max_clusters = num_sms() / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
@@ -892,7 +1065,12 @@ template <typename T, int BK, int CM, int CN>
 static int launch_mc(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t st) {
   using C = Cfg2<256, BK>;
   constexpr int CSIZE = 2 * CM * CN;
-  static int max_clusters = -1;
+  static int max_clusters_dev[64];
+  static DeviceOnce once;
+  int dev = 0;
+  YB_CUDA(cudaGetDevice(&dev));
+  int& max_clusters = max_clusters_dev[dev & 63];
+  if (!(once.mask & (1ull << (dev & 63)))) max_clusters = -1;
   auto kern = conv_igemm_mc_kernel<T, BK, CM, CN>;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -905,7 +1083,7 @@ static int launch_mc(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvP
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if (max_clusters < 0) {
-    YB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    { const int rc = ensure_smem_attr(once, reinterpret_cast<const void*>(kern), C::SMEM_BYTES); if (rc) return rc; }
     cfg.gridDim = dim3(CSIZE * (num_sms() / CSIZE));
     int nc = 0;
     YB_CUDA(cudaOccupancyMaxActiveClusters(&nc, kern, &cfg));
@@ -978,7 +1156,7 @@ static int conv_prepare_core(const yb_conv_desc* d, int win, int kh, int kw, int
   YB_REQUIRE(d->dtype == YB_F16 || d->dtype == YB_BF16, "conv: dtype must be f16 or bf16");
   YB_REQUIRE(d->h % d->stride == 0 && d->w % d->stride == 0, "conv: h,w must be divisible by stride");
   YB_REQUIRE(d->in_ld >= d->cin && d->in_ld % 8 == 0, "conv: in_ld %d invalid for cin %d", d->in_ld, d->cin);
-  YB_REQUIRE(x && w_packed && scale && shift && out, "conv: null pointer");
+  YB_REQUIRE(x && w_packed && out && (scale == nullptr) == (shift == nullptr), "conv: null pointer");   // scale = shift = NULL: identity
   YB_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)out & 15) == 0 &&
                  ((uintptr_t)res & 15) == 0,
              "conv: pointers must be 16-byte aligned");
@@ -997,7 +1175,7 @@ static int conv_prepare_core(const yb_conv_desc* d, int win, int kh, int kw, int
   const int pad = win ? 0 : d->ksize / 2;
   p->M = d->n * P * Q; p->P = P; p->Q = Q;
   // a CTA pair per 256-row tile once there are enough tiles to occupy the 74 SM pairs
-  const char* force = getenv("YB_CONV_MODE");   // "1cta" / "2cta": testing override
+  const char* force = opt("YB_CONV_MODE");      // "1cta" / "2cta": testing override
   // (measured, profiles/r01_b: pairs win 1.4-1.6x on 256-wide tiles — half the L2->smem fill per FLOP — but lose on
   //  64/128-wide tiles, whose short per-tile pipelines are dominated by the cross-CTA barrier latency)
   bool two = cout_pad % 256 == 0 && (long)ceil_div(p->M, 2 * BLOCK_M) * (cout_pad / 256) >= 32;
@@ -1006,7 +1184,7 @@ static int conv_prepare_core(const yb_conv_desc* d, int win, int kh, int kw, int
   p->two_cta = two ? 1 : 0;
   // cluster multicast on top of the pair kernel: 2x2 pairs when there are >= 2 n-tiles, 2x1 (share B) otherwise
   int mc_m = 1, mc_n = 1;
-  const char* mcf = getenv("YB_CONV_MC");       // "0": off, "1": force on where legal (testing)
+  const char* mcf = opt("YB_CONV_MC");          // "0": off, "1": force on where legal (testing)
   if (two && bk == 64 && cout_pad % 256 == 0 && !(mcf && mcf[0] == '0')) {
     const int mt = ceil_div(p->M, 2 * BLOCK_M), nt = cout_pad / 256;
     // measured (profiles/r01_e): +10 % per SM but only 120-132 SMs are schedulable in 8-/4-CTA clusters -> no net gain;
@@ -1015,19 +1193,19 @@ static int conv_prepare_core(const yb_conv_desc* d, int win, int kh, int kw, int
     if (big && mt >= 2) { mc_m = 2; mc_n = (nt % 2 == 0) ? 2 : 1; }
   }
   p->mc_m = mc_m; p->mc_n = mc_n;
-  { const char* dbg = getenv("YB_CONV_DBG"); p->dbg = dbg ? atoi(dbg) : 0; }
+  p->dbg = opt_int("YB_CONV_DBG", 0);
   p->kps = 1;   // set below once the tile shape is known
   const int bn = two ? conv_block_n2(cout_pad) : conv_block_n(cout_pad);
   {
     // resident weights (1-CTA kernel): one n-tile, and the [BN, K] tile leaves room for >= 3 A stages
     const long b_bytes = (long)kh * kw * d->cin * bn * 2;
-    const char* br = getenv("YB_CONV_BRES");
+    const char* br = opt("YB_CONV_BRES");
     p->b_resident = (!two && cout_pad == bn && SMEM_BUDGET - b_bytes >= 3L * BLOCK_M * bk * 2 && (br && br[0] == '1')) ? 1 : 0;   // opt-in: measured no gain (profiles/r01_i)
   }
   if (!two && !p->b_resident) {
     // k-blocks per barrier phase in the 1-CTA kernel: the largest of {4, 3, 2} that divides the k-block count and still
     // leaves two groups in the ring.  YB_CONV_KPS=0 restores one handshake per k-block.
-    const char* ke = getenv("YB_CONV_KPS");
+    const char* ke = opt("YB_CONV_KPS");
     const bool on = !(ke && ke[0] == '0');
     const int num_kb = kh * kw * (d->cin / bk);
     const long stage_bytes = (long)(BLOCK_M + bn) * bk * 2;
@@ -1047,6 +1225,22 @@ static int conv_prepare_core(const yb_conv_desc* d, int win, int kh, int kw, int
   p->out_fp32 = d->out_fp32; p->leaky = d->leaky; p->upsample = d->upsample2x;
   p->stat_sum = stat_sum; p->stat_sqsum = stat_sqsum;
   int rc;
+  // 16-bit outputs leave through shared memory + TMA stores (YB_CONV_EPI=reg: the register-store epilogue of round 1);
+  // the multicast kernel, the 2x-upsampling / parity-scatter stores and the fp32 heads keep the register path
+  {
+    const char* ep = opt("YB_CONV_EPI");
+    p->epi_tma = (!d->out_fp32 && !d->upsample2x && !scatter && mc_m * mc_n == 1 && !(ep[0] == 'r')) ? 1 : 0;
+    memset(&p->tmO, 0, sizeof(p->tmO));
+    memset(&p->tmR, 0, sizeof(p->tmR));
+    if (p->epi_tma) {
+      rc = make_tmap_2d(&p->tmO, out, d->dtype, p->M, d->cout, d->out_ld, 32, 32, 0);
+      if (rc) return rc;
+      if (res) {
+        rc = make_tmap_2d(&p->tmR, res, d->dtype, p->M, d->cout, d->res_ld, 32, 32, 0);
+        if (rc) return rc;
+      }
+    }
+  }
   if (p->im2col) {
     rc = make_tmap_im2col_px(tmA, x, d->dtype, d->n, d->h, d->w, d->cin, d->in_ld, win ? 1 : d->ksize, d->stride, pad, bk,
                              BLOCK_M / mc_n);
@@ -1097,14 +1291,6 @@ extern "C" int yb_conv2d_dgrad_s2(const yb_conv_desc* fwd, const void* dz, int d
   YB_REQUIRE(fwd && dz && w_dgrad_s2 && dx, "dgrad_s2: null pointer");
   YB_REQUIRE(fwd->ksize == 3 && fwd->stride == 2 && fwd->h % 2 == 0 && fwd->w % 2 == 0, "dgrad_s2: 3x3 stride-2 convs only");
   YB_REQUIRE(k_cout >= fwd->cout && k_cout % 32 == 0 && dz_ld >= k_cout, "dgrad_s2: dz must hold k_cout (multiple of 32) channels");
-  static float* unit = nullptr;                  // scale = 1 / shift = 0 vectors (2 x 1024 floats, created once)
-  if (!unit) {
-    float h_unit[2048];
-    for (int i = 0; i < 1024; ++i) { h_unit[i] = 1.f; h_unit[1024 + i] = 0.f; }
-    YB_CUDA(cudaMalloc(&unit, sizeof(h_unit)));
-    YB_CUDA(cudaMemcpy(unit, h_unit, sizeof(h_unit), cudaMemcpyHostToDevice));
-  }
-  YB_REQUIRE(fwd->cin <= 1024, "dgrad_s2: cin > 1024");
   yb_conv_desc d = *fwd;
   d.h = fwd->h / 2; d.w = fwd->w / 2; d.cin = k_cout; d.cout = fwd->cin; d.ksize = 1; d.stride = 1;
   d.in_ld = dz_ld; d.out_ld = dx_ld; d.res_ld = res_ld; d.out_fp32 = 0; d.leaky = 0; d.upsample2x = 0;
@@ -1115,7 +1301,7 @@ extern "C" int yb_conv2d_dgrad_s2(const yb_conv_desc* fwd, const void* dz, int d
     yb::ConvParams p;
     int cout_pad = 0;
     int rc = yb::conv_prepare_win(&d, 1 + (c >> 1), 1 + (c & 1), 1 + c, dz,
-                                  static_cast<const uint8_t*>(w_dgrad_s2) + woff[c] * 2, unit, unit + 1024, res, dx, &tmA,
+                                  static_cast<const uint8_t*>(w_dgrad_s2) + woff[c] * 2, nullptr, nullptr, res, dx, &tmA,
                                   &tmB, &p, &cout_pad);
     if (rc) return rc;
     rc = yb::conv_launch(d.dtype, cout_pad, tmA, tmB, p, static_cast<cudaStream_t>(stream));

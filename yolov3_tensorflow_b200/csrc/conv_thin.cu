@@ -411,11 +411,8 @@ template <typename T, int COUT, int STRIDE, bool STEM>
 static int launch_thin(const ThinParams& p, cudaStream_t st) {
   using C = ThinCfg<T, COUT, STRIDE, STEM>;
   auto kern = conv_thin_kernel<T, COUT, STRIDE, STEM>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    YB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    attr_done = true;
-  }
+  static DeviceOnce once;
+  { const int rc = ensure_smem_attr(once, reinterpret_cast<const void*>(kern), C::SMEM); if (rc) return rc; }
   int per_sm = 227 * 1024 / (C::SMEM + 1024);
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 8) per_sm = 8;
@@ -467,7 +464,7 @@ extern "C" int yb_stem_conv_fwd_tc(const float* x, const float* w_ohwi, const fl
   p.tiles_y = ceil_div(h, TH); p.tiles_x = ceil_div(w, TW);
   p.num_tiles = p.tiles_x * p.tiles_y * n;
   p.leaky = leaky;
-  { const char* dbg = getenv("YB_STEM_DBG"); p.dbg = dbg ? atoi(dbg) : 0; }
+  p.dbg = opt_int("YB_STEM_DBG", 0);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == YB_F16) return launch_thin<__half, 32, 1, true>(p, st);
   if (dtype == YB_BF16) return launch_thin<__nv_bfloat16, 32, 1, true>(p, st);

@@ -208,12 +208,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 template <typename T, int BNW, int TP>
 static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, const WgradParams& p, dim3 grid, cudaStream_t st) {
   using C = WCfg<BNW, TP>;
-  static bool attr_done = false;
+  static DeviceOnce once;
   auto kern = conv_wgrad_kernel<T, BNW, TP>;
-  if (!attr_done) {
-    YB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_done = true;
-  }
+  { const int rc = ensure_smem_attr(once, reinterpret_cast<const void*>(kern), C::SMEM_BYTES); if (rc) return rc; }
   kern<<<grid, WG_THREADS, C::SMEM_BYTES, st>>>(tmA, tmB, p);
   YB_CUDA(cudaGetLastError());
   return YB_OK;
@@ -279,7 +276,7 @@ extern "C" int yb_conv2d_wgrad(const yb_conv_desc* d, const void* x, const void*
   p.dw = dw;
   const int taps = d->ksize * d->ksize;
   // taps accumulated per CTA: all 9 for cin = 32 (288 TMEM columns), one kernel row otherwise; 1x1 convs have one tap
-  const char* tpf = getenv("YB_WGRAD_TP");     // "1": one tap per CTA (the first version; A/B testing)
+  const char* tpf = opt("YB_WGRAD_TP");     // "1": one tap per CTA (the first version; A/B testing)
   const int tp = (taps == 1 || (tpf && tpf[0] == '1')) ? 1 : (bnw == 32 ? 9 : 3);
   const int tap_groups = taps / tp;
   const int co_tiles = ceil_div(d->cout, WG_BM);
@@ -322,7 +319,7 @@ extern "C" int yb_stem_conv_wgrad(const float* x, const void* dz, int dtype, int
   YB_REQUIRE(x && dz && dw && n > 0 && h > 0 && w > 0, "stem_wgrad: bad argument");
   YB_REQUIRE(dtype == YB_F16 || dtype == YB_BF16, "stem_wgrad: dtype must be f16 or bf16");
   {
-    const char* sw = getenv("YB_STEM_WGRAD");   // "cuda": the CUDA-core kernel below (A/B testing)
+    const char* sw = opt("YB_STEM_WGRAD");   // "cuda": the CUDA-core kernel below (A/B testing)
     if (!(sw && sw[0] == 'c')) return yb_stem_conv_wgrad_tc(x, dz, dtype, n, h, w, dw, stream);
   }
   const long P = (long)n * h * w;

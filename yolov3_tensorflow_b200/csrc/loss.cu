@@ -23,6 +23,7 @@ struct LossParams {
   float anchor_w[3], anchor_h[3];
   int label_smooth, focal;
   float inv_n;           // 1 / batch size (model.py:206)
+  float grad_mul;        // inv_n * loss_scale: what the stored gradient is multiplied by (fp16 storage needs loss scaling)
   const float* gt_boxes; // [n, cap, 4] cx,cy,w,h
   const int* gt_count;   // [n]
   int cap;
@@ -135,13 +136,13 @@ __global__ void __launch_bounds__(256) loss_kernel(const LossParams p) {
     }
     if (p.dfm != nullptr && lane < 5) {
       float g;
-      const float cg = cbox * p.inv_n;
+      const float cg = cbox * p.grad_mul;
       if (lane == 0) g = -2.f * dx * sx * (1.f - sx) * cg;
       else if (lane == 1) g = -2.f * dy * sy * (1.f - sy) * cg;
       else if (lane == 2) g = (w_in && !pw_zero) ? -2.f * dw * cg : 0.f;
       else if (lane == 3) g = (h_in && !ph_zero) ? -2.f * dh * cg : 0.f;
       else {
-        const float gc = wconf * mix * p.inv_n;
+        const float gc = wconf * mix * p.grad_mul;
         g = p.focal ? gc * (fm_ * fm_ * (sc - m) - 2.f * fm_ * sc * (1.f - sc) * bce_c) : gc * (sc - m);
       }
       store_grad<T>(p, box, a, cellrow, lane, g);
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(256) loss_kernel(const LossParams p) {
       float t = yrow[5 + k];
       if (p.label_smooth) t = (1.f - 0.01f) * t + 0.01f * 1.f / (float)p.C;
       if (m != 0.f) cls += bce_logits(z, t);
-      if (p.dfm != nullptr) store_grad<T>(p, box, a, cellrow, 5 + k, m * mix * (sigmoid_f(z) - t) * p.inv_n);
+      if (p.dfm != nullptr) store_grad<T>(p, box, a, cellrow, 5 + k, m * mix * (sigmoid_f(z) - t) * p.grad_mul);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cls += __shfl_xor_sync(0xffffffffu, cls, o);
@@ -201,8 +202,8 @@ extern "C" int yb_loss_workspace_bytes(int n, int gh, int gw, size_t* bytes) {
 
 extern "C" int yb_loss_layer(const float* feature_map, const float* y_true, int n, int gh, int gw, int img_h, int img_w,
                              int class_num, const float* anchors3x2, int use_label_smooth, int use_focal_loss,
-                             float inv_batch, void* workspace, size_t workspace_bytes, double* loss4, void* dfm,
-                             int dfm_dtype, int dfm_ld, void* stream) {
+                             float inv_batch, float loss_scale, void* workspace, size_t workspace_bytes, double* loss4,
+                             void* dfm, int dfm_dtype, int dfm_ld, void* stream) {
   YB_REQUIRE(feature_map && y_true && anchors3x2 && workspace && loss4, "loss_layer: null pointer");
   YB_REQUIRE(n > 0 && gh > 0 && gw > 0 && class_num > 0, "loss_layer: bad shape");
   size_t need = 0;
@@ -228,6 +229,7 @@ extern "C" int yb_loss_layer(const float* feature_map, const float* y_true, int 
   p.img_h = (float)img_h; p.img_w = (float)img_w;
   for (int i = 0; i < 3; ++i) { p.anchor_w[i] = anchors3x2[2 * i]; p.anchor_h[i] = anchors3x2[2 * i + 1]; }
   p.label_smooth = use_label_smooth; p.focal = use_focal_loss; p.inv_n = inv_batch;
+  p.grad_mul = inv_batch * (loss_scale > 0.f ? loss_scale : 1.f);
   p.gt_boxes = gt_boxes; p.gt_count = gt_count; p.cap = cells3; p.loss4 = loss4;
   p.dfm = dfm; p.dfm_dtype = dfm_dtype; p.dfm_ld = dfm_ld;
   const long nbox = (long)n * cells3;

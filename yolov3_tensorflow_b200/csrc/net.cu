@@ -14,7 +14,7 @@
 
 namespace yb {
 void train_layout(yb_net* net);
-int train_bind(yb_net* net);
+int train_bind(yb_net* net, cudaStream_t st);
 int train_refresh_dgrad_weights(yb_net* net, int layer, void* stream);
 
 static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
@@ -189,7 +189,7 @@ extern "C" int yb_net_arena_bytes(const yb_net* net, size_t* activation_bytes, s
 }
 
 extern "C" int yb_net_bind(yb_net* net, void* activation_arena, size_t activation_bytes, void* param_arena,
-                           size_t param_bytes) {
+                           size_t param_bytes, void* stream) {
   YB_REQUIRE(net && activation_arena && param_arena, "bind: null pointer");
   YB_REQUIRE(activation_bytes >= net->act_bytes && param_bytes >= net->param_bytes, "bind: arena too small");
   YB_REQUIRE(((uintptr_t)activation_arena & 255) == 0 && ((uintptr_t)param_arena & 255) == 0,
@@ -215,7 +215,7 @@ extern "C" int yb_net_bind(yb_net* net, void* activation_arena, size_t activatio
     if (rc) return rc;
     L.prepared = true;
   }
-  if (net->training) return train_bind(net);
+  if (net->training) return train_bind(net, static_cast<cudaStream_t>(stream));
   return YB_OK;
 }
 
@@ -252,6 +252,20 @@ extern "C" int yb_net_set_conv_params(yb_net* net, int layer, const float* w, in
   return YB_OK;
 }
 
+extern "C" int yb_net_refold_bn(yb_net* net, void* stream) {
+  YB_REQUIRE(net && net->par, "refold_bn: net not bound");
+  for (auto& L : net->layers) {
+    if (!L.info.has_bn) continue;
+    int rc = yb_bn_fold(reinterpret_cast<const float*>(net->par + L.gamma), reinterpret_cast<const float*>(net->par + L.beta),
+                        reinterpret_cast<const float*>(net->par + L.mean), reinterpret_cast<const float*>(net->par + L.var),
+                        L.info.cout, net->bn_eps, reinterpret_cast<float*>(net->par + L.scale),
+                        reinterpret_cast<float*>(net->par + L.shift), stream);
+    if (rc) return rc;
+  }
+  net->fold_dirty = false;
+  return YB_OK;
+}
+
 extern "C" int yb_net_forward(yb_net* net, const float* images, float* fm1, float* fm2, float* fm3, void* stream) {
   return yb_net_forward_layers(net, images, fm1, fm2, fm3, 0, 1 << 30, stream);
 }
@@ -264,17 +278,10 @@ extern "C" int yb_net_forward_layers(yb_net* net, const float* images, float* fm
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* user_fm[3] = {fm1, fm2, fm3};
   if (net->fold_dirty) {   // BN parameters / moving statistics changed by a training step: refold for inference
-    for (auto& L : net->layers) {
-      if (!L.info.has_bn) continue;
-      int rc = yb_bn_fold(reinterpret_cast<const float*>(net->par + L.gamma), reinterpret_cast<const float*>(net->par + L.beta),
-                          reinterpret_cast<const float*>(net->par + L.mean), reinterpret_cast<const float*>(net->par + L.var),
-                          L.info.cout, net->bn_eps, reinterpret_cast<float*>(net->par + L.scale),
-                          reinterpret_cast<float*>(net->par + L.shift), stream);
-      if (rc) return rc;
-    }
-    net->fold_dirty = false;
+    int rc = yb_net_refold_bn(net, stream);
+    if (rc) return rc;
   }
-  static const bool thin = !(getenv("YB_THIN") && getenv("YB_THIN")[0] == '0');   // A/B switch for the thin-layer kernels
+  const bool thin = opt("YB_THIN")[0] != '0';   // A/B switch for the thin-layer kernels
   if (first == 0) {
     Layer& L = net->layers[0];
     int rc;
@@ -294,7 +301,7 @@ extern "C" int yb_net_forward_layers(yb_net* net, const float* images, float* fm
     Layer& L = net->layers[i];
     // (after the r01_j pipeline-loop fixes the tcgen05 kernel runs these two layers in ~455 us against ~500-550 us for
     //  the mma.sync halo kernel, so the latter is now opt-in: YB_THIN=2)
-    static const bool thin_cin32 = getenv("YB_THIN") && getenv("YB_THIN")[0] == '2';
+    const bool thin_cin32 = opt("YB_THIN")[0] == '2';
     if (thin_cin32 && L.info.ksize == 3 && L.info.cin == 32 && L.info.has_bn && !L.upsample) {
       // Cin = 32: 64-byte im2col rows halve the TMA line rate -> direct halo-tile kernel (csrc/conv_thin.cu)
       yb_conv_desc d;

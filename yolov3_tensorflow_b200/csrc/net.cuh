@@ -64,7 +64,9 @@ struct yb_net {
   size_t lossws_off = 0, lossws_bytes = 0;
   size_t bnws_off = 0, bnws_bytes = 0;     // two-stage BN-backward reduction scratch (zeroed at bind)
   size_t ones_off = 0, zeros_off = 0;      // fp32 [1024] constants (param arena)
-  size_t grad_off = 0, vel_off = 0; long grad_count = 0;   // flat fp32 gradient / velocity (param arena)
+  size_t grad_off = 0, vel_off = 0; long grad_count = 0;   // flat fp32 gradient / optimizer slots (param arena)
+  int opt_state_slots = 2;            // slot 1: momentum / adam m; slot 2: rmsprop mean square / adam v
+  size_t opt_step_off = 0;            // int ctrl[64]: non-finite flag, updates applied, steps skipped
   size_t opt_tensors_off = 0, opt_chunks_off = 0, opt_norm_off = 0; int num_opt_tensors = 0, num_opt_chunks = 0;
   std::vector<yb::OptTensor> opt_tensors;
   std::vector<yb::OptChunk> opt_chunks;

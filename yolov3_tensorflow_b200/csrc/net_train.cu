@@ -42,7 +42,7 @@ void train_layout(yb_net* net) {
       L.dz_ld = L.info.cout;
       // stride-2 layers: the input gradient is computed per parity class on the plain dz (4 small convs, no zeros);
       // YB_DGRAD_S2=dilated selects the first version (one 3x3 conv over a zero-inserted dz: 4x the MMA work)
-      const char* s2 = getenv("YB_DGRAD_S2");
+      const char* s2 = opt("YB_DGRAD_S2");
       L.dgrad_parity = (L.info.stride == 2 && !(s2 && s2[0] == 'd')) ? 1 : 0;
       L.dz_dilated = L.info.stride == 2 && !L.dgrad_parity;
       const size_t dz_rows = L.dz_dilated ? (size_t)net->n * L.info.in_h * L.info.in_w : out_rows;
@@ -100,13 +100,13 @@ void train_layout(yb_net* net) {
   }
   net->grad_count = g;
   net->grad_off = o; o = al256(o + (size_t)g * 4);
-  net->vel_off = o; o = al256(o + (size_t)g * 4);
+  net->vel_off = o; o = al256(o + (size_t)g * 4 * net->opt_state_slots);
   // optimizer tables
   net->opt_tensors.clear(); net->opt_chunks.clear();
   const long CH = 1 << 16;
   auto add = [&](long n, int l2) {
     OptTensor t; memset(&t, 0, sizeof(t));
-    t.n = n; t.l2 = l2;
+    t.n = n; t.l2 = l2; t.trainable = 1;
     const int id = (int)net->opt_tensors.size();
     net->opt_tensors.push_back(t);
     for (long b = 0; b < n; b += CH) { OptChunk c; c.tensor = id; c.begin = b; c.end = std::min(n, b + CH); net->opt_chunks.push_back(c); }
@@ -120,6 +120,7 @@ void train_layout(yb_net* net) {
   net->opt_tensors_off = o; o = al256(o + net->opt_tensors.size() * sizeof(OptTensor));
   net->opt_chunks_off = o; o = al256(o + net->opt_chunks.size() * sizeof(OptChunk));
   net->opt_norm_off = o; o = al256(o + net->opt_tensors.size() * 4);
+  net->opt_step_off = o; o = al256(o + 256);
   net->param_bytes = o;
 }
 
@@ -138,20 +139,20 @@ __global__ void fill_f32_kernel(float* p, long n, float v) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) p[i] = v;
 }
 
-// Called from yb_net_bind for training plans.
-int train_bind(yb_net* net) {
-  // constants, zero state
-  fill_f32_kernel<<<4, 256>>>(fpar(net, net->ones_off), 1024, 1.0f);
+// Called from yb_net_bind for training plans.  Everything is enqueued on the caller's stream.  The optimizer state
+// (velocity) lives in the parameter arena, which several plans of different shapes may share: binding never touches it —
+// yb_net_train_reset_state() zeroes it once, when the arena is created.
+int train_bind(yb_net* net, cudaStream_t st) {
+  // constants (idempotent) + this plan's activation-arena scratch
+  fill_f32_kernel<<<4, 256, 0, st>>>(fpar(net, net->ones_off), 1024, 1.0f);
   YB_CUDA(cudaGetLastError());
-  YB_CUDA(cudaMemset(net->par + net->zeros_off, 0, 1024 * 4));
-  YB_CUDA(cudaMemset(net->par + net->vel_off, 0, (size_t)net->grad_count * 4));
-  YB_CUDA(cudaMemset(net->par + net->grad_off, 0, (size_t)net->grad_count * 4));
-  YB_CUDA(cudaMemset(net->act + net->bnws_off, 0, net->bnws_bytes));
+  YB_CUDA(cudaMemsetAsync(net->par + net->zeros_off, 0, 1024 * 4, st));
+  YB_CUDA(cudaMemsetAsync(net->act + net->bnws_off, 0, net->bnws_bytes, st));
   const float* ones = fpar(net, net->ones_off);
   const float* zeros = fpar(net, net->zeros_off);
   for (auto& L : net->layers) {
     if (L.dz_dilated)
-      YB_CUDA(cudaMemset(net->act + L.dz_off, 0, (size_t)net->n * L.info.in_h * L.info.in_w * L.dz_ld * 2));
+      YB_CUDA(cudaMemsetAsync(net->act + L.dz_off, 0, (size_t)net->n * L.info.in_h * L.info.in_w * L.dz_ld * 2, st));
   }
   // ---- training-mode forward convs: raw z + statistics ----
   for (size_t i = 1; i < net->layers.size(); ++i) {
@@ -215,24 +216,26 @@ int train_bind(yb_net* net) {
     size_t ti = 0;
     float* gbase = reinterpret_cast<float*>(net->par + net->grad_off);
     float* vbase = reinterpret_cast<float*>(net->par + net->vel_off);
+    float* v2base = vbase + net->grad_count;
     for (auto& L : net->layers) {
       OptTensor& tw = net->opt_tensors[ti++];
-      tw.w = fpar(net, L.w_master); tw.g = gbase + L.g_w; tw.v = vbase + L.g_w; tw.w16 = net->par + L.w_packed;
+      tw.w = fpar(net, L.w_master); tw.g = gbase + L.g_w; tw.v = vbase + L.g_w; tw.v2 = v2base + L.g_w; tw.w16 = net->par + L.w_packed;
       if (L.info.index == 0) tw.w16 = nullptr;     // the stem reads its fp32 master weights
       if (L.info.has_bn) {
         OptTensor& tg = net->opt_tensors[ti++];
-        tg.w = fpar(net, L.gamma); tg.g = gbase + L.g_gamma; tg.v = vbase + L.g_gamma; tg.w16 = nullptr;
+        tg.w = fpar(net, L.gamma); tg.g = gbase + L.g_gamma; tg.v = vbase + L.g_gamma; tg.v2 = v2base + L.g_gamma; tg.w16 = nullptr;
         OptTensor& tb = net->opt_tensors[ti++];
-        tb.w = fpar(net, L.beta); tb.g = gbase + L.g_beta; tb.v = vbase + L.g_beta; tb.w16 = nullptr;
+        tb.w = fpar(net, L.beta); tb.g = gbase + L.g_beta; tb.v = vbase + L.g_beta; tb.v2 = v2base + L.g_beta; tb.w16 = nullptr;
       } else {
         OptTensor& tb = net->opt_tensors[ti++];
-        tb.w = fpar(net, L.bias); tb.g = gbase + L.g_bias; tb.v = vbase + L.g_bias; tb.w16 = nullptr;
+        tb.w = fpar(net, L.bias); tb.g = gbase + L.g_bias; tb.v = vbase + L.g_bias; tb.v2 = v2base + L.g_bias; tb.w16 = nullptr;
       }
     }
-    YB_CUDA(cudaMemcpy(net->par + net->opt_tensors_off, net->opt_tensors.data(), net->opt_tensors.size() * sizeof(OptTensor),
-                       cudaMemcpyHostToDevice));
-    YB_CUDA(cudaMemcpy(net->par + net->opt_chunks_off, net->opt_chunks.data(), net->opt_chunks.size() * sizeof(OptChunk),
-                       cudaMemcpyHostToDevice));
+    // (pageable host source: the copies are staged before the calls return; the vectors live as long as the plan)
+    YB_CUDA(cudaMemcpyAsync(net->par + net->opt_tensors_off, net->opt_tensors.data(), net->opt_tensors.size() * sizeof(OptTensor),
+                            cudaMemcpyHostToDevice, st));
+    YB_CUDA(cudaMemcpyAsync(net->par + net->opt_chunks_off, net->opt_chunks.data(), net->opt_chunks.size() * sizeof(OptChunk),
+                            cudaMemcpyHostToDevice, st));
   }
   return YB_OK;
 }
@@ -254,8 +257,10 @@ using namespace yb;
 
 extern "C" int yb_net_train_fwd_bwd(yb_net* net, const float* images, const float* y_true_1, const float* y_true_2,
                                     const float* y_true_3, const float* anchors9x2, int use_label_smooth,
-                                    int use_focal_loss, float bn_decay, float* fm1, float* fm2, float* fm3,
-                                    double* loss4, int forward_only, void* stream) {
+                                    int use_focal_loss, float bn_decay, float loss_scale, float* fm1, float* fm2,
+                                    float* fm3, double* loss4, int flags, void* stream) {
+  const int forward_only = flags & YB_TRAIN_FORWARD_ONLY;
+  const bool bn_frozen = (flags & YB_TRAIN_BN_FROZEN) != 0;
   YB_REQUIRE(net && net->training && net->act && net->par, "train_fwd_bwd: not a bound training plan");
   YB_REQUIRE(images, "train_fwd_bwd: null images");
   YB_REQUIRE(forward_only || (y_true_1 && y_true_2 && y_true_3 && anchors9x2 && loss4), "train_fwd_bwd: null pointer");
@@ -293,7 +298,8 @@ extern "C" int yb_net_train_fwd_bwd(yb_net* net, const float* images, const floa
       if (rc) return rc;
     }
     if (L.info.has_bn) {
-      rc = yb_bn_finalize(fact(net, L.st_sum), fact(net, L.st_sqsum), rows, L.info.cout, fpar(net, L.gamma), fpar(net, L.beta),
+      rc = yb_bn_finalize(bn_frozen ? nullptr : fact(net, L.st_sum), bn_frozen ? nullptr : fact(net, L.st_sqsum), rows,
+                          L.info.cout, fpar(net, L.gamma), fpar(net, L.beta),
                           net->bn_eps, bn_decay, fpar(net, L.mean), fpar(net, L.var), fact(net, L.st_scale),
                           fact(net, L.st_shift), fact(net, L.st_mean), fact(net, L.st_invstd), stream);
       if (rc) return rc;
@@ -304,13 +310,13 @@ extern "C" int yb_net_train_fwd_bwd(yb_net* net, const float* images, const floa
       if (rc) return rc;
     }
   }
-  net->fold_dirty = true;
+  if (!bn_frozen) net->fold_dirty = true;
   if (forward_only) return YB_OK;
   // ------------------------------------------------ loss + d(loss)/d(feature maps)
   for (int s = 0; s < 3; ++s) {
     const int div = 32 >> s;
     rc = yb_loss_layer(fm_ptr[s], y_true[s], n, net->h / div, net->w / div, net->h, net->w, net->class_num,
-                       anchors9x2 + 2 * 3 * (2 - s), use_label_smooth, use_focal_loss, 1.0f / (float)n,
+                       anchors9x2 + 2 * 3 * (2 - s), use_label_smooth, use_focal_loss, 1.0f / (float)n, loss_scale,
                        net->act + net->lossws_off, net->lossws_bytes, loss4, net->act + net->dfm_off[s], dt,
                        (3 * (5 + net->class_num) + 31) / 32 * 32, stream);
     if (rc) return rc;
@@ -328,8 +334,10 @@ extern "C" int yb_net_train_fwd_bwd(yb_net* net, const float* images, const floa
                             fact(net, L.st_mean), fact(net, L.st_invstd), n, L.info.out_h, L.info.out_w, L.info.cout, dt, 1,
                             L.upsample ? 1 : 0, dgamma, dbeta, net->act + net->bnws_off, stream);
       if (rc) return rc;
+      // frozen BN: mean / variance are constants -> dz = gamma * invstd * dact (the batch-statistic terms vanish)
       rc = yb_bn_bwd_apply(dA, dA_ld, net->act + L.z_off, L.info.cout, fpar(net, L.gamma), fact(net, L.st_scale),
-                           fact(net, L.st_shift), fact(net, L.st_mean), fact(net, L.st_invstd), dgamma, dbeta, n,
+                           fact(net, L.st_shift), fact(net, L.st_mean), fact(net, L.st_invstd), bn_frozen ? zeros : dgamma,
+                           bn_frozen ? zeros : dbeta, n,
                            L.info.out_h, L.info.out_w, L.info.cout, dt, 1, L.upsample ? 1 : 0, L.dz_dilated,
                            net->act + L.dz_off, L.dz_ld, stream);
       if (rc) return rc;
@@ -360,6 +368,50 @@ extern "C" int yb_net_train_fwd_bwd(yb_net* net, const float* images, const floa
   return YB_OK;
 }
 
+extern "C" int yb_net_train_reset_state(yb_net* net, int optimizer_kind, void* stream) {
+  YB_REQUIRE(net && net->training && net->par, "train_reset_state: not a bound training plan");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  YB_CUDA(cudaMemsetAsync(net->par + net->vel_off, 0, (size_t)net->grad_count * 4 * net->opt_state_slots, st));
+  if (optimizer_kind == YB_OPT_RMSPROP) {       // [TF] RMSPropOptimizer creates its `rms` slot with ones
+    fill_f32_kernel<<<num_sms() * 4, 256, 0, st>>>(reinterpret_cast<float*>(net->par + net->vel_off) + net->grad_count,
+                                                   net->grad_count, 1.0f);
+    YB_CUDA(cudaGetLastError());
+  }
+  YB_CUDA(cudaMemsetAsync(net->par + net->grad_off, 0, (size_t)net->grad_count * 4, st));
+  YB_CUDA(cudaMemsetAsync(net->par + net->opt_step_off, 0, 256, st));
+  return YB_OK;
+}
+
+extern "C" int yb_net_opt_state(yb_net* net, float** slots, size_t* count_per_slot, int* num_slots, int** ctrl) {
+  YB_REQUIRE(net && net->training && net->par, "opt_state: not a bound training plan");
+  if (slots) *slots = reinterpret_cast<float*>(net->par + net->vel_off);
+  if (count_per_slot) *count_per_slot = (size_t)net->grad_count;
+  if (num_slots) *num_slots = net->opt_state_slots;
+  if (ctrl) *ctrl = reinterpret_cast<int*>(net->par + net->opt_step_off);
+  return YB_OK;
+}
+
+// train.py:81 `update_part`: restrict the update to some convs (their weights, gamma/beta or bias)
+extern "C" int yb_net_set_trainable(yb_net* net, int layer, int trainable, void* stream) {
+  YB_REQUIRE(net && net->training && net->par && layer >= 0 && layer < (int)net->layers.size(), "set_trainable: bad argument");
+  size_t ti = 0;
+  for (int i = 0; i < layer; ++i) ti += net->layers[i].info.has_bn ? 3 : 2;
+  const int cnt = net->layers[layer].info.has_bn ? 3 : 2;
+  for (int j = 0; j < cnt; ++j) net->opt_tensors[ti + j].trainable = trainable ? 1 : 0;
+  YB_CUDA(cudaMemcpyAsync(net->par + net->opt_tensors_off + ti * sizeof(OptTensor), &net->opt_tensors[ti], cnt * sizeof(OptTensor),
+                          cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+  return YB_OK;
+}
+
+extern "C" int yb_net_train_refresh_dgrad(yb_net* net, void* stream) {
+  YB_REQUIRE(net && net->training && net->par, "train_refresh_dgrad: not a bound training plan");
+  for (size_t i = 1; i < net->layers.size(); ++i) {
+    int rc = train_refresh_dgrad_weights(net, (int)i, stream);
+    if (rc) return rc;
+  }
+  return YB_OK;
+}
+
 extern "C" int yb_net_grad_buffer(yb_net* net, float** ptr, size_t* count) {
   YB_REQUIRE(net && net->training && net->par && ptr && count, "grad_buffer: not a bound training plan");
   *ptr = reinterpret_cast<float*>(net->par + net->grad_off);
@@ -367,14 +419,13 @@ extern "C" int yb_net_grad_buffer(yb_net* net, float** ptr, size_t* count) {
   return YB_OK;
 }
 
-extern "C" int yb_net_train_update(yb_net* net, float lr, float grad_scale, float momentum, float weight_decay,
-                                   float clip_norm, void* stream) {
-  YB_REQUIRE(net && net->training && net->par, "train_update: not a bound training plan");
+extern "C" int yb_net_train_update(yb_net* net, const yb_optimizer* opt, void* stream) {
+  YB_REQUIRE(net && net->training && net->par && opt, "train_update: not a bound training plan");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = opt_step(reinterpret_cast<const OptTensor*>(net->par + net->opt_tensors_off),
                     reinterpret_cast<const OptChunk*>(net->par + net->opt_chunks_off), net->num_opt_tensors,
-                    net->num_opt_chunks, fpar(net, net->opt_norm_off), net->dtype, lr, grad_scale, momentum, weight_decay,
-                    clip_norm, st);
+                    net->num_opt_chunks, fpar(net, net->opt_norm_off), reinterpret_cast<int*>(net->par + net->opt_step_off),
+                    net->dtype, *opt, st);
   if (rc) return rc;
   for (size_t i = 1; i < net->layers.size(); ++i) {
     rc = train_refresh_dgrad_weights(net, (int)i, stream);

@@ -1,7 +1,9 @@
-// Training-step tail (train.py:78,113-115; utils/misc_utils.py:151-153): L2 regulariser on the
-// conv weights (slim.l2_regularizer: grad += wd*w), per-tensor tf.clip_by_norm(g, clip), Momentum
-// (v = m*v + g ; w -= lr*v), plus the refresh of the 16-bit compute copy of every conv weight —
+// Training-step tail (train.py:78,113-115; utils/misc_utils.py:151-161): L2 regulariser on the
+// conv weights (slim.l2_regularizer: grad += wd*w), per-tensor tf.clip_by_norm(g, clip), then the
+// optimizer chosen by config_optimizer — momentum (the default), rmsprop, adam or sgd with
+// TensorFlow 1.x's update rules — plus the refresh of the 16-bit compute copy of every conv weight:
 // all 222 trainable tensors in two multi-tensor launches driven by a device-side chunk table.
+// A step whose gradient contains a non-finite value (fp16 storage with loss scaling) is skipped as a whole.
 #include "common.cuh"
 #include "optim.cuh"
 
@@ -9,11 +11,12 @@ namespace yb {
 
 __global__ void __launch_bounds__(256)
 opt_norm_kernel(const OptTensor* __restrict__ tensors, const OptChunk* __restrict__ chunks, int num_chunks,
-                float grad_scale, float weight_decay, float* __restrict__ sqnorm) {
+                float grad_scale, float weight_decay, float* __restrict__ sqnorm, int* __restrict__ ctrl) {
   __shared__ float s_red[8];
   for (int ci = blockIdx.x; ci < num_chunks; ci += gridDim.x) {
     const OptChunk ch = chunks[ci];
     const OptTensor t = tensors[ch.tensor];
+    if (!t.trainable) continue;
     const float wd = t.l2 ? weight_decay : 0.f;
     float acc = 0.f;
     for (long i = ch.begin + threadIdx.x; i < ch.end; i += 256) {
@@ -27,48 +30,83 @@ opt_norm_kernel(const OptTensor* __restrict__ tensors, const OptChunk* __restric
     if (threadIdx.x == 0) {
       float s = 0.f;
       for (int w = 0; w < 8; ++w) s += s_red[w];
+      if (!isfinite(s)) atomicOr(ctrl, 1);
       atomicAdd(sqnorm + ch.tensor, s);
     }
     __syncthreads();
   }
 }
 
-template <typename T>
+template <typename T, int KIND>
 __global__ void __launch_bounds__(256)
 opt_update_kernel(const OptTensor* __restrict__ tensors, const OptChunk* __restrict__ chunks, int num_chunks,
-                  float grad_scale, float weight_decay, float clip, float momentum, float lr,
-                  const float* __restrict__ sqnorm) {
+                  const yb_optimizer o, const float* __restrict__ sqnorm, const int* __restrict__ ctrl) {
+  if (ctrl[0]) return;                                                      // non-finite gradient: skip the step
+  float lr = o.lr;
+  if (KIND == YB_OPT_ADAM) {                                                // [TF] AdamOptimizer: lr_t = lr*sqrt(1-b2^t)/(1-b1^t)
+    const float t = (float)(ctrl[1] + 1);
+    lr = o.lr * sqrtf(1.f - powf(o.beta2, t)) / (1.f - powf(o.beta1, t));
+  }
   for (int ci = blockIdx.x; ci < num_chunks; ci += gridDim.x) {
     const OptChunk ch = chunks[ci];
     const OptTensor t = tensors[ch.tensor];
-    const float wd = t.l2 ? weight_decay : 0.f;
+    if (!t.trainable) continue;
+    const float wd = t.l2 ? o.weight_decay : 0.f;
     const float nrm = sqrtf(sqnorm[ch.tensor]);
-    const float cs = clip > 0.f ? clip / fmaxf(nrm, clip) : 1.f;        // tf.clip_by_norm
+    const float cs = o.clip_norm > 0.f ? o.clip_norm / fmaxf(nrm, o.clip_norm) : 1.f;   // tf.clip_by_norm
     T* w16 = static_cast<T*>(t.w16);
     for (long i = ch.begin + threadIdx.x; i < ch.end; i += 256) {
       const float w = t.w[i];
-      const float g = (t.g[i] * grad_scale + wd * w) * cs;
-      const float v = momentum * t.v[i] + g;                              // [TF] MomentumOptimizer, no Nesterov
-      const float nw = w - lr * v;
-      t.v[i] = v;
+      const float g = (t.g[i] * o.grad_scale + wd * w) * cs;
+      float nw;
+      if (KIND == YB_OPT_SGD) {                                             // [TF] GradientDescentOptimizer
+        nw = w - lr * g;
+      } else if (KIND == YB_OPT_MOMENTUM) {                                 // [TF] MomentumOptimizer, no Nesterov
+        const float v = o.momentum * t.v[i] + g;
+        t.v[i] = v;
+        nw = w - lr * v;
+      } else if (KIND == YB_OPT_RMSPROP) {                                  // [TF] RMSPropOptimizer (not centered)
+        const float ms = o.decay * t.v2[i] + (1.f - o.decay) * g * g;
+        const float mom = o.momentum * t.v[i] + lr * g * rsqrtf(ms + o.epsilon);
+        t.v2[i] = ms;
+        t.v[i] = mom;
+        nw = w - mom;
+      } else {                                                              // [TF] AdamOptimizer
+        const float m = o.beta1 * t.v[i] + (1.f - o.beta1) * g;
+        const float v = o.beta2 * t.v2[i] + (1.f - o.beta2) * g * g;
+        t.v[i] = m;
+        t.v2[i] = v;
+        nw = w - lr * m / (sqrtf(v) + o.epsilon);
+      }
       t.w[i] = nw;
       if (w16) w16[i] = static_cast<T>(nw);
     }
   }
 }
 
-int opt_step(const OptTensor* tensors, const OptChunk* chunks, int num_tensors, int num_chunks, float* sqnorm,
-             int dtype, float lr, float grad_scale, float momentum, float weight_decay, float clip, cudaStream_t st) {
+__global__ void opt_finish_kernel(int* ctrl) {
+  if (ctrl[0]) ctrl[2] += 1; else ctrl[1] += 1;
+  ctrl[0] = 0;
+}
+
+int opt_step(const OptTensor* tensors, const OptChunk* chunks, int num_tensors, int num_chunks, float* sqnorm, int* ctrl,
+             int dtype, const yb_optimizer& o, cudaStream_t st) {
+  YB_REQUIRE(o.kind >= YB_OPT_SGD && o.kind <= YB_OPT_ADAM, "optimizer: unsupported kind %d (utils/misc_utils.py:151-161)", o.kind);
   YB_CUDA(cudaMemsetAsync(sqnorm, 0, sizeof(float) * num_tensors, st));
   const int grid = num_chunks < num_sms() * 8 ? num_chunks : num_sms() * 8;
-  opt_norm_kernel<<<grid, 256, 0, st>>>(tensors, chunks, num_chunks, grad_scale, weight_decay, sqnorm);
+  opt_norm_kernel<<<grid, 256, 0, st>>>(tensors, chunks, num_chunks, o.grad_scale, o.weight_decay, sqnorm, ctrl);
   YB_CUDA(cudaGetLastError());
-  if (dtype == YB_BF16)
-    opt_update_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(tensors, chunks, num_chunks, grad_scale, weight_decay, clip,
-                                                          momentum, lr, sqnorm);
-  else
-    opt_update_kernel<__half><<<grid, 256, 0, st>>>(tensors, chunks, num_chunks, grad_scale, weight_decay, clip,
-                                                   momentum, lr, sqnorm);
+#define YB_OPT_LAUNCH(T)                                                                                         \
+  switch (o.kind) {                                                                                              \
+    case YB_OPT_SGD: opt_update_kernel<T, YB_OPT_SGD><<<grid, 256, 0, st>>>(tensors, chunks, num_chunks, o, sqnorm, ctrl); break;           \
+    case YB_OPT_MOMENTUM: opt_update_kernel<T, YB_OPT_MOMENTUM><<<grid, 256, 0, st>>>(tensors, chunks, num_chunks, o, sqnorm, ctrl); break; \
+    case YB_OPT_RMSPROP: opt_update_kernel<T, YB_OPT_RMSPROP><<<grid, 256, 0, st>>>(tensors, chunks, num_chunks, o, sqnorm, ctrl); break;   \
+    default: opt_update_kernel<T, YB_OPT_ADAM><<<grid, 256, 0, st>>>(tensors, chunks, num_chunks, o, sqnorm, ctrl); break;                  \
+  }
+  if (dtype == YB_BF16) { YB_OPT_LAUNCH(__nv_bfloat16) } else { YB_OPT_LAUNCH(__half) }
+#undef YB_OPT_LAUNCH
+  YB_CUDA(cudaGetLastError());
+  opt_finish_kernel<<<1, 1, 0, st>>>(ctrl);
   YB_CUDA(cudaGetLastError());
   return YB_OK;
 }

@@ -40,7 +40,12 @@ def _as_cuda_f32(x, device):
 
 
 class _Plan:
-    """One yb_net (fixed batch/H/W) plus the arenas it is bound to."""
+    """One yb_net (fixed batch/H/W): its own activation arena, bound to the MODEL's parameter arena.
+
+    The parameter-arena layout depends only on (class_num, dtype, training) (include/yolob200.h: yb_net_bind), so all
+    plans of a model share one arena: one set of master weights / 16-bit copies / folded BN and ONE optimizer state,
+    whatever batch size or resolution a step runs at (the reference's single MomentumOptimizer under
+    multi_scale_train, train.py:47-49)."""
 
     def __init__(self, model, n, h, w, training=False):
         self.n, self.h, self.w = n, h, w
@@ -50,13 +55,16 @@ class _Plan:
         check(lib.yb_net_create(C.byref(self.handle), model.class_num, n, h, w, model._dtype_code, int(training)), "yb_net_create")
         a, p = C.c_size_t(), C.c_size_t()
         check(lib.yb_net_arena_bytes(self.handle, C.byref(a), C.byref(p)), "yb_net_arena_bytes")
+        self.param_bytes = p.value
         dev = model.device
         self.act = torch.zeros(max(a.value, 256), dtype=torch.uint8, device=dev)
-        self.par = torch.zeros(max(p.value, 256), dtype=torch.uint8, device=dev)
-        check(lib.yb_net_bind(self.handle, ptr(self.act), self.act.numel(), ptr(self.par), self.par.numel()), "yb_net_bind")
-        self.param_version = -1
+        self.par = None
         self.num_layers = lib.yb_net_num_layers(self.handle)
         self.loss4 = torch.zeros(4, dtype=torch.float64, device=dev) if training else None
+
+    def bind(self, par):
+        self.par = par
+        check(lib.yb_net_bind(self.handle, ptr(self.act), self.act.numel(), ptr(par), par.numel(), stream_handle()), "yb_net_bind")
 
     def _view(self, p, shape, dtype=torch.float32):
         """torch view of `shape` floats at device pointer p inside the parameter arena."""
@@ -151,10 +159,15 @@ class yolov3(object):
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.img_size = None
         self._plans = {}
-        self._params = None          # list of 75 dicts of CUDA float32 tensors
-        self._param_layout = _lib.YB_W_HWIO
-        self._param_version = 0
-        self._trained_plan = None    # plan whose master weights are newer than self._params (after train_step)
+        self._pending = None         # user-supplied parameters not yet uploaded into the arena (75 dicts of CUDA tensors)
+        self._pending_layout = _lib.YB_W_HWIO
+        self._arena = None           # THE parameter arena (uint8 CUDA tensor), shared by every plan of this model
+        self._arena_training = False
+        self._have_params = False
+        self._fold_dirty = False     # BN parameters / moving statistics changed since the inference scale/shift were folded
+        self._opt_kind = None        # optimizer whose slots the arena currently holds
+        self._frozen = set()         # conv indices excluded from the update (train.py:81 update_part)
+        self.loss_scale = 1024.0 if self._torch_dtype == torch.float16 else 1.0   # static loss scale of the 16-bit backward
 
     # ------------------------------------------------------------------ parameters
     @staticmethod
@@ -206,9 +219,8 @@ class yolov3(object):
                 if name not in q or q[name].numel() != cout:
                     raise ValueError(f"conv {i}: missing/ill-shaped '{name}'")
             out.append(q)
-        self._params = out
-        self._param_layout = _lib.YB_W_HWIO if layout == "HWIO" else _lib.YB_W_OIHW
-        self._param_version += 1
+        self._pending = out
+        self._pending_layout = _lib.YB_W_HWIO if layout == "HWIO" else _lib.YB_W_OIHW
 
     def init_params(self, seed=0):
         """Random init as the reference graph would: Glorot-uniform conv weights,
@@ -226,27 +238,71 @@ class yolov3(object):
             ps.append(p)
         self.set_params(ps, "HWIO")
 
+    def _ensure_arena(self, plan):
+        """Make sure the shared parameter arena exists and is large enough for `plan` (a training plan's layout is the
+        inference layout plus gradient / optimizer slots / dgrad weights appended), then bind the plan to it."""
+        need = max(plan.param_bytes, 256)
+        if self._arena is None or self._arena.numel() < need:
+            new = torch.zeros(need, dtype=torch.uint8, device=self.device)
+            if self._arena is not None:
+                new[: self._arena.numel()].copy_(self._arena)          # weights / BN state keep their offsets
+            self._arena = new
+            for other in self._plans.values():                         # tensor maps hold arena pointers: rebind
+                other.bind(self._arena)
+        plan.bind(self._arena)
+        if plan.training and not self._arena_training:
+            self._arena_training = True
+            self._opt_kind = None
+            if self._have_params:                                      # weights were uploaded through an inference plan
+                check(lib.yb_net_train_refresh_dgrad(plan.handle, stream_handle()), "yb_net_train_refresh_dgrad")
+        if plan.training:
+            for i in self._frozen:
+                check(lib.yb_net_set_trainable(plan.handle, i, 0, stream_handle()), "yb_net_set_trainable")
+
+    def _any_plan(self):
+        for pl in self._plans.values():
+            if not self._arena_training or pl.training:
+                return pl
+        return None
+
     def _plan(self, n, h, w, training=False):
         key = (n, h, w)
         plan = self._plans.get(key)
         if plan is not None and training and not plan.training:
-            plan = None                                  # upgrade an inference plan to a training plan
+            del self._plans[key]                         # upgrade an inference plan to a training plan
+            plan = None
         if plan is None:
-            self._sync_params_from_trained()
             plan = _Plan(self, n, h, w, training)
+            self._ensure_arena(plan)
             self._plans[key] = plan
-        if self._trained_plan is not None and plan is not self._trained_plan:
-            self._sync_params_from_trained()
-        if plan.param_version != self._param_version:
-            if self._params is None:
-                raise _lib.YoloB200Error("no parameters: call load_weights(model, file), set_params() or init_params()")
+        if self._pending is not None:
             st = stream_handle()
-            for i, q in enumerate(self._params):
-                check(lib.yb_net_set_conv_params(plan.handle, i, ptr(q["w"]), self._param_layout, ptr(q.get("gamma")),
+            up = plan if (plan.training or not self._arena_training) else self._any_plan()
+            for i, q in enumerate(self._pending):
+                check(lib.yb_net_set_conv_params(up.handle, i, ptr(q["w"]), self._pending_layout, ptr(q.get("gamma")),
                                                  ptr(q.get("beta")), ptr(q.get("mean")), ptr(q.get("var")),
                                                  ptr(q.get("b")), st), f"yb_net_set_conv_params[{i}]")
-            plan.param_version = self._param_version
+            torch.cuda.current_stream().synchronize()    # the staging tensors are released below
+            self._pending = None
+            self._have_params = True
+            self._fold_dirty = False
+        if not self._have_params:
+            raise _lib.YoloB200Error("no parameters: call load_weights(model, file), set_params() or init_params()")
         return plan
+
+    def set_trainable(self, conv_indices, trainable=True):
+        """train.py:81 `update_part`: conv indices (creation order, 0..74) whose weights / BN affine / bias the
+        optimizer updates (True) or leaves untouched (False).  The default trains all 222 tensors."""
+        for i in conv_indices:
+            if trainable:
+                self._frozen.discard(int(i))
+            else:
+                self._frozen.add(int(i))
+        for pl in self._plans.values():
+            if pl.training:
+                for i in conv_indices:
+                    check(lib.yb_net_set_trainable(pl.handle, int(i), int(bool(trainable)), stream_handle()), "yb_net_set_trainable")
+                break        # the table lives in the shared arena: one upload serves every plan
 
     # ------------------------------------------------------------------ model.py:30-80
     def forward(self, inputs, is_training=False, reuse=False):
@@ -265,10 +321,13 @@ class yolov3(object):
         if is_training:
             # BN uses batch statistics and the moving statistics are updated (UPDATE_OPS, train.py:108-109)
             check(lib.yb_net_train_fwd_bwd(plan.handle, ptr(x), None, None, None, None, 0, 0, float(self.batch_norm_decay),
-                                           ptr(fms[0]), ptr(fms[1]), ptr(fms[2]), None, 1, stream_handle()),
+                                           1.0, ptr(fms[0]), ptr(fms[1]), ptr(fms[2]), None, 1, stream_handle()),
                   "yb_net_train_fwd_bwd(forward_only)")
-            self._trained_plan = plan
+            self._fold_dirty = True                      # moving statistics changed
         else:
+            if self._fold_dirty:                         # another plan trained on the shared arena: refold BN
+                check(lib.yb_net_refold_bn(plan.handle, stream_handle()), "yb_net_refold_bn")
+                self._fold_dirty = False
             check(lib.yb_net_forward(plan.handle, ptr(x), ptr(fms[0]), ptr(fms[1]), ptr(fms[2]), stream_handle()),
                   "yb_net_forward")
         self._last_plan = plan
@@ -358,7 +417,7 @@ class yolov3(object):
         anchors = np.asarray(anchors, np.float32).reshape(3, 2)
         check(lib.yb_loss_layer(ptr(fm), ptr(yt), n, gh, gw, self.img_size[0], self.img_size[1], C_,
                                 _lib.fptr(anchors.reshape(-1)), int(self.use_label_smooth), int(self.use_focal_loss),
-                                1.0 / n, ptr(ws), ws.numel(), ptr(loss4), ptr(grad), _lib.YB_F32, 0, stream_handle()),
+                                1.0 / n, 1.0, ptr(ws), ws.numel(), ptr(loss4), ptr(grad), _lib.YB_F32, 0, stream_handle()),
               "yb_loss_layer")
         return grad
 
@@ -395,44 +454,55 @@ class yolov3(object):
         return (losses, grads) if return_grads else losses
 
     # ------------------------------------------------------------------ train.py:105-115
-    def _sync_params_from_trained(self):
-        """After training steps the newest parameters live in the training plan's arena; pull them back
-        (device copies) before another plan is created or refreshed."""
-        plan = self._trained_plan
-        if plan is None:
-            return
-        out = []
-        for i in range(plan.num_layers):
-            q = {k: v.clone() for k, v in plan.conv_params(i).items()}
-            out.append(q)
-        self._params = out
-        self._param_layout = _lib.YB_W_OHWI
-        self._param_version += 1
-        plan.param_version = self._param_version      # its arena already holds these values
-        self._trained_plan = None
-
     def get_params(self):
         """Current parameters as 75 dicts of numpy arrays, weights in TF's HWIO layout."""
-        self._sync_params_from_trained()
-        if self._params is None:
+        if self._pending is not None:
+            out = []
+            for q in self._pending:
+                d = {k: v.detach().cpu().numpy() for k, v in q.items()}
+                if self._pending_layout == _lib.YB_W_OIHW:
+                    d["w"] = np.ascontiguousarray(np.transpose(d["w"], (2, 3, 1, 0)))
+                elif self._pending_layout == _lib.YB_W_OHWI:
+                    d["w"] = np.ascontiguousarray(np.transpose(d["w"], (1, 2, 3, 0)))
+                out.append(d)
+            return out
+        plan = self._any_plan()
+        if plan is None or not self._have_params:
             raise _lib.YoloB200Error("no parameters")
         out = []
-        for q in self._params:
-            d = {k: v.detach().cpu().numpy() for k, v in q.items()}
-            if self._param_layout == _lib.YB_W_OHWI:
-                d["w"] = np.ascontiguousarray(np.transpose(d["w"], (1, 2, 3, 0)))
-            elif self._param_layout == _lib.YB_W_OIHW:
-                d["w"] = np.ascontiguousarray(np.transpose(d["w"], (2, 3, 1, 0)))
+        for i in range(plan.num_layers):
+            d = {k: v.detach().cpu().numpy() for k, v in plan.conv_params(i).items()}
+            d["w"] = np.ascontiguousarray(np.transpose(d["w"], (1, 2, 3, 0)))      # arena OHWI -> HWIO
             out.append(d)
         return out
 
+    def optimizer_state(self):
+        """(slots [num_slots, count] float32 view, ctrl int32[3] view = [non-finite flag, updates applied, steps skipped])
+        of the shared optimizer state — what `save_optimizer=True` (args.py:37, train.py:101-104) checkpoints."""
+        plan = next((pl for pl in self._plans.values() if pl.training), None)
+        if plan is None:
+            raise _lib.YoloB200Error("optimizer_state: no training plan yet")
+        sl, cnt, ns, ctrl = C.c_void_p(), C.c_size_t(), C.c_int(), C.c_void_p()
+        check(lib.yb_net_opt_state(plan.handle, C.byref(sl), C.byref(cnt), C.byref(ns), C.byref(ctrl)), "yb_net_opt_state")
+        off = sl.value - self._arena.data_ptr()
+        slots = self._arena[off: off + ns.value * cnt.value * 4].view(torch.float32).view(ns.value, cnt.value)
+        coff = ctrl.value - self._arena.data_ptr()
+        return slots, self._arena[coff: coff + 12].view(torch.int32)
+
     def train_step(self, images, y_true, learning_rate, momentum=0.9, clip_norm=100.0, process_group=None,
-                   return_feature_maps=False, data_parallel=True):
+                   return_feature_maps=False, data_parallel=True, optimizer="momentum", decay=0.9, beta1=0.9,
+                   beta2=0.999, epsilon=None, freeze_bn=False):
         """One training step of the reference (train.py:105-115): forward(is_training=True) -> compute_loss ->
-        gradients of (loss[0] + l2_loss) w.r.t. all 222 trainable tensors -> per-tensor clip_by_norm(clip_norm)
-        -> Momentum(momentum) update; BN moving statistics updated with self.batch_norm_decay.
+        gradients of (loss[0] + l2_loss) w.r.t. the trainable tensors (all 222 unless set_trainable() restricted them,
+        train.py:81) -> per-tensor clip_by_norm(clip_norm) -> optimizer update; BN moving statistics updated with
+        self.batch_norm_decay.
 
         images float32 [N,H,W,3]; y_true = (y_true_13, y_true_26, y_true_52) in process_box format.
+        learning_rate: this step's value (utils.misc_utils.config_learning_rate / LearningRateSchedule evaluate the
+        reference's schedules on the host).  optimizer: 'momentum' (default), 'sgd', 'rmsprop', 'adam' or the object
+        returned by utils.misc_utils.config_optimizer (utils/misc_utils.py:151-161; TF1 update rules).
+        freeze_bn: BN layers normalise with their moving statistics and keep them (the graph the reference builds with
+        is_training=False, train.py:72): fine-tuning with frozen BN.
         Data parallel: when torch.distributed is initialised (or process_group is given) the flat gradient is
         all-reduced (NCCL over NVLink) and averaged over the ranks before the update; every loss term is a
         mean over the local batch (model.py:276-302), so this equals one big batch of world*N images.
@@ -447,23 +517,47 @@ class yolov3(object):
         for y, s in zip(ys, (32, 16, 8)):
             if tuple(y.shape) != (n, h // s, w // s, 3, 6 + C_):
                 raise ValueError(f"y_true shape {tuple(y.shape)} != {(n, h // s, w // s, 3, 6 + C_)}")
+        if hasattr(optimizer, "name"):                   # utils.misc_utils.config_optimizer(...) object
+            momentum, decay = getattr(optimizer, "momentum", momentum), getattr(optimizer, "decay", decay)
+            optimizer = optimizer.name
+        kinds = {"sgd": _lib.YB_OPT_SGD, "momentum": _lib.YB_OPT_MOMENTUM, "rmsprop": _lib.YB_OPT_RMSPROP, "adam": _lib.YB_OPT_ADAM}
+        if optimizer not in kinds:
+            raise ValueError("Unsupported optimizer type!")                 # utils/misc_utils.py:161
+        kind = kinds[optimizer]
+        if epsilon is None:
+            epsilon = 1e-10 if kind == _lib.YB_OPT_RMSPROP else 1e-8        # [TF] defaults
         self.img_size = (h, w)
         plan = self._plan(n, h, w, training=True)
+        st = stream_handle()
+        if self._opt_kind != kind:                                          # fresh arena or optimizer switch: new slots
+            check(lib.yb_net_train_reset_state(plan.handle, kind, st), "yb_net_train_reset_state")
+            self._opt_kind = kind
+            saved = getattr(self, "_restore_optimizer", None)               # utils.misc_utils.restore_checkpoint
+            if saved is not None and saved[2] == kind:
+                slots, ctrl = self.optimizer_state()
+                if tuple(slots.shape) != tuple(saved[0].shape):
+                    raise ValueError(f"optimizer slots in the checkpoint have shape {saved[0].shape}, expected {tuple(slots.shape)}")
+                slots.copy_(torch.from_numpy(saved[0]).to(self.device))
+                ctrl.copy_(torch.from_numpy(saved[1]).to(self.device))
+            self._restore_optimizer = None
         fms = [None, None, None]
         if return_feature_maps:
             fms = [torch.empty((n, h // s, w // s, 3 * (5 + C_)), dtype=torch.float32, device=self.device) for s in (32, 16, 8)]
-        st = stream_handle()
+        from .parallel import allreduce_gradients
+        use_dp = data_parallel and (process_group is not None or (dist.is_available() and dist.is_initialized()))
         check(lib.yb_net_train_fwd_bwd(plan.handle, ptr(x), ptr(ys[0]), ptr(ys[1]), ptr(ys[2]),
                                        _lib.fptr(self.anchors.reshape(-1)), int(self.use_label_smooth),
-                                       int(self.use_focal_loss), float(self.batch_norm_decay), ptr(fms[0]), ptr(fms[1]),
-                                       ptr(fms[2]), ptr(plan.loss4), 0, st), "yb_net_train_fwd_bwd")
-        from .parallel import allreduce_gradients
-        grad_scale = 1.0
-        if data_parallel and (process_group is not None or (dist.is_available() and dist.is_initialized())):
-            grad_scale = allreduce_gradients(plan.grad_flat(), process_group)   # one NCCL all-reduce per step
-        check(lib.yb_net_train_update(plan.handle, float(learning_rate), grad_scale, float(momentum),
-                                      float(self.weight_decay), float(clip_norm), st), "yb_net_train_update")
-        self._trained_plan = plan
+                                       int(self.use_focal_loss), float(self.batch_norm_decay), float(self.loss_scale),
+                                       ptr(fms[0]), ptr(fms[1]), ptr(fms[2]), ptr(plan.loss4),
+                                       _lib.YB_TRAIN_BN_FROZEN if freeze_bn else 0, st), "yb_net_train_fwd_bwd")
+        grad_scale = 1.0 / float(self.loss_scale)
+        if use_dp:
+            grad_scale *= allreduce_gradients(plan.grad_flat(), process_group)   # NCCL all-reduce (sum) -> 1/world
+        opt = _lib.Optimizer(kind=kind, lr=float(learning_rate), grad_scale=grad_scale, momentum=float(momentum),
+                             decay=float(decay), beta1=float(beta1), beta2=float(beta2), epsilon=float(epsilon),
+                             weight_decay=float(self.weight_decay), clip_norm=float(clip_norm))
+        check(lib.yb_net_train_update(plan.handle, C.byref(opt), st), "yb_net_train_update")
+        self._fold_dirty = True
         self._last_plan = plan
         out = torch.empty(5, dtype=torch.float32, device=self.device)
         check(lib.yb_loss_finalize(ptr(plan.loss4), ptr(out), st), "yb_loss_finalize")
