@@ -292,15 +292,13 @@ def latency_b1(pkg, S, iters=30):
     for i in range(iters + 5):
         a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
         a.record()
-        fms = model.forward(x, is_training=False)
-        boxes, scores = model.predict_scores(fms)
-        out = pkg.batched_gpu_nms(boxes, scores, CLASS_NUM, max_boxes=200, score_thresh=0.3, nms_thresh=0.45)
+        out = model.detect_raw(x, max_boxes=200, score_thresh=0.3, nms_thresh=0.45)
         b.record(); torch.cuda.synchronize()
         if i >= 5:
             ts.append(a.elapsed_time(b))
     ts.sort()
     return {"ms_median": ts[len(ts) // 2], "ms_min": ts[0], "images_per_s": 1e3 / ts[len(ts) // 2],
-            "what": "batch 1, %dx%d, forward + decode + NMS, device-resident input, 81 launches" % (S, S)}
+            "what": "batch 1, %dx%d, forward + decode + NMS (yb_net_detect), device-resident input, 77 launches" % (S, S)}
 
 
 def main():
@@ -363,6 +361,11 @@ def main():
     x_dev = x_host.cuda()
 
     def step_device():
+        # forward -> decode -> score -> per-image NMS in one engine call (decode + score filter fused into the
+        # detection-head epilogues; bit-identical to forward() + predict_scores() + batched_nms_raw(), tests/test_gpu_path.py)
+        return model.detect_raw(x_dev, **NMS_ARGS)[1:]
+
+    def step_device_unfused():
         fms = model.forward(x_dev)
         boxes, scores = model.predict_scores(fms)
         return batched_nms_raw(boxes, scores, CLASS_NUM, **NMS_ARGS)
@@ -390,10 +393,8 @@ def main():
         e2e_prefetch(i + 1)                                                    # next batch's copy overlaps this compute
         cur = torch.cuda.current_stream()
         cur.wait_event(h2d_done[i % 2])
-        fms = model.forward(x_bufs[i % 2])
+        _, ob, os_, ol, oi, cnt = model.detect_raw(x_bufs[i % 2], **NMS_ARGS)
         buf_free[i % 2].record(cur)
-        boxes, scores = model.predict_scores(fms)
-        ob, os_, ol, oi, cnt = batched_nms_raw(boxes, scores, CLASS_NUM, **NMS_ARGS)
         h_counts.copy_(cnt, non_blocking=True)                                 # D2H: K per image
         h_boxes.copy_(ob, non_blocking=True)                                   # D2H: detections (fixed-size, contiguous)
         h_scores.copy_(os_, non_blocking=True)
@@ -450,22 +451,32 @@ def main():
     e2e_ms = float(ms2)
 
     # ---------------- roofline: the tensor-core conv kernel, event-timed inside the step ----------------
-    plan = model._last_plan
-    D = 3 * (5 + CLASS_NUM)
-    fm = [torch.empty((B, S // s, S // s, D), dtype=torch.float32, device="cuda") for s in (32, 16, 8)]
-    st = _lib.stream_handle()
-    conv_ms, stem_ms = [], []
+    # the same step, its three parts bracketed by events: stem | 74 tcgen05 convs (decode fused into the heads) | NMS
+    conv_ms, stem_ms, nms_ms = [], [], []
+    res = model.detect_raw(x_dev, **NMS_ARGS)
     for i in range(args.steps + 2):
-        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a, b, c, d_ = (torch.cuda.Event(enable_timing=True) for _ in range(4))
         a.record()
-        _lib.check(_lib.lib.yb_net_forward_layers(plan.handle, _lib.ptr(x_dev), _lib.ptr(fm[0]), _lib.ptr(fm[1]), _lib.ptr(fm[2]), 0, 0, st), "stem")
+        model.detect_raw(x_dev, **NMS_ARGS, phases=1, out=res)
         b.record()
-        _lib.check(_lib.lib.yb_net_forward_layers(plan.handle, _lib.ptr(x_dev), _lib.ptr(fm[0]), _lib.ptr(fm[1]), _lib.ptr(fm[2]), 1, 74, st), "convs")
+        model.detect_raw(x_dev, **NMS_ARGS, phases=2, out=res)
         c.record()
+        model.detect_raw(x_dev, **NMS_ARGS, phases=4, out=res)
+        d_.record()
         torch.cuda.synchronize()
         if i >= 2:
-            stem_ms.append(a.elapsed_time(b)); conv_ms.append(b.elapsed_time(c))
+            stem_ms.append(a.elapsed_time(b)); conv_ms.append(b.elapsed_time(c)); nms_ms.append(c.elapsed_time(d_))
     conv_t = float(np.mean(conv_ms)) * 1e-3
+    # the reference-shaped three-call pipeline (forward -> predict -> gpu_nms with fp32 feature maps and scores in HBM)
+    for _ in range(3):
+        step_device_unfused()
+    u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    u0.record()
+    for _ in range(args.steps):
+        step_device_unfused()
+    u1.record()
+    torch.cuda.synchronize()
+    unfused_ms = u0.elapsed_time(u1) / args.steps
     scale = (S / 416.0) ** 2
     conv_flop = (FWD_GFLOP_416 - STEM_GFLOP_416) * scale * 1e9 * B
     pk = peaks()
@@ -481,6 +492,7 @@ def main():
                 "achieved": achieved,
                 "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": traffic,
                 "peak_source": pk["src"], "ms_per_step_conv": conv_t * 1e3, "ms_per_step_stem": float(np.mean(stem_ms)),
+                "ms_per_step_nms": float(np.mean(nms_ms)),
                 "algorithmic_flop_per_step": conv_flop}
 
     # ---------------- training steps (BASELINE.json configs[3] shape: batch 32/GPU @416 bf16; configs[2]: batch 32 @608) ----------------
@@ -540,9 +552,10 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": config,
             "e2e": {"value": imgs / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": args.steps * (1 + 74 + 1 + 3),
-            "launches_per_step": {"stem(mma.sync)": 1, "conv_igemm(tcgen05: 1-CTA + CTA-pair kernels)": 74, "predict": 1,
-                                  "nms": 3},
+            "gpu_launches": args.steps * (1 + 74 + 2),
+            "launches_per_step": {"stem(mma.sync)": 1, "conv_igemm(tcgen05: 1-CTA + CTA-pair kernels; decode + score filter in the 3 head epilogues)": 74,
+                                  "nms_select + nms_gather": 2},
+            "unfused_api_ms_per_step": unfused_ms,
             "detections_per_step": n_det, "clocks": clocks, "roofline": roofline,
             "fraction_of_conv_flop_roofline": (value / world) * FWD_GFLOP_416 * scale * 1e9 / (pk["tflops"] * 1e12)}
     if train is not None:

@@ -89,6 +89,9 @@ int yb_conv2d_fwd(const yb_conv_desc* d, const void* x, const void* w_packed, co
                   const float* shift, const void* res, void* out, float* stat_sum, float* stat_sqsum,
                   void* stream);
 int yb_conv_cout_pad(int cout);
+/* Profiling aid (tools/conv_trace.py): convs prepared after this call make CTA 0 stamp clock64 at its pipeline events
+ * into buf ([6 roles][64 tile iterations][32 slots] + 2 int64, device memory, caller-zeroed); NULL switches it off. */
+int yb_debug_set_conv_trace(long long* buf);
 
 /* First layer (darknet53_body/Conv, 3->32, 3x3 s1; utils/layer_utils.py:35): float32 NHWC image in,
  * `dtype` NHWC out.  w is OHWI float32 [32,3,3,3]. */
@@ -260,6 +263,29 @@ int yb_net_set_conv_params(yb_net* net, int layer, const float* w, int layout, c
 /* forward (model.py:30-80), inference mode: images float32 [n,h,w,3] -> fm1 [n,h/32,w/32,D],
  * fm2 [n,h/16,w/16,D], fm3 [n,h/8,w/8,D] float32, D = 3*(5+class_num). */
 int yb_net_forward(yb_net* net, const float* images, float* fm1, float* fm2, float* fm3, void* stream);
+/* The whole detection pipeline of test_single_image.py:50-57 in one call:
+ *   forward (model.py:30-80) -> predict (model.py:140-190) -> pred_scores = confs * probs (test_single_image.py:55)
+ *   -> gpu_nms per image (utils/nms_utils.py:8-48; max_boxes per class, score >= score_thresh, IoU > iou_thresh suppresses).
+ * The decode and the score filter run INSIDE the epilogues of the three detection-head convs (fp32 accumulators ->
+ * boxes + per-(image, class) candidate lists); the feature maps and the [n, B, C] score tensor are never written.
+ * Results are bit-identical to yb_net_forward + yb_predict + yb_nms.
+ *   anchors9x2 host float[18] (w,h pixels, small -> large);  boxes [n, B, 4] float32 out: every decoded box
+ *   (xmin,ymin,xmax,ymax), B = 3*(h/32*w/32 + h/16*w/16 + h/8*w/8);  workspace >= yb_net_detect_workspace_bytes;
+ *   out_* as yb_nms (fixed shape [n, class_num*max_boxes(,4)], out_counts [n]).
+ * yb_net_detect_supported: 1 when a fused kernel exists for the plan's class count (80 and 20), else 0 — callers
+ * then use the three separate calls. */
+int yb_net_detect_supported(const yb_net* net);
+int yb_net_detect_workspace_bytes(const yb_net* net, int max_boxes, size_t* bytes);
+int yb_net_detect(yb_net* net, const float* images, const float* anchors9x2, int max_boxes, float score_thresh,
+                  float iou_thresh, void* workspace, size_t workspace_bytes, float* boxes, float* out_boxes,
+                  float* out_scores, int32_t* out_labels, int32_t* out_indices, int32_t* out_counts, void* stream);
+/* yb_net_detect split for benchmarks that bracket its parts with their own events: phases is a bit mask,
+ * 1 = candidate-list reset + stem (layer 0), 2 = the 74 tensor-core convs (decode fused into the heads), 4 = NMS
+ * selection + gather.  yb_net_detect == phases 7. */
+int yb_net_detect_phases(yb_net* net, const float* images, const float* anchors9x2, int max_boxes, float score_thresh,
+                         float iou_thresh, void* workspace, size_t workspace_bytes, float* boxes, float* out_boxes,
+                         float* out_scores, int32_t* out_labels, int32_t* out_indices, int32_t* out_counts, int phases,
+                         void* stream);
 /* Same, restricted to layers [first, last] (creation order) — lets a benchmark bracket the CUDA-core stem
  * (layer 0) and the tensor-core convs (1..74) with its own events. */
 int yb_net_forward_layers(yb_net* net, const float* images, float* fm1, float* fm2, float* fm3, int first,

@@ -635,8 +635,8 @@ def train_step(x_nhwc, y_true, params, velocity, lr, anchors, class_num=80, use_
             q[k] = t
         tp.append(q)
     H, W = x_nhwc.shape[1:3]
-    fms, new_stats = forward(torch.tensor(x_nhwc, dtype=dtype), tp, class_num, not freeze_bn, emulate, bn_decay,
-                             dtype, as_torch=True)
+    out = forward(torch.tensor(x_nhwc, dtype=dtype), tp, class_num, not freeze_bn, emulate, bn_decay, dtype, as_torch=True)
+    fms, new_stats = (out, None) if freeze_bn else out       # forward() returns the moving statistics only when training
     losses = compute_loss(list(fms), y_true, anchors, (H, W), class_num, use_label_smooth, use_focal_loss)
     l2 = sum((q["w"] ** 2).sum() for q in tp) * (weight_decay / 2.0)        # train.py:78
     (losses[0] + l2).backward()                                              # train.py:112

@@ -54,6 +54,7 @@ _SIGS = {
     "yb_device_info": ([C.POINTER(i32)] * 3, i32),
     "yb_conv2d_fwd": ([C.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp], i32),
     "yb_conv_cout_pad": ([i32], i32),
+    "yb_debug_set_conv_trace": ([vp], i32),
     "yb_stem_conv_fwd": ([vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp], i32),
     "yb_conv3x3_thin_fwd": ([C.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp], i32),
     "yb_stem_conv_fwd_tc": ([vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp], i32),
@@ -89,6 +90,10 @@ _SIGS = {
     "yb_net_refold_bn": ([vp, vp], i32),
     "yb_net_set_conv_params": ([vp, i32, vp, i32, vp, vp, vp, vp, vp, vp], i32),
     "yb_net_forward": ([vp, vp, vp, vp, vp, vp], i32),
+    "yb_net_detect_supported": ([vp], i32),
+    "yb_net_detect_workspace_bytes": ([vp, i32, C.POINTER(sz)], i32),
+    "yb_net_detect": ([vp, vp, C.POINTER(f32), i32, f32, f32, vp, sz, vp, vp, vp, vp, vp, vp, vp], i32),
+    "yb_net_detect_phases": ([vp, vp, C.POINTER(f32), i32, f32, f32, vp, sz, vp, vp, vp, vp, vp, vp, i32, vp], i32),
     "yb_net_forward_layers": ([vp, vp, vp, vp, vp, i32, i32, vp], i32),
     "yb_net_train_fwd_bwd": ([vp, vp, vp, vp, vp, C.POINTER(f32), i32, i32, f32, f32, vp, vp, vp, vp, i32, vp], i32),
     "yb_net_grad_buffer": ([vp, C.POINTER(vp), C.POINTER(sz)], i32),

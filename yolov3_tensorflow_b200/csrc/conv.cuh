@@ -1,6 +1,7 @@
 // Shared between conv_igemm.cu (kernel + launcher) and net.cu (network plan).
 #pragma once
 #include "common.cuh"
+#include "decode.cuh"
 
 namespace yb {
 
@@ -30,6 +31,8 @@ struct ConvParams {
   int epi_tma;            // 1: 16-bit output tiles leave through shared memory + TMA stores (tmO), the residual comes in by TMA (tmR)
   CUtensorMap tmO;        // [M, cout] view of the output slice, box 32 rows x 32 channels, SWIZZLE_64B
   CUtensorMap tmR;        // same view of the residual
+  DetParams det;          // det.on: decode + NMS candidate filter instead of the fp32 feature-map store (detection heads)
+  long long* trace;       // debugging only (yb_debug_set_conv_trace): CTA 0 stamps clock64 at its pipeline events, else NULL
 };
 
 int conv_prepare(const yb_conv_desc* d, const void* x, const void* w_packed, const float* scale, const float* shift,
@@ -41,6 +44,8 @@ int conv_prepare(const yb_conv_desc* d, const void* x, const void* w_packed, con
 int conv_prepare_win(const yb_conv_desc* d, int kh, int kw, int scatter, const void* x, const void* w_packed,
                      const float* scale, const float* shift, const void* res, void* out, CUtensorMap* tmA,
                      CUtensorMap* tmB, ConvParams* p, int* cout_pad_out);
+int conv_prepare_det(const yb_conv_desc* d, int class_num, const void* x, const void* w_packed, const float* scale,
+                     const float* shift, CUtensorMap* tmA, CUtensorMap* tmB, ConvParams* p, int* cout_pad_out);
 int conv_launch(int dtype, int cout_pad, const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p,
                 cudaStream_t st);
 

@@ -54,6 +54,11 @@ struct Cfg {
   static constexpr uint32_t SBO = 8 * BK * 2;                  // bytes between 8-row groups
 };
 
+// debugging aid: CTA 0 stamps clock64 into p.trace[(role * 64 + tile iteration) * 32 + slot] (tools/conv_trace.py)
+__device__ __forceinline__ void trace_stamp(const ConvParams& p, int role, int it, int slot) {
+  if (p.trace != nullptr && blockIdx.x == 0 && it < 64) p.trace[(role * 64 + it) * 32 + slot] = clock64();
+}
+
 // tile index -> (m tile, n tile).  Inference walks n fastest (the A tile stays hot in L2 across its n tiles);
 // with BN statistics on, m runs fastest so a CTA's tiles share their n tile and its per-CTA column sums are
 // flushed to global at most num_n_tiles times.
@@ -76,9 +81,6 @@ __device__ __forceinline__ void stat_flush(const ConvParams& p, float* s_stat, i
   asm volatile("bar.sync 1, 128;" ::: "memory");
 }
 
-// One epilogue pass of a warp over its 32 accumulator rows x BN columns:
-// TMEM -> registers -> scale/shift (+leaky) (+residual) -> 16-bit / fp32 global stores
-// (channel-slice and 2x-upsample aware), optional BN batch statistics.
 // executed by the 128 epilogue threads together: (re)load the n-tile's scale/shift into shared memory
 template <int BN>
 __device__ __forceinline__ void load_scale_shift(const ConvParams& p, float* s_ss, int n0, int et /*0..127*/) {
@@ -90,12 +92,122 @@ __device__ __forceinline__ void load_scale_shift(const ConvParams& p, float* s_s
   asm volatile("bar.sync 1, 128;" ::: "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Epilogues.  One warp owns 32 accumulator rows (TMEM lanes) and walks the tile's columns in chunks of 32.
+// The chunk loop is ROLLED (two bodies, for the two TMEM read buffers): fully unrolled, the two epilogues of a
+// 256-wide tile were ~15 k SASS instructions of straight-line code executed once per tile, the kernel outgrew the
+// instruction cache (18 k instructions, 290 KB) and the epilogue warps spent most of their time in `no_inst` stalls —
+// 1100 cycles per chunk against a ~250-cycle TMEM-read floor (profiles/r02_b: ncu source page + in-kernel timeline).
+// ---------------------------------------------------------------------------------------------------------------
+
+// One chunk of the register-store epilogue: scale/shift (+leaky) (+residual) -> 16-bit / fp32 global stores
+// (channel-slice, 2x-upsample and parity-scatter aware), optional BN batch statistics.  `r` holds the chunk.
+template <typename T, int BN>
+__device__ __forceinline__ void epi_reg_chunk(const ConvParams& p, const uint32_t (&r)[32], const int ch, const int row,
+                                              const bool row_ok, const int n0, const long (&orow)[4], const int nrep,
+                                              const int lane, float* stage, float* s_stat, const float* s_ss) {
+  const int col0 = n0 + ch * 32;
+  if (p.stat_sum != nullptr) {
+    // BN batch statistics of the raw conv output.  Transpose the warp's 32x32 block through its staging
+    // tile so each lane sums ONE column over the 32 rows, then accumulate per-CTA column sums in shared
+    // memory; they are flushed to global once per (CTA, n-tile) by the caller (global atomics contend badly).
+#pragma unroll
+    for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = row_ok ? __uint_as_float(r[j]) : 0.f;
+    __syncwarp();
+    float cs = 0.f, cs2 = 0.f;
+#pragma unroll
+    for (int rr = 0; rr < 32; ++rr) {
+      const float t = stage[rr * 33 + lane];
+      cs += t;
+      cs2 = fmaf(t, t, cs2);
+    }
+    __syncwarp();
+    atomicAdd(&s_stat[ch * 32 + lane], cs);
+    atomicAdd(&s_stat[BN + ch * 32 + lane], cs2);
+  }
+  if (row_ok) {
+    float v[32];
+    const float4* sc4 = reinterpret_cast<const float4*>(s_ss + ch * 32);
+    const float4* sh4 = reinterpret_cast<const float4*>(s_ss + BN + ch * 32);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 sc = sc4[j];
+      const float4 sh = sh4[j];
+      v[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), sc.x, sh.x);
+      v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), sc.y, sh.y);
+      v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), sc.z, sh.z);
+      v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), sc.w, sh.w);
+    }
+    if (p.leaky) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.1f * v[j]);   // == v > 0 ? v : 0.1 v
+    }
+    if (p.res != nullptr) {
+      const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const T*>(p.res) +
+                                                       (p.scatter ? orow[0] : (long)row) * p.res_ld + col0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 u = __ldg(rp + j);
+        float2 f;
+        f = Pack2<T>::unpack(u.x); v[8 * j + 0] += f.x; v[8 * j + 1] += f.y;
+        f = Pack2<T>::unpack(u.y); v[8 * j + 2] += f.x; v[8 * j + 3] += f.y;
+        f = Pack2<T>::unpack(u.z); v[8 * j + 4] += f.x; v[8 * j + 5] += f.y;
+        f = Pack2<T>::unpack(u.w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
+      }
+    }
+    if (p.out_fp32) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = v[j];
+    } else {
+      uint4 pk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        pk[j].x = Pack2<T>::pack(v[8 * j + 0], v[8 * j + 1]);
+        pk[j].y = Pack2<T>::pack(v[8 * j + 2], v[8 * j + 3]);
+        pk[j].z = Pack2<T>::pack(v[8 * j + 4], v[8 * j + 5]);
+        pk[j].w = Pack2<T>::pack(v[8 * j + 6], v[8 * j + 7]);
+      }
+      for (int rep = 0; rep < nrep; ++rep) {
+        uint4* op = reinterpret_cast<uint4*>(static_cast<T*>(p.out) + orow[rep] * p.out_ld + col0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) op[j] = pk[j];
+      }
+    }
+  }
+  if (p.out_fp32) {
+    // detection heads (cout = 255, fp32): transpose through shared memory so that each store
+    // instruction writes one 128-byte row segment instead of 32 scattered words
+    __syncwarp();
+    const int row_base = row - lane;
+#pragma unroll 1
+    for (int rr = 0; rr < 32; ++rr) {
+      const int r2 = row_base + rr;
+      if (r2 >= p.M) break;
+      if (col0 + lane < p.cout) {
+        const float val = stage[rr * 33 + lane];
+        if (!p.upsample) {
+          static_cast<float*>(p.out)[(long)r2 * p.out_ld + col0 + lane] = val;
+        } else {
+          const int q = r2 % p.Q, pp = (r2 / p.Q) % p.P, img = r2 / (p.Q * p.P);
+          const long W2 = 2L * p.Q;
+          const long base = ((long)img * 2 * p.P + 2 * pp) * W2 + 2 * q;
+          float* o = static_cast<float*>(p.out) + col0 + lane;
+          o[base * p.out_ld] = val; o[(base + 1) * p.out_ld] = val;
+          o[(base + W2) * p.out_ld] = val; o[(base + W2 + 1) * p.out_ld] = val;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// Register-store epilogue of one warp over its 32 accumulator rows x BN columns (fp32 heads, 2x-upsample stores,
+// parity scatter, the multicast kernel).  The TMEM load of chunk c+1 is in flight while chunk c is processed.
 template <typename T, int BN>
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const int row, const int n0, const uint32_t t_row,
                                               const int lane, float* stage, float* s_stat, const float* s_ss) {
   const bool row_ok = row < p.M;
-  // output row(s)
-  long orow[4];
+  long orow[4] = {row, 0, 0, 0};
   int nrep = 1;
   if (p.upsample || p.scatter) {
     const int q = row % p.Q;
@@ -109,113 +221,21 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const int row
       orow[0] = base; orow[1] = base + 1; orow[2] = base + W2; orow[3] = base + W2 + 1;
       nrep = 4;
     }
-  } else {
-    orow[0] = row;
   }
-  // The TMEM load of chunk c+1 is in flight while chunk c is processed (TMEM reads run at 64 B/clk per SM: a
-  // 128x128 fp32 tile alone is 1024 cycles), and scale/shift come from shared memory: the first version waited for
-  // each chunk's tcgen05.ld and for 16 L2-latency loads per chunk, 3.2-3.7 us per 128x128 tile, which bounded every
-  // short-K layer (profiles/r01_j).
   constexpr int NCH = BN / 32;
-  uint32_t rbuf[2][32];
-  tmem_ld_32x32(t_row, rbuf[0]);
-#pragma unroll
-  for (int ch = 0; ch < NCH; ++ch) {
-    if (n0 + ch * 32 >= p.cout) break;   // zero-padded weight rows (cout_pad > cout): nothing to store
+  const int nvalid = min(NCH, (p.cout - n0 + 31) >> 5);      // zero-padded weight rows (cout_pad > cout): nothing to store
+  if (nvalid <= 0) return;
+  uint32_t ra[32], rb[32];
+  tmem_ld_32x32(t_row, ra);
+#pragma unroll 1
+  for (int ch = 0; ch < nvalid; ch += 2) {
     tmem_ld_wait();
-    uint32_t (&r)[32] = rbuf[ch & 1];
-    if (ch + 1 < NCH && n0 + (ch + 1) * 32 < p.cout) tmem_ld_32x32(t_row + (ch + 1) * 32, rbuf[(ch + 1) & 1]);
-    const int col0 = n0 + ch * 32;
-    if (p.stat_sum != nullptr) {
-      // BN batch statistics of the raw conv output.  Transpose the warp's 32x32 block through its staging
-      // tile so each lane sums ONE column over the 32 rows, then accumulate per-CTA column sums in shared
-      // memory; they are flushed to global once per (CTA, n-tile) by the caller (global atomics contend badly).
-#pragma unroll
-      for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = row_ok ? __uint_as_float(r[j]) : 0.f;
-      __syncwarp();
-      float cs = 0.f, cs2 = 0.f;
-#pragma unroll
-      for (int rr = 0; rr < 32; ++rr) {
-        const float t = stage[rr * 33 + lane];
-        cs += t;
-        cs2 = fmaf(t, t, cs2);
-      }
-      __syncwarp();
-      atomicAdd(&s_stat[ch * 32 + lane], cs);
-      atomicAdd(&s_stat[BN + ch * 32 + lane], cs2);
-    }
-    if (row_ok) {
-      float v[32];
-      const float4* sc4 = reinterpret_cast<const float4*>(s_ss + ch * 32);
-      const float4* sh4 = reinterpret_cast<const float4*>(s_ss + BN + ch * 32);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 sc = sc4[j];
-        const float4 sh = sh4[j];
-        v[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), sc.x, sh.x);
-        v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), sc.y, sh.y);
-        v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), sc.z, sh.z);
-        v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), sc.w, sh.w);
-      }
-      if (p.leaky) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.1f * v[j]);   // == v > 0 ? v : 0.1 v
-      }
-      if (p.res != nullptr) {
-        const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const T*>(p.res) +
-                                                         (p.scatter ? orow[0] : (long)row) * p.res_ld + col0);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint4 u = __ldg(rp + j);
-          float2 f;
-          f = Pack2<T>::unpack(u.x); v[8 * j + 0] += f.x; v[8 * j + 1] += f.y;
-          f = Pack2<T>::unpack(u.y); v[8 * j + 2] += f.x; v[8 * j + 3] += f.y;
-          f = Pack2<T>::unpack(u.z); v[8 * j + 4] += f.x; v[8 * j + 5] += f.y;
-          f = Pack2<T>::unpack(u.w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
-        }
-      }
-      if (p.out_fp32) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = v[j];
-      } else {
-        uint4 pk[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          pk[j].x = Pack2<T>::pack(v[8 * j + 0], v[8 * j + 1]);
-          pk[j].y = Pack2<T>::pack(v[8 * j + 2], v[8 * j + 3]);
-          pk[j].z = Pack2<T>::pack(v[8 * j + 4], v[8 * j + 5]);
-          pk[j].w = Pack2<T>::pack(v[8 * j + 6], v[8 * j + 7]);
-        }
-        for (int rep = 0; rep < nrep; ++rep) {
-          uint4* op = reinterpret_cast<uint4*>(static_cast<T*>(p.out) + orow[rep] * p.out_ld + col0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) op[j] = pk[j];
-        }
-      }
-    }
-    if (p.out_fp32) {
-      // detection heads (cout = 255, fp32): transpose through shared memory so that each store
-      // instruction writes one 128-byte row segment instead of 32 scattered words
-      __syncwarp();
-      const int row_base = row - lane;
-      for (int rr = 0; rr < 32; ++rr) {
-        const int r2 = row_base + rr;
-        if (r2 >= p.M) break;
-        if (col0 + lane < p.cout) {
-          const float val = stage[rr * 33 + lane];
-          if (!p.upsample) {
-            static_cast<float*>(p.out)[(long)r2 * p.out_ld + col0 + lane] = val;
-          } else {
-            const int q = r2 % p.Q, pp = (r2 / p.Q) % p.P, img = r2 / (p.Q * p.P);
-            const long W2 = 2L * p.Q;
-            const long base = ((long)img * 2 * p.P + 2 * pp) * W2 + 2 * q;
-            float* o = static_cast<float*>(p.out) + col0 + lane;
-            o[base * p.out_ld] = val; o[(base + 1) * p.out_ld] = val;
-            o[(base + W2) * p.out_ld] = val; o[(base + W2 + 1) * p.out_ld] = val;
-          }
-        }
-      }
-      __syncwarp();
+    if (ch + 1 < nvalid) tmem_ld_32x32(t_row + (ch + 1) * 32, rb);
+    epi_reg_chunk<T, BN>(p, ra, ch, row, row_ok, n0, orow, nrep, lane, stage, s_stat, s_ss);
+    if (ch + 1 < nvalid) {
+      tmem_ld_wait();
+      if (ch + 2 < nvalid) tmem_ld_32x32(t_row + (ch + 2) * 32, ra);
+      epi_reg_chunk<T, BN>(p, rb, ch + 1, row, row_ok, n0, orow, nrep, lane, stage, s_stat, s_ss);
     }
   }
 }
@@ -243,116 +263,253 @@ __device__ __forceinline__ float warp_col_sum32(float (&v)[32], const int lane) 
 //   TMEM -> registers -> scale/shift (+leaky) -> [+ residual tile, fetched by TMA into the same staging tile]
 //   -> 16-bit, written in place into the SWIZZLE_64B staging tile -> cp.async.bulk.tensor store (rows >= M clipped).
 // The first version stored straight from registers: one row per lane, so every 16-byte store instruction touched 32
-// different 128-byte lines (32 L1 wavefronts, half-written sectors) and the residual loads did the same; with loads and
-// MMAs disabled a 128x128 tile still took 3.2 us against a 0.55 us TMEM-read floor, which bounded every 1x1 layer and
-// the 52x52 3x3 layers (profiles/r01_j_conv_floor.txt).  Here the LSU only sees conflict-free
-// 16-byte shared-memory accesses; global traffic is full 64-byte row segments issued by the TMA unit.
+// different 128-byte lines (32 L1 wavefronts, half-written sectors) and the residual loads did the same.  Here the LSU
+// only sees conflict-free 16-byte shared-memory accesses; global traffic is full 64-byte row segments issued by the TMA.
 // Three staging tiles rotate per warp: while chunk c is processed, chunk c+1's residual is landing and chunk c-1's
 // store is draining.  `cnt` (chunks processed by this warp so far) indexes tiles and barrier phases across tiles.
+struct EpiTmaState {
+  uint8_t* stage;
+  uint64_t* res_bar;
+  uint32_t cnt;
+  bool prefetched;
+};
+
+template <typename T, int BN>
+__device__ __forceinline__ void epi_tma_chunk(const ConvParams& p, const uint32_t (&r)[32], const int ch, const int nvalid,
+                                              const int m0w, const int n0, const bool row_ok, const bool has_res,
+                                              const int lane, EpiTmaState& st, float* s_stat, const float* s_ss,
+                                              const bool has_next, const int next_m0w, const int next_n0,
+                                              const int tr_role, const int tr_it) {
+  const int sw = (lane >> 1) & 3;                // SWIZZLE_64B: 16-byte chunk j of row r sits at chunk j ^ ((r >> 1) & 3)
+  const uint32_t b = st.cnt % EPI_TILES;
+  uint8_t* buf = st.stage + b * EPI_TILE_BYTES;
+  if (has_res) {
+    // fetch the NEXT chunk's residual (this tile's, or the first of the next tile) into the tile freed two stores ago
+    const bool last = ch + 1 >= nvalid;
+    const int nm = last ? next_m0w : m0w;
+    const int nc = last ? next_n0 : n0 + (ch + 1) * 32;
+    const bool go = last ? (has_next && next_m0w < p.M) : true;
+    if (go && lane == 0) {
+      bulk_wait_group_read<1>();
+      const uint32_t nb = (st.cnt + 1) % EPI_TILES;
+      mbar_arrive_expect_tx(&st.res_bar[nb], EPI_TILE_BYTES);
+      tma_load_2d(st.stage + nb * EPI_TILE_BYTES, &p.tmR, &st.res_bar[nb], nc, nm);
+    }
+    if (last) st.prefetched = go;
+  }
+  if (p.stat_sum != nullptr) {
+    // BN batch statistics of the raw conv output: per-CTA column sums in shared memory, flushed by the caller
+    float a[32], q[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float t = row_ok ? __uint_as_float(r[j]) : 0.f;
+      a[j] = t;
+      q[j] = t * t;
+    }
+    const float cs = warp_col_sum32(a, lane);
+    const float cs2 = warp_col_sum32(q, lane);
+    atomicAdd(&s_stat[ch * 32 + lane], cs);
+    atomicAdd(&s_stat[BN + ch * 32 + lane], cs2);
+  }
+  float v[32];
+  const float4* sc4 = reinterpret_cast<const float4*>(s_ss + ch * 32);
+  const float4* sh4 = reinterpret_cast<const float4*>(s_ss + BN + ch * 32);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 sc = sc4[j];
+    const float4 sh = sh4[j];
+    v[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), sc.x, sh.x);
+    v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), sc.y, sh.y);
+    v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), sc.z, sh.z);
+    v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), sc.w, sh.w);
+  }
+  if (p.leaky) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.1f * v[j]);   // == v > 0 ? v : 0.1 v
+  }
+  uint4* rowp = reinterpret_cast<uint4*>(buf + lane * 64);
+  if (has_res) {
+    mbar_wait(&st.res_bar[b], (st.cnt / EPI_TILES) & 1);             // residual tile landed (async proxy -> visible)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 u = rowp[j ^ sw];
+      float2 f;
+      f = Pack2<T>::unpack(u.x); v[8 * j + 0] += f.x; v[8 * j + 1] += f.y;
+      f = Pack2<T>::unpack(u.y); v[8 * j + 2] += f.x; v[8 * j + 3] += f.y;
+      f = Pack2<T>::unpack(u.z); v[8 * j + 4] += f.x; v[8 * j + 5] += f.y;
+      f = Pack2<T>::unpack(u.w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
+    }
+  } else {                                       // the store that last read this tile (3 chunks ago) has drained
+    if (lane == 0) bulk_wait_group_read<EPI_TILES - 1>();
+    __syncwarp();
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 pk;
+    pk.x = Pack2<T>::pack(v[8 * j + 0], v[8 * j + 1]);
+    pk.y = Pack2<T>::pack(v[8 * j + 2], v[8 * j + 3]);
+    pk.z = Pack2<T>::pack(v[8 * j + 4], v[8 * j + 5]);
+    pk.w = Pack2<T>::pack(v[8 * j + 6], v[8 * j + 7]);
+    rowp[j ^ sw] = pk;
+  }
+  fence_proxy_async();                           // generic-proxy writes -> visible to the TMA (async proxy)
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(&p.tmO, buf, n0 + ch * 32, m0w);
+    bulk_commit_group();
+    trace_stamp(p, tr_role, tr_it, 4 + 3 * (ch & 7));
+  }
+  ++st.cnt;
+}
+
 template <typename T, int BN>
 __device__ __forceinline__ void epilogue_tile_tma(const ConvParams& p, const int m0w, const int n0, const uint32_t t_row,
-                                                  const int lane, uint8_t* stage, uint64_t* res_bar, uint32_t& cnt,
-                                                  bool& prefetched, float* s_stat, const float* s_ss, const bool has_next,
-                                                  const int next_m0w, const int next_n0) {
+                                                  const int lane, EpiTmaState& st, float* s_stat, const float* s_ss,
+                                                  const bool has_next, const int next_m0w, const int next_n0,
+                                                  const int tr_role = 0, const int tr_it = 64) {
   if (m0w >= p.M) return;                        // warp-uniform: all 32 rows lie past the last pixel (tail tile)
   const bool has_res = p.res != nullptr;
   const bool row_ok = m0w + lane < p.M;
   constexpr int NCH = BN / 32;
   const int nvalid = min(NCH, (p.cout - n0) >> 5);           // zero-padded weight rows (cout_pad > cout) are not stored
-  const int sw = (lane >> 1) & 3;                // SWIZZLE_64B: 16-byte chunk j of row r sits at chunk j ^ ((r >> 1) & 3)
-  uint32_t rbuf[2][32];
-  tmem_ld_32x32(t_row, rbuf[0]);
-  if (has_res && !prefetched && lane == 0) {     // first chunk of the run: nobody fetched its residual ahead of time
+  if (nvalid <= 0) return;
+  uint32_t ra[32], rb[32];
+  tmem_ld_32x32(t_row, ra);
+  if (has_res && !st.prefetched && lane == 0) {  // first chunk of the run: nobody fetched its residual ahead of time
     bulk_wait_group_read<EPI_TILES - 1>();
-    const uint32_t b = cnt % EPI_TILES;
-    mbar_arrive_expect_tx(&res_bar[b], EPI_TILE_BYTES);
-    tma_load_2d(stage + b * EPI_TILE_BYTES, &p.tmR, &res_bar[b], n0, m0w);
+    const uint32_t b = st.cnt % EPI_TILES;
+    mbar_arrive_expect_tx(&st.res_bar[b], EPI_TILE_BYTES);
+    tma_load_2d(st.stage + b * EPI_TILE_BYTES, &p.tmR, &st.res_bar[b], n0, m0w);
   }
-#pragma unroll
-  for (int ch = 0; ch < NCH; ++ch) {
-    if (ch >= nvalid) break;
-    const uint32_t b = cnt % EPI_TILES;
-    uint8_t* buf = stage + b * EPI_TILE_BYTES;
-    if (!has_res) {                              // the store that last read this tile (3 chunks ago) has drained
-      if (lane == 0) bulk_wait_group_read<EPI_TILES - 1>();
-      __syncwarp();
-    }
+#pragma unroll 1
+  for (int ch = 0; ch < nvalid; ch += 2) {
+    if (lane == 0) trace_stamp(p, tr_role, tr_it, 2 + 3 * (ch & 7));
     tmem_ld_wait();
-    uint32_t (&r)[32] = rbuf[ch & 1];
-    if (ch + 1 < nvalid) tmem_ld_32x32(t_row + (ch + 1) * 32, rbuf[(ch + 1) & 1]);
-    if (has_res) {
-      // fetch the NEXT chunk's residual (this tile's, or the first of the next tile) into the tile freed two stores ago
-      const bool last = ch + 1 >= nvalid;
-      const int nm = last ? next_m0w : m0w;
-      const int nc = last ? next_n0 : n0 + (ch + 1) * 32;
-      const bool go = last ? (has_next && next_m0w < p.M) : true;
-      if (go && lane == 0) {
-        bulk_wait_group_read<1>();
-        const uint32_t nb = (cnt + 1) % EPI_TILES;
-        mbar_arrive_expect_tx(&res_bar[nb], EPI_TILE_BYTES);
-        tma_load_2d(stage + nb * EPI_TILE_BYTES, &p.tmR, &res_bar[nb], nc, nm);
+    if (lane == 0) trace_stamp(p, tr_role, tr_it, 3 + 3 * (ch & 7));
+    if (ch + 1 < nvalid) tmem_ld_32x32(t_row + (ch + 1) * 32, rb);
+    epi_tma_chunk<T, BN>(p, ra, ch, nvalid, m0w, n0, row_ok, has_res, lane, st, s_stat, s_ss, has_next, next_m0w, next_n0,
+                         tr_role, tr_it);
+    if (ch + 1 < nvalid) {
+      if (lane == 0) trace_stamp(p, tr_role, tr_it, 2 + 3 * ((ch + 1) & 7));
+      tmem_ld_wait();
+      if (lane == 0) trace_stamp(p, tr_role, tr_it, 3 + 3 * ((ch + 1) & 7));
+      if (ch + 2 < nvalid) tmem_ld_32x32(t_row + (ch + 2) * 32, ra);
+      epi_tma_chunk<T, BN>(p, rb, ch + 1, nvalid, m0w, n0, row_ok, has_res, lane, st, s_stat, s_ss, has_next, next_m0w,
+                           next_n0, tr_role, tr_it);
+    }
+  }
+}
+
+// Detection-head epilogue with the decode fused in (yb_net_detect): instead of storing the fp32 feature map
+// (model.py:55-58) for predict_kernel and nms_compact_kernel to re-read, every thread turns its accumulator row — one
+// grid cell, 3 anchors x E = 5 + C logits, all inside this n-tile — into 3 boxes (model.py:82-137, 182-188) and appends
+// the (box, class) pairs with score = sigmoid(conf) * sigmoid(prob) >= thr (test_single_image.py:55,
+// utils/nms_utils.py:30) to the per-(image, class) candidate lists of the NMS (csrc/nms.cu).  Same arithmetic as
+// predict_kernel (decode.cuh), so boxes and scores are bit-identical to the unfused path; the feature maps, the
+// [n, B, C] score tensor and their ~440 MB of HBM round trips at batch 64 never exist.
+//   phase 1: the 3 x 5 box / objectness logits come from three 16-column TMEM reads -> boxes stored, conf kept;
+//            a warp none of whose 96 (row, anchor) pairs reaches conf >= thr is done (score <= conf).
+//   phase 2: the class logits, chunk by chunk: TMEM -> registers -> the thread's own row of the staging tile, then a
+//            ROLLED loop over the columns (column -> (anchor, class) carried as warp-uniform counters), so the code
+//            stays small (see the instruction-cache note above).
+template <int BN, int E>
+__device__ __forceinline__ void epilogue_tile_detect(const ConvParams& p, const int row, const uint32_t t_row,
+                                                     const int lane, const float* s_ss, float* stage) {
+  static_assert(3 * E <= BN, "all three anchors must lie in one n-tile");
+  static_assert((E % 16) <= 11 && ((2 * E) % 16) <= 11, "an anchor's 5 head logits must fit one aligned 16-column read");
+  const DetParams& d = p.det;
+  const bool row_ok = row < p.M;
+  const int cells = p.P * p.Q;
+  const int img = row_ok ? row / cells : -1 - lane;          // rows past M: distinct dummies, never grouped, never stored
+  const int cell = row_ok ? row - img * cells : 0;
+  const unsigned same = __match_any_sync(0xffffffffu, img);   // lanes of my image (candidate slots are reserved per image)
+  const unsigned lt = (1u << lane) - 1u;
+  const float offx = (float)(cell % p.Q), offy = (float)(cell / p.Q);
+  const int box0 = d.box_off + cell * 3;
+  // ---- phase 1: boxes + objectness ----
+  uint32_t h0[16], h1[16], h2[16];
+  tmem_ld_32x16(t_row + ((0 * E) & ~15), h0);
+  tmem_ld_32x16(t_row + ((1 * E) & ~15), h1);
+  tmem_ld_32x16(t_row + ((2 * E) & ~15), h2);
+  tmem_ld_wait();
+  float conf[3];
+  bool ok[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const uint32_t (&h)[16] = a == 0 ? h0 : (a == 1 ? h1 : h2);
+    constexpr int dummy = 0; (void)dummy;
+    const int o = (a * E) & 15, c0 = a * E;
+    float t[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) t[k] = fmaf(__uint_as_float(h[o + k]), s_ss[c0 + k], s_ss[BN + c0 + k]);   // scale 1, shift = bias
+    conf[a] = sigmoid_ref(t[4]);                               // model.py:167
+    ok[a] = row_ok && conf[a] >= d.thr;                        // score = conf * prob <= conf: nothing below thr can pass
+    if (row_ok) {
+      float4 b;
+      decode_axis(t[0], t[2], offx, d.ratio_w, d.anchor_w[a], b.x, b.z);
+      decode_axis(t[1], t[3], offy, d.ratio_h, d.anchor_h[a], b.y, b.w);
+      reinterpret_cast<float4*>(d.boxes)[(long)img * d.B + box0 + a] = b;
+    }
+  }
+  const bool any0 = __any_sync(0xffffffffu, ok[0]), any1 = __any_sync(0xffffffffu, ok[1]), any2 = __any_sync(0xffffffffu, ok[2]);
+  if (!(any0 || any1 || any2)) return;
+  // ---- phase 2: class scores ----
+  constexpr int NCH = (3 * E + 31) / 32;
+  float* myrow = stage + lane * 33;
+  int a = 0, e = 0;                                            // (anchor, element) of the current column: warp-uniform
+  float cconf = conf[0];
+  bool cok = ok[0], cany = any0;
+  auto body = [&](const uint32_t (&r)[32], const int ch) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) myrow[j] = __uint_as_float(r[j]);
+    const int ncol = min(32, 3 * E - ch * 32);
+#pragma unroll 2
+    for (int j = 0; j < ncol; ++j) {
+      const int col = ch * 32 + j;
+      if (e >= 5 && cany) {
+        const float v = fmaf(myrow[j], s_ss[col], s_ss[BN + col]);
+        bool pass = false;
+        float sc = 0.f;
+        if (cok && v >= d.logit_lo) {
+          sc = __fmul_rn(cconf, sigmoid_ref(v));               // model.py:168, test_single_image.py:55
+          pass = sc >= d.thr;                                  // utils/nms_utils.py:30
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (m != 0u) {                                         // warp-uniform
+          const int c = e - 5;
+          const unsigned mine = m & same;
+          const int leader = pass ? __ffs(mine) - 1 : lane;
+          int base = 0;
+          if (pass && lane == leader) base = atomicAdd(d.cand_count + img * d.C + c, __popc(mine));
+          base = __shfl_sync(0xffffffffu, base, leader);
+          if (pass) {
+            const long seg = ((long)img * d.C + c) * d.B;
+            const int slot = base + __popc(mine & lt);
+            d.cand_score[seg + slot] = sc;
+            d.cand_idx[seg + slot] = box0 + a;
+          }
+        }
       }
-      if (last) prefetched = go;
-    }
-    if (p.stat_sum != nullptr) {
-      // BN batch statistics of the raw conv output: per-CTA column sums in shared memory, flushed by the caller
-      float a[32], q[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float t = row_ok ? __uint_as_float(r[j]) : 0.f;
-        a[j] = t;
-        q[j] = t * t;
-      }
-      const float cs = warp_col_sum32(a, lane);
-      const float cs2 = warp_col_sum32(q, lane);
-      atomicAdd(&s_stat[ch * 32 + lane], cs);
-      atomicAdd(&s_stat[BN + ch * 32 + lane], cs2);
-    }
-    float v[32];
-    const float4* sc4 = reinterpret_cast<const float4*>(s_ss + ch * 32);
-    const float4* sh4 = reinterpret_cast<const float4*>(s_ss + BN + ch * 32);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 sc = sc4[j];
-      const float4 sh = sh4[j];
-      v[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), sc.x, sh.x);
-      v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), sc.y, sh.y);
-      v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), sc.z, sh.z);
-      v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), sc.w, sh.w);
-    }
-    if (p.leaky) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.1f * v[j]);   // == v > 0 ? v : 0.1 v
-    }
-    uint4* rowp = reinterpret_cast<uint4*>(buf + lane * 64);
-    if (has_res) {
-      mbar_wait(&res_bar[b], (cnt / EPI_TILES) & 1);                   // residual tile landed (async proxy -> visible)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint4 u = rowp[j ^ sw];
-        float2 f;
-        f = Pack2<T>::unpack(u.x); v[8 * j + 0] += f.x; v[8 * j + 1] += f.y;
-        f = Pack2<T>::unpack(u.y); v[8 * j + 2] += f.x; v[8 * j + 3] += f.y;
-        f = Pack2<T>::unpack(u.z); v[8 * j + 4] += f.x; v[8 * j + 5] += f.y;
-        f = Pack2<T>::unpack(u.w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
+      if (++e == E) {
+        e = 0; ++a;
+        cconf = a == 1 ? conf[1] : conf[2];
+        cok = a == 1 ? ok[1] : ok[2];
+        cany = a == 1 ? any1 : any2;
       }
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint4 pk;
-      pk.x = Pack2<T>::pack(v[8 * j + 0], v[8 * j + 1]);
-      pk.y = Pack2<T>::pack(v[8 * j + 2], v[8 * j + 3]);
-      pk.z = Pack2<T>::pack(v[8 * j + 4], v[8 * j + 5]);
-      pk.w = Pack2<T>::pack(v[8 * j + 6], v[8 * j + 7]);
-      rowp[j ^ sw] = pk;
+  };
+  uint32_t ra[32], rb[32];
+  tmem_ld_32x32(t_row, ra);
+#pragma unroll 1
+  for (int ch = 0; ch < NCH; ch += 2) {
+    tmem_ld_wait();
+    if (ch + 1 < NCH) tmem_ld_32x32(t_row + (ch + 1) * 32, rb);
+    body(ra, ch);
+    if (ch + 1 < NCH) {
+      tmem_ld_wait();
+      if (ch + 2 < NCH) tmem_ld_32x32(t_row + (ch + 2) * 32, ra);
+      body(rb, ch + 1);
     }
-    fence_proxy_async();                         // generic-proxy writes -> visible to the TMA (async proxy)
-    __syncwarp();
-    if (lane == 0) {
-      tma_store_2d(&p.tmO, buf, n0 + ch * 32, m0w);
-      bulk_commit_group();
-    }
-    ++cnt;
   }
 }
 
@@ -392,6 +549,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int kb_per_tap = p.cin / BK;
   const int num_kb = p.kh * p.kw * kb_per_tap;
+  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[6 * 64 * 32] = clock64();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -413,6 +571,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[6 * 64 * 32 + 1] = clock64();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -444,6 +603,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int w_base = q * p.stride - p.pad;
         const int h_base = pp * p.stride - p.pad;
         int c0 = 0, tw = 0, th = 0, kcol = 0;                  // channel chunk, tap (tw, th), column in the packed weights
+        trace_stamp(p, 0, (tile - blockIdx.x) / gridDim.x, 0);
         for (int kb = 0; kb < num_kb; kb += kps) {
           // one handshake per group of kps k-blocks: the short-K-block layers (Cin = 32: two 32-cycle MMAs per
           // k-block) were bound by ~230-440 ns of barrier round trip per k-block (profiles/r01_k_layers_infer.md)
@@ -466,6 +626,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           if (++stage == nst) { stage = 0; phase ^= 1; }
         }
+        trace_stamp(p, 0, (tile - blockIdx.x) / gridDim.x, 1);
       }
     }
     __syncwarp();
@@ -481,12 +642,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
+        trace_stamp(p, 1, it, 0);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue drained this accumulator
         tcgen05_fence_after();
+        trace_stamp(p, 1, it, 1);
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_kb; kb += kps) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
+          if (kb == 0) trace_stamp(p, 1, it, 2);
           for (int j = 0; j < kps; ++j) {
             const int slot = stage * kps + j;
             const uint32_t a_addr = a_base + slot * C::A_BYTES;
@@ -502,6 +666,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (kb + kps >= num_kb) umma_commit(&tfull_bar[acc]);       // accumulator complete
           if (++stage == nst) { stage = 0; phase ^= 1; }
         }
+        trace_stamp(p, 1, it, 3);
       }
     }
     __syncwarp();
@@ -515,10 +680,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
     int it = 0;
-    uint32_t epi_cnt = 0;
-    bool epi_prefetched = false;
     uint8_t* my_stage = reinterpret_cast<uint8_t*>(stage_base) + (warp - 2) * STAGE_BYTES_W;
-    uint64_t* my_res_bar = res_bar + (warp - 2) * EPI_TILES;
+    EpiTmaState epi_st{my_stage, res_bar + (warp - 2) * EPI_TILES, 0u, false};
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -536,11 +699,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int ntile = tile + gridDim.x;
         int nm = 0, nn = 0;
         if (ntile < num_tiles) tile_coords(p, ntile, nm, nn);
+        if (lane == 0) trace_stamp(p, warp, it, 0);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tcgen05_fence_after();
+        if (lane == 0) trace_stamp(p, warp, it, 1);
         if (!(p.dbg & 8))
-          epilogue_tile_tma<T, BN>(p, m0 + quarter * 32, n0, t_row, lane, my_stage, my_res_bar, epi_cnt, epi_prefetched,
-                                   s_stat, s_ss, ntile < num_tiles, nm * BLOCK_M + quarter * 32, nn * BN);
+          epilogue_tile_tma<T, BN>(p, m0 + quarter * 32, n0, t_row, lane, epi_st, s_stat, s_ss, ntile < num_tiles,
+                                   nm * BLOCK_M + quarter * 32, nn * BN, warp, it);
+        if (lane == 0) trace_stamp(p, warp, it, 31);
       } else {
         mbar_wait(&tfull_bar[acc], acc_phase);
         tcgen05_fence_after();
@@ -583,7 +749,7 @@ struct Cfg2 {
   static constexpr uint32_t SBO = 8 * BK * 2;
 };
 
-template <typename T, int BN, int BK>
+template <typename T, int BN, int BK, int DET_E = 0>   // DET_E = 5 + classes: detection head with the decode fused in
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ ConvParams p) {
@@ -714,10 +880,8 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
     int it = 0;
-    uint32_t epi_cnt = 0;
-    bool epi_prefetched = false;
     uint8_t* my_stage = reinterpret_cast<uint8_t*>(stage_base) + (warp - 2) * STAGE_BYTES_W;
-    uint64_t* my_res_bar = res_bar + (warp - 2) * EPI_TILES;
+    EpiTmaState epi_st{my_stage, res_bar + (warp - 2) * EPI_TILES, 0u, false};
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -733,13 +897,14 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_fence_after();
-      if (p.epi_tma) {
+      if constexpr (DET_E > 0) {
+        if (!(p.dbg & 8)) epilogue_tile_detect<BN, DET_E>(p, m0 + quarter * 32 + lane, t_row, lane, s_ss, reinterpret_cast<float*>(my_stage));
+      } else if (p.epi_tma) {
         const int ntile = tile + num_clusters;
         int nm = 0, nn = 0;
         if (ntile < num_tiles) tile_coords(p, ntile, nm, nn);
         if (!(p.dbg & 8))
-          epilogue_tile_tma<T, BN>(p, m0 + quarter * 32, n0, t_row, lane, my_stage, my_res_bar, epi_cnt, epi_prefetched,
-                                   s_stat, s_ss, ntile < num_tiles,
+          epilogue_tile_tma<T, BN>(p, m0 + quarter * 32, n0, t_row, lane, epi_st, s_stat, s_ss, ntile < num_tiles,
                                    nm * (2 * BLOCK_M) + (int)rank * BLOCK_M + quarter * 32, nn * BN);
       } else if (!(p.dbg & 8)) {
         epilogue_tile<T, BN>(p, m0 + quarter * 32 + lane, n0, t_row, lane, reinterpret_cast<float*>(my_stage), s_stat, s_ss);
@@ -1037,11 +1202,11 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv
   return YB_OK;
 }
 
-template <typename T, int BN, int BK>
+template <typename T, int BN, int BK, int DET_E = 0>
 static int launch_cfg2(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t st) {
   using C = Cfg2<BN, BK>;
   static DeviceOnce once;
-  auto kern = conv_igemm_2cta_kernel<T, BN, BK>;
+  auto kern = conv_igemm_2cta_kernel<T, BN, BK, DET_E>;
   { const int rc = ensure_smem_attr(once, reinterpret_cast<const void*>(kern), C::SMEM_BYTES); if (rc) return rc; }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int max_clusters = num_sms() / 2;
@@ -1096,6 +1261,7 @@ static int launch_mc(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvP
   return YB_OK;
 }
 
+static long long* g_conv_trace = nullptr;   // yb_debug_set_conv_trace (tools only)
 int conv_block_k(int cin) { return (cin % 64 == 0) ? 64 : 32; }
 // 1-CTA tile width
 int conv_block_n(int cout_pad) { return (cout_pad % 128 == 0) ? 128 : 64; }
@@ -1114,6 +1280,18 @@ int conv_launch(int dtype, int cout_pad, const CUtensorMap& tmA, const CUtensorM
     else if (dtype == YB_BF16) { YB_DISPATCH_MC(__nv_bfloat16) }
 #undef YB_DISPATCH_MC
     set_error("conv_launch: unsupported multicast configuration");
+    return YB_ERR_UNSUPPORTED;
+  }
+  if (p.det.on) {
+    // detection head with the decode fused in: pair kernel, one n-tile holding all 3 * E columns
+    const int bn = conv_block_n2(cout_pad);
+#define YB_DISPATCH_DET(T)                                                                            \
+  if (bn == 256 && bk == 64 && p.det.E == 85) return launch_cfg2<T, 256, 64, 85>(tmA, tmB, p, st); \
+  if (bn == 128 && bk == 64 && p.det.E == 25) return launch_cfg2<T, 128, 64, 25>(tmA, tmB, p, st);
+    if (p.two_cta && dtype == YB_F16) { YB_DISPATCH_DET(__half) }
+    else if (p.two_cta && dtype == YB_BF16) { YB_DISPATCH_DET(__nv_bfloat16) }
+#undef YB_DISPATCH_DET
+    set_error("conv_launch: no fused-decode kernel for %d classes (tile %d x %d)", p.det.C, bn, bk);
     return YB_ERR_UNSUPPORTED;
   }
   if (p.two_cta) {
@@ -1148,7 +1326,7 @@ int conv_launch(int dtype, int cout_pad, const CUtensorMap& tmA, const CUtensorM
 static int conv_prepare_core(const yb_conv_desc* d, int win, int kh, int kw, int scatter, const void* x,
                              const void* w_packed, const float* scale, const float* shift, const void* res, void* out,
                              float* stat_sum, float* stat_sqsum, CUtensorMap* tmA, CUtensorMap* tmB, ConvParams* p,
-                             int* cout_pad_out) {
+                             int* cout_pad_out, int force_pair = 0) {
   YB_REQUIRE(win || d->ksize == 1 || d->ksize == 3, "conv: ksize must be 1 or 3 (got %d)", d->ksize);
   YB_REQUIRE(d->stride == 1 || d->stride == 2, "conv: stride must be 1 or 2 (got %d)", d->stride);
   YB_REQUIRE(!(d->ksize == 1 && d->stride != 1), "conv: 1x1 stride-2 is not on the YOLOv3 path");
@@ -1181,6 +1359,7 @@ static int conv_prepare_core(const yb_conv_desc* d, int win, int kh, int kw, int
   bool two = cout_pad % 256 == 0 && (long)ceil_div(p->M, 2 * BLOCK_M) * (cout_pad / 256) >= 32;
   if (force && force[0] == '1') two = false;
   if (force && force[0] == '2') two = true;
+  if (force_pair) two = true;
   p->two_cta = two ? 1 : 0;
   // cluster multicast on top of the pair kernel: 2x2 pairs when there are >= 2 n-tiles, 2x1 (share B) otherwise
   int mc_m = 1, mc_n = 1;
@@ -1194,6 +1373,8 @@ static int conv_prepare_core(const yb_conv_desc* d, int win, int kh, int kw, int
   }
   p->mc_m = mc_m; p->mc_n = mc_n;
   p->dbg = opt_int("YB_CONV_DBG", 0);
+  p->trace = g_conv_trace;
+  memset(&p->det, 0, sizeof(p->det));
   p->kps = 1;   // set below once the tile shape is known
   const int bn = two ? conv_block_n2(cout_pad) : conv_block_n(cout_pad);
   {
@@ -1261,6 +1442,20 @@ int conv_prepare(const yb_conv_desc* d, const void* x, const void* w_packed, con
                            cout_pad_out);
 }
 
+// Detection head with the decode fused into the epilogue (yb_net_detect): always the pair kernel with ONE n-tile that
+// holds all 3 * (5 + C) columns; `out` is never written.  YB_ERR_UNSUPPORTED when the class count has no kernel.
+int conv_prepare_det(const yb_conv_desc* d, int class_num, const void* x, const void* w_packed, const float* scale,
+                     const float* shift, CUtensorMap* tmA, CUtensorMap* tmB, ConvParams* p, int* cout_pad_out) {
+  const int E = 5 + class_num;
+  const int bn = conv_block_n2(yb_conv_cout_pad(d->cout));
+  if (d->cout != 3 * E || conv_block_k(d->cin) != 64 || !((bn == 256 && E == 85) || (bn == 128 && E == 25))) {
+    set_error("fused decode: no kernel for %d classes", class_num);
+    return YB_ERR_UNSUPPORTED;
+  }
+  return conv_prepare_core(d, 0, 0, 0, 0, x, w_packed, scale, shift, nullptr, const_cast<void*>(x) /*unused*/, nullptr,
+                           nullptr, tmA, tmB, p, cout_pad_out, 1);
+}
+
 int conv_prepare_win(const yb_conv_desc* d, int kh, int kw, int scatter, const void* x, const void* w_packed,
                      const float* scale, const float* shift, const void* res, void* out, CUtensorMap* tmA,
                      CUtensorMap* tmB, ConvParams* p, int* cout_pad_out) {
@@ -1273,6 +1468,10 @@ int conv_prepare_win(const yb_conv_desc* d, int kh, int kw, int scatter, const v
 }  // namespace yb
 
 extern "C" int yb_conv_cout_pad(int cout) { return (cout + 63) / 64 * 64; }
+
+// tools/conv_trace.py: convs PREPARED after this call stamp CTA 0's pipeline events (clock64) into `buf`
+// ([6 roles][64 tile iterations][32 slots] + 2 (kernel entry, set-up done) int64, caller-zeroed); NULL switches it off again.
+extern "C" int yb_debug_set_conv_trace(long long* buf) { yb::g_conv_trace = buf; return YB_OK; }
 
 extern "C" int yb_conv2d_fwd(const yb_conv_desc* d, const void* x, const void* w_packed, const float* scale,
                              const float* shift, const void* res, void* out, float* stat_sum, float* stat_sqsum,

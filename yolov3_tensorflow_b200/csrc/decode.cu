@@ -5,6 +5,7 @@
 // Replaces model.py:82-137 (reorg_layer), :140-190 (predict) and the caller's
 // pred_scores = pred_confs * pred_probs (test_single_image.py:55).
 #include "common.cuh"
+#include "decode.cuh"
 
 namespace yb {
 
@@ -21,7 +22,7 @@ struct DecodeParams {
   float* scores;         // [n,B,C] or null
 };
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float sigmoidf_(float x) { return sigmoid_ref(x); }
 
 // one WARP per box: the 5+C logits of a box are contiguous (coalesced 128-byte reads), the box logits are
 // broadcast by shuffle, and probs / scores rows are written coalesced.  confs / probs / scores are optional
@@ -48,10 +49,9 @@ __global__ void __launch_bounds__(256) predict_kernel(const DecodeParams p) {
       const float ratio = axis == 0 ? p.ratio_w[s] : p.ratio_h[s];
       const int ai = (2 - s) * 3 + a;                                     // anchor groups 6:9, 3:6, 0:3
       const float anc = axis == 0 ? p.anchor_w[ai] : p.anchor_h[ai];
-      const float center = __fmul_rn(__fadd_rn(sigmoidf_(t_c), off), ratio);          // model.py:118-120
-      const float size = __fmul_rn(__fmul_rn(expf(t_s), __fdiv_rn(anc, ratio)), ratio);  // :94,:123-126
-      const float half = __fmul_rn(size, 0.5f);
-      p.boxes[gb * 4 + lane] = lane < 2 ? __fsub_rn(center, half) : __fadd_rn(center, half);  // :182-188
+      float lo, hi;
+      decode_axis(t_c, t_s, off, ratio, anc, lo, hi);                      // model.py:118-126, 182-188
+      p.boxes[gb * 4 + lane] = lane < 2 ? lo : hi;
     }
     if (lane == 0 && p.confs) p.confs[gb] = conf;                          // model.py:167
     for (int k = lane; k < p.C; k += 32) {

@@ -2,6 +2,7 @@
 // for a fixed (batch, H, W, dtype): layer schedule, activation/parameter arena layout,
 // TMA tensor maps.  concat (model.py:62,72) and NN-upsample (utils/layer_utils.py:82-87)
 // never run as ops: producers store straight into channel slices of the concat buffers.
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -16,6 +17,11 @@ namespace yb {
 void train_layout(yb_net* net);
 int train_bind(yb_net* net, cudaStream_t st);
 int train_refresh_dgrad_weights(yb_net* net, int layer, void* stream);
+int nms_candidate_buffers(void* workspace, size_t workspace_bytes, int n_images, int num_boxes, int num_classes,
+                          int max_boxes, int** cand_count, float** cand_score, int** cand_idx);
+int nms_select_gather(const float* boxes, int n_images, int num_boxes, int num_classes, int max_boxes, float iou_thresh,
+                      void* workspace, size_t workspace_bytes, float* out_boxes, float* out_scores, int32_t* out_labels,
+                      int32_t* out_indices, int32_t* out_counts, cudaStream_t st);
 
 static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
@@ -214,6 +220,13 @@ extern "C" int yb_net_bind(yb_net* net, void* activation_arena, size_t activatio
                           &L.tmB, &L.params, &cp);
     if (rc) return rc;
     L.prepared = true;
+    if (!L.info.has_bn) {
+      // fused-decode variant of the head (yb_net_detect); class counts without a kernel keep the unfused pipeline
+      L.det_ok = conv_prepare_det(&d, net->class_num, ten_ptr(net, L.in), net->par + L.w_packed,
+                                  reinterpret_cast<const float*>(net->par + L.scale),
+                                  reinterpret_cast<const float*>(net->par + L.shift), &L.det_tmA, &L.det_tmB, &L.det_params,
+                                  &L.det_cout_pad) == YB_OK;
+    }
   }
   if (net->training) return train_bind(net, static_cast<cudaStream_t>(stream));
   return YB_OK;
@@ -270,8 +283,16 @@ extern "C" int yb_net_forward(yb_net* net, const float* images, float* fm1, floa
   return yb_net_forward_layers(net, images, fm1, fm2, fm3, 0, 1 << 30, stream);
 }
 
+static int forward_layers_impl(yb_net* net, const float* images, float* fm1, float* fm2, float* fm3, int first, int last,
+                               const DetParams* det /* [3] or NULL */, void* stream);
+
 extern "C" int yb_net_forward_layers(yb_net* net, const float* images, float* fm1, float* fm2, float* fm3, int first,
                                      int last, void* stream) {
+  return forward_layers_impl(net, images, fm1, fm2, fm3, first, last, nullptr, stream);
+}
+
+static int forward_layers_impl(yb_net* net, const float* images, float* fm1, float* fm2, float* fm3, int first, int last,
+                               const DetParams* det, void* stream) {
   YB_REQUIRE(net && net->act && net->par, "forward: net not bound");
   YB_REQUIRE(images, "forward: null images");
   YB_REQUIRE(first >= 0 && first <= last, "forward: bad layer range");
@@ -319,12 +340,105 @@ extern "C" int yb_net_forward_layers(yb_net* net, const float* images, float* fm
     ConvParams* p = &L.params;
     if (!L.info.has_bn) {
       int which = L.out.buf == net->fm_buf[0] ? 0 : (L.out.buf == net->fm_buf[1] ? 1 : 2);
+      if (det) {                                      // decode + candidate filter in the epilogue, no feature map
+        ConvParams dp = L.det_params;
+        dp.det = det[which];
+        int rc = conv_launch(net->dtype, L.det_cout_pad, L.det_tmA, L.det_tmB, dp, st);
+        if (rc) return rc;
+        continue;
+      }
       p->out = user_fm[which] ? (void*)user_fm[which] : ten_ptr(net, L.out);
     }
     int rc = conv_launch(net->dtype, L.cout_pad, L.tmA, L.tmB, *p, st);
     if (rc) return rc;
   }
   return YB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward -> predict -> score = conf * prob -> per-image gpu_nms in one call (test_single_image.py:50-57): the decode and
+// the score filter run inside the three detection-head epilogues, then the greedy selection reads the candidate lists.
+// ---------------------------------------------------------------------------------------------------------------
+static int det_num_boxes(const yb_net* net) {
+  int b = 0;
+  for (int s = 0; s < 3; ++s) b += 3 * (net->h / (32 >> s)) * (net->w / (32 >> s));
+  return b;
+}
+
+extern "C" int yb_net_detect_supported(const yb_net* net) {
+  if (!net || !net->act) return 0;
+  for (auto& L : net->layers) if (!L.info.has_bn && !L.det_ok) return 0;
+  return 1;
+}
+
+extern "C" int yb_net_detect_workspace_bytes(const yb_net* net, int max_boxes, size_t* bytes) {
+  YB_REQUIRE(net && bytes && max_boxes >= 0, "detect_workspace_bytes: bad argument");
+  return yb_nms_workspace_bytes(net->n, det_num_boxes(net), net->class_num, max_boxes, bytes);
+}
+
+extern "C" int yb_net_detect(yb_net* net, const float* images, const float* anchors9x2, int max_boxes, float score_thresh,
+                             float iou_thresh, void* workspace, size_t workspace_bytes, float* boxes, float* out_boxes,
+                             float* out_scores, int32_t* out_labels, int32_t* out_indices, int32_t* out_counts,
+                             void* stream) {
+  return yb_net_detect_phases(net, images, anchors9x2, max_boxes, score_thresh, iou_thresh, workspace, workspace_bytes,
+                              boxes, out_boxes, out_scores, out_labels, out_indices, out_counts, 7, stream);
+}
+
+extern "C" int yb_net_detect_phases(yb_net* net, const float* images, const float* anchors9x2, int max_boxes,
+                                    float score_thresh, float iou_thresh, void* workspace, size_t workspace_bytes,
+                                    float* boxes, float* out_boxes, float* out_scores, int32_t* out_labels,
+                                    int32_t* out_indices, int32_t* out_counts, int phases, void* stream) {
+  YB_REQUIRE(net && net->act && net->par, "detect: net not bound");
+  YB_REQUIRE(images && anchors9x2 && workspace && boxes && out_counts, "detect: null pointer");
+  YB_REQUIRE(max_boxes >= 0, "detect: bad max_boxes");
+  if (!yb_net_detect_supported(net)) {
+    set_error("detect: no fused-decode kernel for %d classes (use forward + predict + nms)", net->class_num);
+    return YB_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n = net->n, B = det_num_boxes(net), C = net->class_num;
+  if (max_boxes == 0) {
+    YB_CUDA(cudaMemsetAsync(out_counts, 0, sizeof(int32_t) * n, st));
+    return YB_OK;
+  }
+  YB_REQUIRE(out_boxes && out_scores && out_labels && out_indices, "detect: null pointer");
+  YB_REQUIRE(((uintptr_t)boxes & 15) == 0 && ((uintptr_t)out_boxes & 15) == 0, "detect: boxes must be 16-byte aligned");
+  int* cand_count; float* cand_score; int* cand_idx;
+  int rc = nms_candidate_buffers(workspace, workspace_bytes, n, B, C, max_boxes, &cand_count, &cand_score, &cand_idx);
+  if (rc) return rc;
+  if (phases & 1) YB_CUDA(cudaMemsetAsync(cand_count, 0, sizeof(int) * (size_t)n * C, st));
+  DetParams det[3];
+  int off = 0;
+  for (int s = 0; s < 3; ++s) {
+    DetParams& d = det[s];
+    memset(&d, 0, sizeof(d));
+    const int gh = net->h / (32 >> s), gw = net->w / (32 >> s);
+    d.boxes = boxes; d.cand_count = cand_count; d.cand_score = cand_score; d.cand_idx = cand_idx;
+    d.B = B; d.C = C; d.E = 5 + C; d.box_off = off;
+    off += 3 * gh * gw;
+    d.ratio_h = (float)((double)net->h / (double)gh);        // model.py:91 (float64 divide, cast to f32)
+    d.ratio_w = (float)((double)net->w / (double)gw);
+    for (int a = 0; a < 3; ++a) {                            // anchor groups 6:9, 3:6, 0:3 (model.py:148-150)
+      d.anchor_w[a] = anchors9x2[2 * ((2 - s) * 3 + a)];
+      d.anchor_h[a] = anchors9x2[2 * ((2 - s) * 3 + a) + 1];
+    }
+    d.thr = score_thresh;
+    // logits below logit(thr) - 0.01 give sigmoid < thr by > 1e-3 (float error ~1e-7): exact pre-filter
+    d.logit_lo = (score_thresh > 0.f && score_thresh < 1.f)
+                     ? (float)(log((double)score_thresh / (1.0 - (double)score_thresh)) - 0.01) : -INFINITY;
+    d.on = 1;
+  }
+  if (phases & 1) {
+    rc = forward_layers_impl(net, images, nullptr, nullptr, nullptr, 0, 0, det, stream);
+    if (rc) return rc;
+  }
+  if (phases & 2) {
+    rc = forward_layers_impl(net, images, nullptr, nullptr, nullptr, 1, 1 << 30, det, stream);
+    if (rc) return rc;
+  }
+  if (!(phases & 4)) return YB_OK;
+  return nms_select_gather(boxes, n, B, C, max_boxes, iou_thresh, workspace, workspace_bytes, out_boxes, out_scores,
+                           out_labels, out_indices, out_counts, st);
 }
 
 extern "C" int yb_net_layer_output(const yb_net* net, int layer, void** ptr, int* ld, int* dtype) {

@@ -31,6 +31,11 @@ struct Layer {
   CUtensorMap tmA, tmB;
   ConvParams params;
   bool prepared = false;
+  // detection heads: the same conv with the decode + NMS candidate filter fused into its epilogue (yb_net_detect)
+  CUtensorMap det_tmA, det_tmB;
+  ConvParams det_params;
+  int det_cout_pad = 0;
+  bool det_ok = false;
   // ---- training plan (net_train.cu) ----
   size_t z_off = 0, dz_off = 0;      // raw conv output z / its gradient (activation arena); dz is zero-inserted for stride 2
   int dz_ld = 0, dz_dilated = 0, k_cout = 0;

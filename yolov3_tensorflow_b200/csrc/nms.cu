@@ -361,6 +361,58 @@ extern "C" int yb_nms_workspace_bytes(int n_images, int num_boxes, int num_class
   return YB_OK;
 }
 
+namespace yb {
+
+// Workspace carve-up for callers that fill the candidate lists themselves (the fused detection-head epilogue).
+int nms_candidate_buffers(void* workspace, size_t workspace_bytes, int n_images, int num_boxes, int num_classes,
+                          int max_boxes, int** cand_count, float** cand_score, int** cand_idx) {
+  const NmsWs w = nms_layout(n_images, num_boxes, num_classes, max_boxes > 0 ? max_boxes : 1);
+  if (workspace_bytes < w.total) {
+    set_error("nms: workspace too small (%zu < %zu)", workspace_bytes, w.total);
+    return YB_ERR_WORKSPACE;
+  }
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  *cand_count = reinterpret_cast<int*>(ws + w.cand_count);
+  *cand_score = reinterpret_cast<float*>(ws + w.cand_score);
+  *cand_idx = reinterpret_cast<int*>(ws + w.cand_idx);
+  return YB_OK;
+}
+
+// Greedy selection + class-ascending gather over candidate lists that are already in the workspace.
+int nms_select_gather(const float* boxes, int n_images, int num_boxes, int num_classes, int max_boxes, float iou_thresh,
+                      void* workspace, size_t workspace_bytes, float* out_boxes, float* out_scores, int32_t* out_labels,
+                      int32_t* out_indices, int32_t* out_counts, cudaStream_t st) {
+  const NmsWs w = nms_layout(n_images, num_boxes, num_classes, max_boxes);
+  if (workspace_bytes < w.total) {
+    set_error("nms: workspace too small (%zu < %zu)", workspace_bytes, w.total);
+    return YB_ERR_WORKSPACE;
+  }
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  int* cand_count = reinterpret_cast<int*>(ws + w.cand_count);
+  float* cand_score = reinterpret_cast<float*>(ws + w.cand_score);
+  int* cand_idx = reinterpret_cast<int*>(ws + w.cand_idx);
+  int* sel_count = reinterpret_cast<int*>(ws + w.sel_count);
+  int* sel_idx = reinterpret_cast<int*>(ws + w.sel_idx);
+  float* sel_score = reinterpret_cast<float*>(ws + w.sel_score);
+  dim3 g2(num_classes, n_images);
+  static_assert(HIST_BINS * sizeof(int) <= BAND_CAP * (sizeof(unsigned long long) + sizeof(BoxN)), "histogram must fit the staging area");
+  const size_t sel_smem = (size_t)BAND_CAP * (sizeof(unsigned long long) + sizeof(BoxN)) + (size_t)max_boxes * sizeof(BoxN);
+  constexpr int SEL_SMEM_MAX = 200 * 1024;
+  YB_REQUIRE(sel_smem <= (size_t)SEL_SMEM_MAX, "nms: max_boxes %d too large for the shared-memory staging", max_boxes);
+  static DeviceOnce once;       // per device, not per process
+  { const int rc = ensure_smem_attr(once, reinterpret_cast<const void*>(nms_select_kernel), SEL_SMEM_MAX); if (rc) return rc; }
+  nms_select_kernel<<<g2, SELECT_THREADS, sel_smem, st>>>(boxes, num_boxes, num_classes, max_boxes, iou_thresh, cand_count,
+                                                          cand_score, cand_idx, sel_count, sel_idx, sel_score);
+  YB_CUDA(cudaGetLastError());
+  nms_gather_kernel<<<n_images, 256, (num_classes + 1) * sizeof(int), st>>>(
+      boxes, num_boxes, num_classes, max_boxes, sel_count, sel_idx, sel_score, out_boxes, out_scores, out_labels,
+      out_indices, out_counts);
+  YB_CUDA(cudaGetLastError());
+  return YB_OK;
+}
+
+}  // namespace yb
+
 extern "C" int yb_nms(const float* boxes, const float* scores, int n_images, int num_boxes, int num_classes,
                       int max_boxes, float score_thresh, float iou_thresh, void* workspace, size_t workspace_bytes,
                       float* out_boxes, float* out_scores, int32_t* out_labels, int32_t* out_indices,
@@ -376,18 +428,10 @@ extern "C" int yb_nms(const float* boxes, const float* scores, int n_images, int
   }
   YB_REQUIRE(boxes && scores && out_boxes && out_scores && out_labels && out_indices, "nms: null pointer");
   YB_REQUIRE(((uintptr_t)boxes & 15) == 0 && ((uintptr_t)out_boxes & 15) == 0, "nms: boxes must be 16-byte aligned");
-  const NmsWs w = nms_layout(n_images, num_boxes, num_classes, max_boxes);
-  if (workspace_bytes < w.total) {
-    set_error("nms: workspace too small (%zu < %zu)", workspace_bytes, w.total);
-    return YB_ERR_WORKSPACE;
-  }
-  uint8_t* ws = static_cast<uint8_t*>(workspace);
-  int* cand_count = reinterpret_cast<int*>(ws + w.cand_count);
-  float* cand_score = reinterpret_cast<float*>(ws + w.cand_score);
-  int* cand_idx = reinterpret_cast<int*>(ws + w.cand_idx);
-  int* sel_count = reinterpret_cast<int*>(ws + w.sel_count);
-  int* sel_idx = reinterpret_cast<int*>(ws + w.sel_idx);
-  float* sel_score = reinterpret_cast<float*>(ws + w.sel_score);
+  int* cand_count; float* cand_score; int* cand_idx;
+  int rc = nms_candidate_buffers(workspace, workspace_bytes, n_images, num_boxes, num_classes, max_boxes, &cand_count,
+                                 &cand_score, &cand_idx);
+  if (rc) return rc;
   YB_CUDA(cudaMemsetAsync(cand_count, 0, sizeof(int) * (size_t)n_images * num_classes, st));
   int bpb = (COMPACT_THREADS * COMPACT_EPT) / num_classes;
   if (bpb < 1) bpb = 1;
@@ -395,21 +439,6 @@ extern "C" int yb_nms(const float* boxes, const float* scores, int n_images, int
   nms_compact_kernel<<<g1, COMPACT_THREADS, 2 * num_classes * sizeof(int), st>>>(
       scores, num_boxes, num_classes, bpb, score_thresh, cand_count, cand_score, cand_idx);
   YB_CUDA(cudaGetLastError());
-  dim3 g2(num_classes, n_images);
-  static_assert(HIST_BINS * sizeof(int) <= BAND_CAP * (sizeof(unsigned long long) + sizeof(BoxN)), "histogram must fit the staging area");
-  const size_t sel_smem = (size_t)BAND_CAP * (sizeof(unsigned long long) + sizeof(BoxN)) + (size_t)max_boxes * sizeof(BoxN);
-  YB_REQUIRE(sel_smem <= 200 * 1024, "nms: max_boxes %d too large for the shared-memory staging", max_boxes);
-  static size_t smem_set = 0;
-  if (sel_smem > smem_set) {
-    YB_CUDA(cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
-    smem_set = sel_smem;
-  }
-  nms_select_kernel<<<g2, SELECT_THREADS, sel_smem, st>>>(boxes, num_boxes, num_classes, max_boxes, iou_thresh, cand_count,
-                                                          cand_score, cand_idx, sel_count, sel_idx, sel_score);
-  YB_CUDA(cudaGetLastError());
-  nms_gather_kernel<<<n_images, 256, (num_classes + 1) * sizeof(int), st>>>(
-      boxes, num_boxes, num_classes, max_boxes, sel_count, sel_idx, sel_score, out_boxes, out_scores, out_labels,
-      out_indices, out_counts);
-  YB_CUDA(cudaGetLastError());
-  return YB_OK;
+  return nms_select_gather(boxes, n_images, num_boxes, num_classes, max_boxes, iou_thresh, workspace, workspace_bytes,
+                           out_boxes, out_scores, out_labels, out_indices, out_counts, st);
 }

@@ -396,6 +396,62 @@ class yolov3(object):
                              ptr(boxes), None, None, ptr(scores), stream_handle()), "yb_predict")
         return boxes, scores
 
+    # ------------------------------------------------------------------ test_single_image.py:50-57
+    def detect_raw(self, inputs, max_boxes=200, score_thresh=0.3, nms_thresh=0.45, phases=7, out=None):
+        """The detection pipeline of test_single_image.py:50-57 for a batch, in ONE engine call:
+        forward -> predict -> pred_scores = confs * probs -> gpu_nms per image.  The anchor decode and the score filter
+        run inside the detection-head conv epilogues (no feature map / score tensor round trip through HBM); results
+        are bit-identical to forward() + predict_scores() + batched_nms_raw().
+        -> (boxes_all [N,B,4], out_boxes [N,C*max_boxes,4], out_scores, out_labels, out_indices [N,C*max_boxes],
+            counts [N]) on the device, no host synchronisation.
+        phases / out: benchmarks bracket the parts (1 stem, 2 tensor-core convs, 4 NMS) with their own events and pass
+        the previous call's result tuple back in as `out`."""
+        x = _as_cuda_f32(inputs, self.device)
+        if x.dim() != 4 or x.shape[3] != 3:
+            raise ValueError(f"inputs must be [N,H,W,3], got {tuple(x.shape)}")
+        n, h, w = int(x.shape[0]), int(x.shape[1]), int(x.shape[2])
+        if h % 32 or w % 32:
+            raise ValueError(f"H and W must be multiples of 32, got {h}x{w}")
+        self.img_size = (h, w)
+        plan = self._plan(n, h, w, training=False)
+        if self._fold_dirty:
+            check(lib.yb_net_refold_bn(plan.handle, stream_handle()), "yb_net_refold_bn")
+            self._fold_dirty = False
+        self._last_plan = plan
+        C_, mb = self.class_num, int(max_boxes)
+        if not lib.yb_net_detect_supported(plan.handle):
+            from .utils.nms_utils import batched_nms_raw       # class counts without a fused kernel: three calls
+            boxes, scores = self.predict_scores(self.forward(x))
+            return (boxes,) + tuple(batched_nms_raw(boxes, scores, C_, mb, score_thresh, nms_thresh))
+        B = 3 * sum((h // s) * (w // s) for s in (32, 16, 8))
+        dev = self.device
+        cap = max(C_ * max(mb, 0), 1)
+        if out is not None:
+            boxes, ob, os_, ol, oi, cnt = out
+        else:
+            boxes = torch.empty((n, B, 4), dtype=torch.float32, device=dev)
+            ob = torch.empty((n, cap, 4), dtype=torch.float32, device=dev)
+            os_ = torch.empty((n, cap), dtype=torch.float32, device=dev)
+            ol = torch.empty((n, cap), dtype=torch.int32, device=dev)
+            oi = torch.empty((n, cap), dtype=torch.int32, device=dev)
+            cnt = torch.empty((n,), dtype=torch.int32, device=dev)
+        need = C.c_size_t()
+        check(lib.yb_net_detect_workspace_bytes(plan.handle, mb, C.byref(need)), "yb_net_detect_workspace_bytes")
+        ws = getattr(plan, "_det_ws", None)
+        if ws is None or ws.numel() < need.value:
+            ws = torch.empty(max(need.value, 256), dtype=torch.uint8, device=dev)
+            plan._det_ws = ws                                  # per plan: stream-ordered reuse by this model only
+        check(lib.yb_net_detect_phases(plan.handle, ptr(x), _lib.fptr(self.anchors.reshape(-1)), mb, float(score_thresh),
+                                       float(nms_thresh), ptr(ws), ws.numel(), ptr(boxes), ptr(ob), ptr(os_), ptr(ol),
+                                       ptr(oi), ptr(cnt), int(phases), stream_handle()), "yb_net_detect")
+        return boxes, ob, os_, ol, oi, cnt
+
+    def detect(self, inputs, max_boxes=200, score_thresh=0.3, nms_thresh=0.45):
+        """detect_raw() unpacked like the reference's per-image result: a list of (boxes [K,4], scores [K], labels [K])
+        per image (classes ascending, descending score inside a class).  Reading the counts is the one host sync."""
+        _, ob, os_, ol, oi, cnt = self.detect_raw(inputs, max_boxes, score_thresh, nms_thresh)
+        return [(ob[i, :k], os_[i, :k], ol[i, :k]) for i, k in enumerate(cnt.tolist())]
+
     # ------------------------------------------------------------------ model.py:192-304
     def _loss_scale(self, feature_map_i, y_true, anchors, loss4, want_grad=False, grad_out=None):
         fm = _as_cuda_f32(feature_map_i, self.device)
