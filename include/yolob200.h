@@ -90,7 +90,7 @@ int yb_conv2d_fwd(const yb_conv_desc* d, const void* x, const void* w_packed, co
                   void* stream);
 int yb_conv_cout_pad(int cout);
 /* Profiling aid (tools/conv_trace.py): convs prepared after this call make CTA 0 stamp clock64 at its pipeline events
- * into buf ([6 roles][64 tile iterations][32 slots] + 2 int64, device memory, caller-zeroed); NULL switches it off. */
+ * into buf ([10 warps][64 tile iterations][32 slots] + 2 int64, device memory, caller-zeroed); NULL switches it off. */
 int yb_debug_set_conv_trace(long long* buf);
 
 /* First layer (darknet53_body/Conv, 3->32, 3x3 s1; utils/layer_utils.py:35): float32 NHWC image in,
@@ -105,6 +105,33 @@ int yb_conv3x3_thin_fwd(const yb_conv_desc* d, const void* x, const void* w_pack
                         const float* shift, const void* res, void* out, void* stream);
 int yb_stem_conv_fwd_tc(const float* x, const float* w_ohwi, const float* scale, const float* shift, int n, int h,
                         int w, int dtype, int leaky, void* out, void* stream);
+
+/* 3x3 convs with cin in {32, 64} and cout in {64, 128} (darknet53_body Conv_1/3/6/8, utils/layer_utils.py:36-44) from
+ * a shared-memory HALO tile: one tiled TMA load per 16x8-pixel output tile (four parity planes for stride 2), the nine
+ * taps are nine UMMA descriptors into that tile, weights resident in shared memory (csrc/conv_halo.cu).  Same contract
+ * as yb_conv2d_fwd without statistics; 16-bit output; (w / stride) % 8 == 0.  yb_conv3x3_halo_supported: 1 if d fits. */
+int yb_conv3x3_halo_supported(const yb_conv_desc* d);
+int yb_conv3x3_halo_fwd(const yb_conv_desc* d, const void* x, const void* w_packed, const float* scale,
+                        const float* shift, const void* res, void* out, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Pre-processing either side of the hot path, on the device
+ * --------------------------------------------------------------------------------- */
+/* process_box (utils/data_utils.py:51-115) for a batch: ground-truth lists -> y_true_13/26/52.
+ *   boxes  float32 [n, vmax, 5] (x_min, y_min, x_max, y_max, mixup weight), labels int32 [n, vmax], counts int32 [n]
+ *   (boxes beyond counts[i] are ignored); anchors9x2 host float[18]; y_true_s float32 [n, h/s, w/s, 3, 6 + class_num],
+ *   fully overwritten (zeros, mix weight 1, then the boxes in list order: the last box of a slot wins, class bits
+ *   accumulate — exactly the reference's loop).  Bit-exact vs the reference.  vmax <= 256. */
+int yb_process_box(const float* boxes, const int32_t* labels, const int32_t* counts, int n, int vmax, int img_w,
+                   int img_h, int class_num, const float* anchors9x2, float* y_true_1, float* y_true_2,
+                   float* y_true_3, void* stream);
+/* letterbox_resize(img, new_w, new_h, interp=0) (utils/data_aug.py:274-293) + BGR->RGB + float32 / 255
+ * (test_single_image.py:39-46): uint8 BGR [src_h, src_w, 3] (row pitch in bytes) -> float32 RGB [new_h, new_w, 3].
+ * yb_letterbox_params returns the host-side scalars of the same call (resize_ratio, resized size, dh, dw). */
+int yb_letterbox_params(int src_h, int src_w, int new_h, int new_w, double* resize_ratio, int* resize_h, int* resize_w,
+                        int* dh, int* dw);
+int yb_letterbox_normalize(const uint8_t* bgr, int src_h, int src_w, long src_pitch_bytes, int new_h, int new_w,
+                           float* out_rgb, void* stream);
 
 /* Weight repack (utils/misc_utils.py:114-123 does (Cout,Cin,kh,kw) -> HWIO on the host):
  * src float32 in `layout` -> dst `dtype` (or float32) OHWI [cout_pad,k,k,cin], rows >= cout zeroed. */

@@ -758,3 +758,26 @@ def load_darknet_weights(path, class_num=80):
         params.append(p)
     assert ptr == ws.size, (ptr, ws.size)
     return params
+
+
+# --------------------------------------------------------------------------------------
+# Pre-processing (utils/data_aug.py:274-293 letterbox_resize with interp=0; test_single_image.py:44-46)
+# --------------------------------------------------------------------------------------
+def letterbox_preprocess(img_bgr_u8, new_width, new_height):
+    """letterbox_resize(img, new_width, new_height, interp=0) -> cvtColor(BGR2RGB) -> float32 / 255, in numpy.
+    [TF-free] OpenCV's nearest-neighbour resize restated: src index = min(floor(dst * (1 / (dst_size / src_size))),
+    src_size - 1), computed in double (modules/imgproc/src/resize.cpp: resizeNN).
+    Returns (x [1, new_height, new_width, 3] float32 RGB in [0, 1], resize_ratio, dw, dh)."""
+    img = np.asarray(img_bgr_u8, np.uint8)
+    ori_h, ori_w = img.shape[:2]
+    ratio = min(new_width / ori_w, new_height / ori_h)                            # :280
+    rw, rh = int(ratio * ori_w), int(ratio * ori_h)                               # :282-283
+    ifx, ify = 1.0 / (rw / ori_w), 1.0 / (rh / ori_h)
+    sx = np.minimum(np.floor(np.arange(rw) * ifx).astype(np.int64), ori_w - 1)
+    sy = np.minimum(np.floor(np.arange(rh) * ify).astype(np.int64), ori_h - 1)
+    resized = img[sy][:, sx]                                                      # cv2.resize(..., interpolation=0)
+    padded = np.full((new_height, new_width, 3), 128, np.uint8)                   # :286
+    dw, dh = int((new_width - rw) / 2), int((new_height - rh) / 2)                # :288-289
+    padded[dh: rh + dh, dw: rw + dw, :] = resized                                 # :291
+    x = padded[..., ::-1].astype(F32)                                             # BGR -> RGB, np.asarray(img, np.float32)
+    return (x[np.newaxis] / F32(255.0)).astype(F32), ratio, dw, dh

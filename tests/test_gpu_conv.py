@@ -12,20 +12,23 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["1cta", "2cta", "mc", "1cta-reg", "2cta-reg"], autouse=True)
+@pytest.fixture(params=["1cta", "2cta", "mc", "1cta-reg", "2cta-reg", "1cta-eg1", "2cta-eg1", "1cta-eg2", "2cta-eg2"], autouse=True)
 def conv_mode(request):
     """Every conv test runs against the three tcgen05 kernels: cta_group::1 (128-row tiles), cta_group::2 (a CTA
     pair per 256-row tile) and the cluster-multicast pair kernel (2x2 / 2x1 pairs; only 256-wide tiles take it,
     the other shapes fall back to the plain pair kernel), and — for the first two — against both epilogues: the
-    shared-memory + TMA-store one (default) and the register-store one of round 1 ("-reg").  The library's option
+    TMA-store / TMA-residual one (default) and the register-store one of round 1 ("-reg"), and with one ("-eg1") or —
+    wherever a kernel exists — two ("-eg2") groups of epilogue warps (the default picks two for 1x1 and Cin <= 64
+    layers).  The library's option
     table (yb_set_option) overrides the heuristics; it is restored after each test."""
     L = _lib()
     mode, _, epi = request.param.partition("-")
     L.set_option("YB_CONV_MODE", "2cta" if mode == "mc" else mode)
     L.set_option("YB_CONV_MC", "1" if mode == "mc" else "0")
     L.set_option("YB_CONV_EPI", "reg" if epi == "reg" else None)
+    L.set_option("YB_CONV_EG", epi[2:] if epi.startswith("eg") else None)
     yield request.param
-    for k in ("YB_CONV_MODE", "YB_CONV_MC", "YB_CONV_EPI"):
+    for k in ("YB_CONV_MODE", "YB_CONV_MC", "YB_CONV_EPI", "YB_CONV_EG"):
         L.set_option(k, None)
 
 
@@ -35,7 +38,7 @@ def _lib():
 
 
 def _run_conv(n, h, w, cin, cout, k, s, dtype=torch.float16, in_extra=0, out_extra=0, residual=False, upsample=False,
-              out_fp32=False, leaky=True, stats=False, seed=0):
+              out_fp32=False, leaky=True, stats=False, seed=0, halo=False):
     L = _lib()
     lib, check, ptr, st = L.lib, L.check, L.ptr, L.stream_handle
     dev = "cuda"
@@ -69,7 +72,11 @@ def _run_conv(n, h, w, cin, cout, k, s, dtype=torch.float16, in_extra=0, out_ext
     ssq = torch.zeros(cout_pad, device=dev) if stats else None
     xp = C.c_void_p(xfull.data_ptr() + in_off * 2)
     op = C.c_void_p(outfull.data_ptr() + out_off * esz)
-    check(lib.yb_conv2d_fwd(C.byref(d), xp, ptr(wp), ptr(sc), ptr(sh), ptr(res), op, ptr(ssum), ptr(ssq), st()), "conv")
+    if halo:
+        assert lib.yb_conv3x3_halo_supported(C.byref(d)) == 1
+        check(lib.yb_conv3x3_halo_fwd(C.byref(d), xp, ptr(wp), ptr(sc), ptr(sh), ptr(res), op, st()), "conv_halo")
+    else:
+        check(lib.yb_conv2d_fwd(C.byref(d), xp, ptr(wp), ptr(sc), ptr(sh), ptr(res), op, ptr(ssum), ptr(ssq), st()), "conv")
     torch.cuda.synchronize()
     # ---- reference (fp32 math on the rounded operands) ----
     xr = x.float().permute(0, 3, 1, 2)
@@ -295,3 +302,34 @@ def test_stem_conv_tensor_core(dtype, conv_mode):
     eps = 2.0 ** -9 if dtype == torch.float16 else 2.0 ** -6
     err = (out.float() - ref).abs()
     assert torch.all(err <= eps * torch.clamp(ref.abs(), min=1.0)), float(err.max())
+
+
+# ------------------------------------------------------------------------- halo-tile tcgen05 conv (csrc/conv_halo.cu)
+@pytest.mark.parametrize("n,h,w,cin,cout,s,res,dtype", [
+    (2, 32, 16, 64, 128, 1, False, torch.float16),      # exact tiles
+    (2, 32, 16, 32, 64, 1, True, torch.float16),
+    (3, 40, 24, 64, 128, 1, True, torch.float16),       # partial bottom tile (40 = 2.5 x 16), several tiles per CTA row
+    (2, 104, 104, 64, 128, 1, True, torch.bfloat16),    # the 416-input layer 6 / 8 geometry (6.5 tile rows)
+    (1, 208, 208, 32, 64, 1, True, torch.float16),      # layer 3 geometry
+    (2, 64, 32, 32, 64, 2, False, torch.float16),       # stride 2: four parity planes
+    (3, 80, 48, 32, 64, 2, False, torch.bfloat16),      # stride 2, partial bottom tile (40 rows out)
+    (2, 64, 32, 64, 64, 2, False, torch.float16),
+    (1, 416, 416, 32, 64, 2, False, torch.float16),     # layer 1 geometry
+    (2, 48, 40, 32, 128, 1, False, torch.float16),
+    (2, 32, 16, 64, 64, 1, True, torch.bfloat16),
+])
+def test_conv3x3_halo(n, h, w, cin, cout, s, res, dtype, conv_mode):
+    if conv_mode != "1cta":
+        pytest.skip("independent of the igemm kernel selection")
+    _run_conv(n, h, w, cin, cout, 3, s, dtype=dtype, residual=res, halo=True)
+    _run_conv(n, h, w, cin, cout, 3, s, dtype=dtype, residual=res, halo=True, in_extra=16, out_extra=32, seed=3)
+
+
+def test_conv3x3_halo_rejects_unsupported():
+    L = _lib()
+    d = L.ConvDesc(n=1, h=26, w=26, cin=256, cout=512, ksize=3, stride=1, in_ld=256, out_ld=512, res_ld=0, dtype=0,
+                   out_fp32=0, leaky=1, upsample2x=0)
+    assert L.lib.yb_conv3x3_halo_supported(C.byref(d)) == 0
+    d2 = L.ConvDesc(n=1, h=20, w=20, cin=64, cout=128, ksize=3, stride=1, in_ld=64, out_ld=128, res_ld=0, dtype=0,
+                    out_fp32=0, leaky=1, upsample2x=0)
+    assert L.lib.yb_conv3x3_halo_supported(C.byref(d2)) == 0          # 20 % 8 != 0

@@ -184,3 +184,28 @@ def test_c_nms_oracle_equals_numpy_oracle(golden_dir):
             assert np.array_equal(x, y)
     b = O.gpu_nms_c(g["boxes_in"][None], g["scores_in"][None], 6, 20, 0.3, 0.45)
     assert np.array_equal(b[0], g["gpu_boxes"]) and np.array_equal(b[2], g["gpu_labels"])
+
+
+def test_letterbox_preprocess_matches_reference(golden_dir):
+    """oracle.letterbox_preprocess (numpy restatement of cv2's nearest-neighbour resize) vs the reference's own
+    letterbox_resize + BGR2RGB + /255 run over OpenCV (tests/golden/make_golden_preprocess.py): bit-exact."""
+    g = _load(golden_dir, "preprocess.npz")
+    for i, (sh, sw, nw, nh) in enumerate(g["letterbox_cases"]):
+        x, ratio, dw, dh = O.letterbox_preprocess(g[f"lb_src{i}"], int(nw), int(nh))
+        assert np.array_equal(x, g[f"lb_out{i}"])
+        assert (ratio, dw, dh) == tuple(g[f"lb_meta{i}"].tolist())
+
+
+def test_process_box_collisions_match_reference(golden_dir):
+    g = _load(golden_dir, "preprocess.npz")
+    W, H, C = (int(v) for v in g["pb_shape"])
+    ys = [[], [], []]
+    for i in range(3):
+        y = O.process_box(g[f"pb_boxes{i}"], g[f"pb_labels{i}"], [W, H], C, O.COCO_ANCHORS)
+        for j in range(3):
+            ys[j].append(y[j])
+    for j, name in enumerate(("y13", "y26", "y52")):
+        y = np.stack(ys[j], 0)
+        ref = np.zeros(tuple(g[f"pb_{name}_shape"]), np.float32); ref[..., -1] = 1.0
+        ref.reshape(-1)[g[f"pb_{name}_idx"]] = g[f"pb_{name}_val"]
+        assert np.array_equal(y, ref)

@@ -21,12 +21,15 @@ for i in range(iters + 2):
     flush.zero_()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    L.check(L.lib.yb_conv2d_fwd(C.byref(d), L.ptr(x), L.ptr(wp), L.ptr(sc), L.ptr(sh), L.ptr(res), L.ptr(out), None, None, L.stream_handle()), "conv")
+    if os.environ.get("YB_PROBE_HALO") == "1":
+        L.check(L.lib.yb_conv3x3_halo_fwd(C.byref(d), L.ptr(x), L.ptr(wp), L.ptr(sc), L.ptr(sh), L.ptr(res), L.ptr(out), L.stream_handle()), "conv_halo")
+    else:
+        L.check(L.lib.yb_conv2d_fwd(C.byref(d), L.ptr(x), L.ptr(wp), L.ptr(sc), L.ptr(sh), L.ptr(res), L.ptr(out), None, None, L.stream_handle()), "conv")
     b.record(); torch.cuda.synchronize()
     if i >= 2: ts.append(a.elapsed_time(b) * 1e3)
 ts.sort()
 fl = 2.0 * n * (h // s) * (w // s) * cout * cin * k * k
 byt = 2.0 * n * (h * w * cin + (h // s) * (w // s) * cout * (2 if with_res else 1))
-opts = " ".join(f"{k_[3:]}={L.get_option(k_)}" for k_ in ("YB_CONV_DBG", "YB_CONV_MODE", "YB_CONV_EPI", "YB_CONV_BRES", "YB_CONV_KPS") if L.get_option(k_))
+opts = ("HALO " if os.environ.get("YB_PROBE_HALO") == "1" else "") + " ".join(f"{k_[3:]}={L.get_option(k_)}" for k_ in ("YB_CONV_DBG", "YB_CONV_MODE", "YB_CONV_EPI", "YB_CONV_BRES", "YB_CONV_KPS", "YB_CONV_EG") if L.get_option(k_))
 print(f"[{opts}] n{n} {h}x{w} {cin}->{cout} k{k}s{s}{' +res' if with_res else ''}: median {ts[len(ts)//2]:.1f} us  min {ts[0]:.1f} us  "
       f"{fl/ts[len(ts)//2]/1e6:.0f} TFLOP/s  {byt/ts[len(ts)//2]/1e3:.0f} GB/s(alg)")

@@ -1,0 +1,50 @@
+#!/bin/bash
+# round-2 GPU session 10: direct 256-bit store epilogue
+mkdir -p gpurun_out
+cd "$(dirname "$0")/.."
+echo "=== tests"
+timeout 900 python -m pytest tests/test_gpu_conv.py -m gpu -q -p no:cacheprovider --tb=short -x 2>&1 | tail -25 > gpurun_out/r02_10_tests.log; tail -12 gpurun_out/r02_10_tests.log | cut -c1-300
+timeout 900 python -m pytest tests/test_gpu_train_ops.py -m gpu -q -p no:cacheprovider --tb=short 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_gpu_path.py -m gpu -q -p no:cacheprovider --tb=short -k "detect or forward_matches or nms_bit_exact or train_step_frozen" 2>&1 | tail -5
+echo "=== traces"
+T=gpurun_out/r02_10_traces.txt; : > $T
+trace() { timeout 120 python tools/conv_trace.py "$@" 2>&1 | head -9 >> $T; }
+trace 64 52 52 256 128 1 1
+YB_CONV_EG=1 trace 64 52 52 256 128 1 1
+trace 64 104 104 128 64 1 1
+cut -c1-250 $T
+echo "=== probes"
+P=gpurun_out/r02_10_probes.txt; : > $P
+probe() { timeout 120 python tools/conv_probe.py "$@" >> $P 2>&1; }
+for eg in 0 1; do
+[ $eg = 1 ] && export YB_CONV_EG=1
+probe 64 52 52 256 128 1 1
+probe 64 26 26 512 256 1 1
+probe 64 13 13 1024 512 1 1
+probe 64 104 104 128 64 1 1
+probe 64 208 208 64 32 1 1
+probe 64 104 104 64 128 3 1 10 res
+probe 64 208 208 32 64 3 1 10 res
+probe 64 416 416 32 64 3 2
+probe 64 208 208 64 128 3 2
+done
+unset YB_CONV_EG
+probe 64 52 52 128 256 3 1 10 res
+probe 64 26 26 256 512 3 1 10 res
+probe 64 13 13 512 1024 3 1 10 res
+YB_CONV_EPI=tma probe 64 52 52 128 256 3 1 10 res
+YB_CONV_EPI=tma probe 64 26 26 256 512 3 1 10 res
+YB_CONV_EPI=tma probe 64 52 52 256 128 1 1
+cat $P
+echo "=== bench"
+for eg in "" 1; do
+YB_CONV_EG=$eg timeout 900 python bench.py --no-cpu-baseline --steps 10 --no-train608 > gpurun_out/r02_10_bench_eg$eg.json 2> gpurun_out/r02_10_bench.err; tail -c 600 gpurun_out/r02_10_bench.err
+python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/r02_10_bench_eg$eg.json").read().strip().splitlines()[-1])
+    r=d["roofline"]
+    print("eg=$eg value", d["value"], "ms", d["ms_per_step"], "e2e", d["e2e"]["value"], "roof", r["frac"], "conv ms", r["ms_per_step_conv"], "stem", r["ms_per_step_stem"], "nms", r["ms_per_step_nms"], "unfused", d["unfused_api_ms_per_step"], "train", d["train"]["ms_per_step"], "lat", d["latency_batch1"]["ms_median"])
+except Exception as e: print("bench parse failed", e)
+PY
+done

@@ -1,0 +1,56 @@
+#!/bin/bash
+# round-2 GPU session 6: four TMEM loads in flight; halo-tile conv kernel
+mkdir -p gpurun_out
+cd "$(dirname "$0")/.."
+echo "=== tests"
+timeout 900 python -m pytest tests/test_gpu_conv.py -m gpu -q -p no:cacheprovider --tb=short -x 2>&1 | tail -40 > gpurun_out/r02_6_tests.log; tail -25 gpurun_out/r02_6_tests.log | cut -c1-300
+timeout 600 python -m pytest tests/test_gpu_preprocess.py -m gpu -q -p no:cacheprovider --tb=short 2>&1 | tail -15 | cut -c1-250
+timeout 900 python -m pytest tests/test_gpu_train_ops.py -m gpu -q -p no:cacheprovider --tb=short 2>&1 | tail -5
+timeout 900 python -m pytest tests/test_gpu_path.py -m gpu -q -p no:cacheprovider --tb=short -k "detect or forward_matches or nms_bit_exact" 2>&1 | tail -5
+echo "=== traces"
+T=gpurun_out/r02_6_traces.txt; : > $T
+trace() { timeout 120 python tools/conv_trace.py "$@" 2>&1 | head -9 >> $T; }
+trace 64 52 52 256 128 1 1
+YB_CONV_DBG=7 trace 64 52 52 256 128 1 1
+trace 64 104 104 128 64 1 1
+YB_CONV_MODE=1cta trace 64 52 52 128 256 3 1 res
+cut -c1-250 $T
+echo "=== probes"
+P=gpurun_out/r02_6_probes.txt; : > $P
+probe() { timeout 120 python tools/conv_probe.py "$@" >> $P 2>&1; }
+probe 64 52 52 256 128 1 1
+probe 64 26 26 512 256 1 1
+probe 64 13 13 1024 512 1 1
+probe 64 104 104 128 64 1 1
+probe 64 208 208 64 32 1 1
+probe 64 52 52 128 256 3 1 10 res
+probe 64 26 26 256 512 3 1 10 res
+probe 64 13 13 512 1024 3 1 10 res
+probe 64 104 104 64 128 3 1 10 res
+probe 64 208 208 32 64 3 1 10 res
+probe 64 416 416 32 64 3 2
+probe 64 208 208 64 128 3 2
+YB_CONV_EPI=reg probe 64 52 52 256 128 1 1
+YB_CONV_EPI=reg probe 64 208 208 64 32 1 1
+YB_CONV_EPI=reg probe 64 104 104 128 64 1 1
+YB_CONV_BRES=1 probe 64 52 52 256 128 1 1
+YB_CONV_BRES=1 probe 64 104 104 128 64 1 1
+export YB_PROBE_HALO=1
+probe 64 104 104 64 128 3 1 10 res
+probe 64 208 208 32 64 3 1 10 res
+probe 64 416 416 32 64 3 2
+probe 64 208 208 64 64 3 1
+unset YB_PROBE_HALO
+cat $P
+echo "=== bench"
+for halo in 0 1; do
+YB_HALO=$halo timeout 900 python bench.py --no-cpu-baseline --steps 10 --no-train608 > gpurun_out/r02_6_bench_halo$halo.json 2> gpurun_out/r02_6_bench.err; tail -c 600 gpurun_out/r02_6_bench.err
+python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/r02_6_bench_halo$halo.json").read().strip().splitlines()[-1])
+    r=d["roofline"]
+    print("halo=$halo value", d["value"], "ms", d["ms_per_step"], "e2e", d["e2e"]["value"], "roof", r["frac"], "conv ms", r["ms_per_step_conv"], "stem", r["ms_per_step_stem"], "nms", r["ms_per_step_nms"], "unfused", d["unfused_api_ms_per_step"], "train", d["train"]["ms_per_step"], "lat", d["latency_batch1"]["ms_median"], "det", d["detections_per_step"])
+except Exception as e: print("bench parse failed", e)
+PY
+done

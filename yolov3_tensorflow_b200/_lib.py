@@ -57,7 +57,12 @@ _SIGS = {
     "yb_debug_set_conv_trace": ([vp], i32),
     "yb_stem_conv_fwd": ([vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp], i32),
     "yb_conv3x3_thin_fwd": ([C.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp], i32),
+    "yb_conv3x3_halo_supported": ([C.POINTER(ConvDesc)], i32),
+    "yb_conv3x3_halo_fwd": ([C.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp], i32),
     "yb_stem_conv_fwd_tc": ([vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp], i32),
+    "yb_process_box": ([vp, vp, vp, i32, i32, i32, i32, i32, C.POINTER(f32), vp, vp, vp, vp], i32),
+    "yb_letterbox_params": ([i32, i32, i32, i32, C.POINTER(C.c_double), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)], i32),
+    "yb_letterbox_normalize": ([vp, i32, i32, C.c_long, i32, i32, vp, vp], i32),
     "yb_pack_conv_weights": ([vp, i32, i32, i32, i32, i32, i32, vp, vp], i32),
     "yb_bn_fold": ([vp, vp, vp, vp, i32, f32, vp, vp, vp], i32),
     "yb_conv2d_wgrad": ([C.POINTER(ConvDesc), vp, vp, i32, i32, vp, vp], i32),

@@ -15,6 +15,7 @@ struct ConvParams {
   int im2col;             // 1: A via im2col TMA, 0: A via 2D tiled TMA
   int two_cta;            // 1: cta_group::2 kernel (256-row tiles per CTA pair)
   int b_resident;         // 1-CTA kernel: the whole [BN, K] weight tile stays in shared memory (single n-tile, fits)
+  int epi_groups;         // 1 | 2 sets of four epilogue warps (2: two tiles' epilogues run concurrently; short-K layers)
   int kps;                // 1-CTA kernel: k-blocks per barrier phase (one empty/full handshake per kps k-blocks)
   int dbg;                // timing experiments only (YB_CONV_DBG bitmask: 1 skip A loads, 2 skip B loads, 4 skip MMAs)
   int mc_m, mc_n;         // cluster of mc_m x mc_n pairs with TMA multicast (1,1: plain pair kernel)
@@ -46,6 +47,24 @@ int conv_prepare_win(const yb_conv_desc* d, int kh, int kw, int scatter, const v
                      CUtensorMap* tmB, ConvParams* p, int* cout_pad_out);
 int conv_prepare_det(const yb_conv_desc* d, int class_num, const void* x, const void* w_packed, const float* scale,
                      const float* shift, CUtensorMap* tmA, CUtensorMap* tmB, ConvParams* p, int* cout_pad_out);
+// halo-tile conv for the Cin <= 64 3x3 layers (csrc/conv_halo.cu)
+struct HaloMaps { CUtensorMap plane[4]; CUtensorMap w; };
+struct HaloParams {
+  int n, ho, wo;               // output geometry
+  int tiles_x, tiles_y, num_tiles;
+  int cout;
+  int leaky;
+  const float* scale;
+  const float* shift;
+  const void* res;             // nullable, [n, ho, wo, res_ld]
+  long res_ld;
+  void* out;                   // [n, ho, wo, out_ld]
+  long out_ld;
+};
+bool conv_halo_supported(const yb_conv_desc* d);
+int conv_halo_prepare(const yb_conv_desc* d, const void* x, const void* w_packed, const float* scale, const float* shift,
+                      const void* res, void* out, HaloMaps* maps, HaloParams* p);
+int conv_halo_launch(const yb_conv_desc* d, const HaloMaps& maps, const HaloParams& p, cudaStream_t st);
 int conv_launch(int dtype, int cout_pad, const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p,
                 cudaStream_t st);
 

@@ -32,8 +32,15 @@ namespace yb {
 
 static constexpr int BLOCK_M = 128;
 static constexpr int UMMA_K = 16;
-static constexpr int NUM_THREADS = 192;
-static constexpr int SMEM_BUDGET = 192 * 1024;  // operand ring (6 x 32 KB / 8 x 24 KB stages); the rest of the 227 KB is below
+static constexpr int NUM_THREADS = 192;         // warp 0 producer, warp 1 MMA, warps 2..5 epilogue (one epilogue group)
+// Epilogue groups (EG): with ONE warp per scheduler the epilogue's ~200 instructions per 32-column chunk issue at
+// IPC ~0.2 (fixed-latency dependencies and nothing to switch to: ~1100 cycles per chunk, profiles/r02_c) and pace every
+// short-K layer.  EG = 2 adds a second set of four epilogue warps: group g drains accumulator stage g (tiles with
+// iteration % 2 == g), so two tiles' epilogues run concurrently, two warps per scheduler.  Its staging tiles cost one
+// operand stage.
+__host__ __device__ constexpr int nthreads(int eg) { return 64 + 128 * eg; }
+__host__ __device__ constexpr int ring_budget(int eg) { return eg == 1 ? 192 * 1024 : 160 * 1024; }   // operand ring
+static constexpr int SMEM_BUDGET = ring_budget(1);
 // Per-epilogue-warp staging: three 2 KB [32 rows][32 channels] SWIZZLE_64B tiles that rotate between the TMA residual
 // load, the in-place epilogue and the TMA store of a chunk (or one 32x33 fp32 transpose tile for the detection heads).
 static constexpr int EPI_TILE_BYTES = 2048;
@@ -42,19 +49,20 @@ static constexpr int STAGE_BYTES_W = EPI_TILES * EPI_TILE_BYTES;   // 6144 = 12 
 static constexpr int STAGE_FLOATS = STAGE_BYTES_W / 4;
 static constexpr int BAR_BYTES = 512;           // pipeline barriers + 4 x 3 residual barriers + TMEM slot
 
-template <int BN, int BK>
+template <int BN, int BK, int EG = 1>
 struct Cfg {
   static constexpr int A_BYTES = BLOCK_M * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
+  static constexpr int RING = ring_budget(EG);
+  static constexpr int STAGES = (RING / STAGE_BYTES) > 8 ? 8 : (RING / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BN;  // power of two >= 32 for BN in {64,128,256}
-  static constexpr int SMEM_BYTES = SMEM_BUDGET + 1024 /*align*/ + 4 * STAGE_BYTES_W + BAR_BYTES + 4 * BN * 4;
+  static constexpr int SMEM_BYTES = RING + 1024 /*align*/ + 4 * EG * STAGE_BYTES_W + BAR_BYTES + (2 + 2 * EG) * BN * 4;
   static constexpr uint32_t SWIZZLE = (BK == 64) ? 2u : 4u;   // UMMA layout_type: 128B / 64B
   static constexpr uint32_t SBO = 8 * BK * 2;                  // bytes between 8-row groups
 };
 
-// debugging aid: CTA 0 stamps clock64 into p.trace[(role * 64 + tile iteration) * 32 + slot] (tools/conv_trace.py)
+// debugging aid: CTA 0 stamps clock64 into p.trace[(role * 64 + tile iteration) * 32 + slot], role = warp 0..9 (tools/conv_trace.py)
 __device__ __forceinline__ void trace_stamp(const ConvParams& p, int role, int it, int slot) {
   if (p.trace != nullptr && blockIdx.x == 0 && it < 64) p.trace[(role * 64 + it) * 32 + slot] = clock64();
 }
@@ -69,7 +77,7 @@ __device__ __forceinline__ void tile_coords(const ConvParams& p, int tile, int& 
 // executed by the 128 epilogue threads together (named barrier 1)
 template <int BN>
 __device__ __forceinline__ void stat_flush(const ConvParams& p, float* s_stat, int n0, int et /*0..127*/) {
-  asm volatile("bar.sync 1, 128;" ::: "memory");
+  asm volatile("bar.sync 1, 128;" ::: "memory");   // (statistics only run with one epilogue group)
   for (int c = et; c < BN; c += 128) {
     if (n0 + c < p.cout) {
       atomicAdd(p.stat_sum + n0 + c, s_stat[c]);
@@ -83,13 +91,13 @@ __device__ __forceinline__ void stat_flush(const ConvParams& p, float* s_stat, i
 
 // executed by the 128 epilogue threads together: (re)load the n-tile's scale/shift into shared memory
 template <int BN>
-__device__ __forceinline__ void load_scale_shift(const ConvParams& p, float* s_ss, int n0, int et /*0..127*/) {
-  asm volatile("bar.sync 1, 128;" ::: "memory");          // nobody still reads the previous n-tile's values
+__device__ __forceinline__ void load_scale_shift(const ConvParams& p, float* s_ss, int n0, int et /*0..127*/, int group = 0) {
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");   // nobody of this group still reads the previous n-tile's values
   for (int c = et; c < BN; c += 128) {
     s_ss[c] = p.scale ? __ldg(p.scale + n0 + c) : 1.f;      // scale = shift = NULL: identity (dgrad convs)
     s_ss[BN + c] = p.shift ? __ldg(p.shift + n0 + c) : 0.f;
   }
-  asm volatile("bar.sync 1, 128;" ::: "memory");
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -225,6 +233,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const int row
   constexpr int NCH = BN / 32;
   const int nvalid = min(NCH, (p.cout - n0 + 31) >> 5);      // zero-padded weight rows (cout_pad > cout): nothing to store
   if (nvalid <= 0) return;
+  // chunk c + 1's TMEM load is in flight while chunk c is processed (two buffers: tcgen05.ld itself is fast — 90 cycles
+  // per 32 columns, tools/probes/tmem_ld_probe.cu — more loads in flight bought nothing and cost 64 registers)
   uint32_t ra[32], rb[32];
   tmem_ld_32x32(t_row, ra);
 #pragma unroll 1
@@ -297,20 +307,6 @@ __device__ __forceinline__ void epi_tma_chunk(const ConvParams& p, const uint32_
     }
     if (last) st.prefetched = go;
   }
-  if (p.stat_sum != nullptr) {
-    // BN batch statistics of the raw conv output: per-CTA column sums in shared memory, flushed by the caller
-    float a[32], q[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float t = row_ok ? __uint_as_float(r[j]) : 0.f;
-      a[j] = t;
-      q[j] = t * t;
-    }
-    const float cs = warp_col_sum32(a, lane);
-    const float cs2 = warp_col_sum32(q, lane);
-    atomicAdd(&s_stat[ch * 32 + lane], cs);
-    atomicAdd(&s_stat[BN + ch * 32 + lane], cs2);
-  }
   float v[32];
   const float4* sc4 = reinterpret_cast<const float4*>(s_ss + ch * 32);
   const float4* sh4 = reinterpret_cast<const float4*>(s_ss + BN + ch * 32);
@@ -339,26 +335,36 @@ __device__ __forceinline__ void epi_tma_chunk(const ConvParams& p, const uint32_
       f = Pack2<T>::unpack(u.z); v[8 * j + 4] += f.x; v[8 * j + 5] += f.y;
       f = Pack2<T>::unpack(u.w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
     }
-  } else {                                       // the store that last read this tile (3 chunks ago) has drained
+  } else if (!(p.dbg & 16)) {                    // the store that last read this tile (3 chunks ago) has drained
     if (lane == 0) bulk_wait_group_read<EPI_TILES - 1>();
     __syncwarp();
   }
+  // (ablation switches, timing only: dbg & 32 no staging stores, dbg & 16 no fence / TMA store)
+  if (!(p.dbg & 32)) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint4 pk;
-    pk.x = Pack2<T>::pack(v[8 * j + 0], v[8 * j + 1]);
-    pk.y = Pack2<T>::pack(v[8 * j + 2], v[8 * j + 3]);
-    pk.z = Pack2<T>::pack(v[8 * j + 4], v[8 * j + 5]);
-    pk.w = Pack2<T>::pack(v[8 * j + 6], v[8 * j + 7]);
-    rowp[j ^ sw] = pk;
+    for (int j = 0; j < 4; ++j) {
+      uint4 pk;
+      pk.x = Pack2<T>::pack(v[8 * j + 0], v[8 * j + 1]);
+      pk.y = Pack2<T>::pack(v[8 * j + 2], v[8 * j + 3]);
+      pk.z = Pack2<T>::pack(v[8 * j + 4], v[8 * j + 5]);
+      pk.w = Pack2<T>::pack(v[8 * j + 6], v[8 * j + 7]);
+      rowp[j ^ sw] = pk;
+    }
+  } else {
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc += v[j];
+    if (acc == 123.456f) rowp[0] = make_uint4(1u, 2u, 3u, 4u);     // keeps the arithmetic alive
   }
-  fence_proxy_async();                           // generic-proxy writes -> visible to the TMA (async proxy)
-  __syncwarp();
-  if (lane == 0) {
-    tma_store_2d(&p.tmO, buf, n0 + ch * 32, m0w);
-    bulk_commit_group();
-    trace_stamp(p, tr_role, tr_it, 4 + 3 * (ch & 7));
+  if (!(p.dbg & 16)) {
+    fence_proxy_async();                         // generic-proxy writes -> visible to the TMA (async proxy)
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(&p.tmO, buf, n0 + ch * 32, m0w);
+      bulk_commit_group();
+    }
   }
+  if (lane == 0) trace_stamp(p, tr_role, tr_it, 4 + 3 * (ch & 7));
   ++st.cnt;
 }
 
@@ -373,14 +379,14 @@ __device__ __forceinline__ void epilogue_tile_tma(const ConvParams& p, const int
   constexpr int NCH = BN / 32;
   const int nvalid = min(NCH, (p.cout - n0) >> 5);           // zero-padded weight rows (cout_pad > cout) are not stored
   if (nvalid <= 0) return;
-  uint32_t ra[32], rb[32];
-  tmem_ld_32x32(t_row, ra);
   if (has_res && !st.prefetched && lane == 0) {  // first chunk of the run: nobody fetched its residual ahead of time
     bulk_wait_group_read<EPI_TILES - 1>();
     const uint32_t b = st.cnt % EPI_TILES;
     mbar_arrive_expect_tx(&st.res_bar[b], EPI_TILE_BYTES);
     tma_load_2d(st.stage + b * EPI_TILE_BYTES, &p.tmR, &st.res_bar[b], n0, m0w);
   }
+  uint32_t ra[32], rb[32];                       // two TMEM read buffers (see epilogue_tile)
+  tmem_ld_32x32(t_row, ra);
 #pragma unroll 1
   for (int ch = 0; ch < nvalid; ch += 2) {
     if (lane == 0) trace_stamp(p, tr_role, tr_it, 2 + 3 * (ch & 7));
@@ -513,13 +519,15 @@ __device__ __forceinline__ void epilogue_tile_detect(const ConvParams& p, const 
   }
 }
 
-template <typename T, int BN, int BK>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <typename T, int BN, int BK, int EG = 1>
+__global__ void __launch_bounds__(nthreads(EG), 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ ConvParams p) {
-  using C = Cfg<BN, BK>;
+  using C = Cfg<BN, BK, EG>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by POINTER ARITHMETIC on the __shared__ array: an integer round trip makes the pointer generic,
+  // and every staging-tile access then compiles to LD.E / ST.E + MEMBAR.ALL.CTA instead of LDS / STS (profiles/r02_b)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int kb_per_tap_ = p.cin / BK;
   const int num_kb_ = p.kh * p.kw * kb_per_tap_;
   // operand ring: [nst x A][nst x B], or with resident weights [nst x A][num_kb x B] (B loaded once per CTA)
@@ -527,29 +535,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int kps = p.kps;                 // slots per barrier group (1: one handshake per k-block)
   if (kps > 1) nst = (C::STAGES / kps);  // number of groups; slot index = group * kps + j
   if (p.b_resident) {
-    nst = (SMEM_BUDGET - num_kb_ * C::B_BYTES) / C::A_BYTES;
+    nst = (C::RING - num_kb_ * C::B_BYTES) / C::A_BYTES;
     if (nst > 8) nst = 8;
   }
   uint8_t* sA = smem;
   uint8_t* sB = smem + nst * (kps > 1 ? kps : 1) * C::A_BYTES;
-  float* stage_base = reinterpret_cast<float*>(smem + SMEM_BUDGET);          // 4 x STAGE_BYTES_W, 1024-aligned
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BUDGET + 4 * STAGE_BYTES_W);
+  float* stage_base = reinterpret_cast<float*>(smem + C::RING);              // 4 * EG x STAGE_BYTES_W, 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::RING + 4 * EG * STAGE_BYTES_W);
   uint64_t* full_bar = bars;                       // [<=8] TMA -> MMA
   uint64_t* empty_bar = bars + 8;                  // [<=8] MMA -> TMA
   uint64_t* tfull_bar = bars + 16;                 // [2] MMA -> epilogue
   uint64_t* tempty_bar = bars + 18;                // [2] epilogue -> MMA
   uint64_t* bres_bar = bars + 20;                  // resident weights landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
-  uint64_t* res_bar = bars + 32;                   // [4 warps][EPI_TILES] residual tile landed (TMA)
-  float* s_stat = reinterpret_cast<float*>(smem + SMEM_BUDGET + 4 * STAGE_BYTES_W + BAR_BYTES);   // [2][BN] per-CTA column sums / sums of squares
-  float* s_ss = s_stat + 2 * BN;                   // [2][BN] scale / shift of the current n-tile
+  uint64_t* res_bar = bars + 32;                   // [4 * EG warps][EPI_TILES] residual tile landed (TMA)
+  float* s_stat = reinterpret_cast<float*>(smem + C::RING + 4 * EG * STAGE_BYTES_W + BAR_BYTES);   // [2][BN] per-CTA column sums / sums of squares
+  float* s_ss = s_stat + 2 * BN;                   // [EG][2][BN] scale / shift of each epilogue group's current n-tile
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int kb_per_tap = p.cin / BK;
   const int num_kb = p.kh * p.kw * kb_per_tap;
-  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[6 * 64 * 32] = clock64();
+  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[10 * 64 * 32] = clock64();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -563,7 +571,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
     }
     mbar_init(bres_bar, 1);
-    for (int i = 0; i < 4 * EPI_TILES; ++i) mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < 4 * EG * EPI_TILES; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
@@ -571,7 +579,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[6 * 64 * 32 + 1] = clock64();
+  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[10 * 64 * 32 + 1] = clock64();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -673,16 +681,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are this warp's
-    const int et = threadIdx.x - 64;
+    const int grp = (warp - 2) >> 2;               // epilogue group: drains accumulator stage grp, tiles with iteration % EG == grp
+    const int et = (threadIdx.x - 64) & 127;
+    s_ss += grp * 2 * BN;
     int cur_n0 = -1, ss_n0 = -1;
     if (p.stat_sum != nullptr) {
       for (int c = et; c < 2 * BN; c += 128) s_stat[c] = 0.f;
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
-    int it = 0;
+    int it = grp;
     uint8_t* my_stage = reinterpret_cast<uint8_t*>(stage_base) + (warp - 2) * STAGE_BYTES_W;
     EpiTmaState epi_st{my_stage, res_bar + (warp - 2) * EPI_TILES, 0u, false};
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < num_tiles; tile += EG * gridDim.x, it += EG) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       int m_idx, n_idx;
@@ -693,10 +703,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (cur_n0 >= 0) stat_flush<BN>(p, s_stat, cur_n0, et);
         cur_n0 = n0;
       }
-      if (n0 != ss_n0) { load_scale_shift<BN>(p, s_ss, n0, et); ss_n0 = n0; }
+      if (n0 != ss_n0) { load_scale_shift<BN>(p, s_ss, n0, et, grp); ss_n0 = n0; }
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
       if (p.epi_tma) {
-        const int ntile = tile + gridDim.x;
+        const int ntile = tile + EG * gridDim.x;
         int nm = 0, nn = 0;
         if (ntile < num_tiles) tile_coords(p, ntile, nm, nn);
         if (lane == 0) trace_stamp(p, warp, it, 0);
@@ -737,37 +747,39 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // (cluster rank 0) issues the MMAs; tcgen05.commit multicasts barrier arrivals to both
 // CTAs; each CTA drains its own 128 TMEM lanes in its own epilogue warps.
 // ----------------------------------------------------------------------------------
-template <int BN, int BK>
+template <int BN, int BK, int EG = 1>
 struct Cfg2 {
   static constexpr int A_BYTES = BLOCK_M * BK * 2;         // this CTA's 128 rows
   static constexpr int B_BYTES = (BN / 2) * BK * 2;        // this CTA's half of the BN weight rows
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
+  static constexpr int STAGES = (ring_budget(EG) / STAGE_BYTES) > 8 ? 8 : (ring_budget(EG) / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 4 * STAGE_BYTES_W + BAR_BYTES + 4 * BN * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 4 * EG * STAGE_BYTES_W + BAR_BYTES + (2 + 2 * EG) * BN * 4;
   static constexpr uint32_t SWIZZLE = (BK == 64) ? 2u : 4u;
   static constexpr uint32_t SBO = 8 * BK * 2;
 };
 
-template <typename T, int BN, int BK, int DET_E = 0>   // DET_E = 5 + classes: detection head with the decode fused in
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <typename T, int BN, int BK, int DET_E = 0, int EG = 1>   // DET_E = 5 + classes: detection head with the decode fused in
+__global__ void __launch_bounds__(nthreads(EG), 1)
 conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ ConvParams p) {
-  using C = Cfg2<BN, BK>;
+  using C = Cfg2<BN, BK, EG>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by POINTER ARITHMETIC on the __shared__ array: an integer round trip makes the pointer generic,
+  // and every staging-tile access then compiles to LD.E / ST.E + MEMBAR.ALL.CTA instead of LDS / STS (profiles/r02_b)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + C::STAGES * C::A_BYTES;
-  float* stage_base = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);   // 4 x STAGE_BYTES_W, 1024-aligned
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + 4 * STAGE_BYTES_W);
+  float* stage_base = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);   // 4 * EG x STAGE_BYTES_W, 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + 4 * EG * STAGE_BYTES_W);
   uint64_t* full_bar = bars;                        // [STAGES] used in the leader only
   uint64_t* empty_bar = bars + C::STAGES;           // [STAGES] one per CTA (multicast commit)
   uint64_t* tfull_bar = bars + 2 * C::STAGES;       // [2] one per CTA (multicast commit)
   uint64_t* tempty_bar = bars + 2 * C::STAGES + 2;  // [2] used in the leader only (8 arrivals: 4 warps x 2 CTAs)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
   uint64_t* res_bar = bars + 32;                    // [4 warps][EPI_TILES] residual tile landed (TMA), CTA-local
-  float* s_stat = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 4 * STAGE_BYTES_W + BAR_BYTES);
-  float* s_ss = s_stat + 2 * BN;
+  float* s_stat = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 4 * EG * STAGE_BYTES_W + BAR_BYTES);
+  float* s_ss = s_stat + 2 * BN;                   // [EG][2][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -789,7 +801,7 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 8);
     }
-    for (int i = 0; i < 4 * EPI_TILES; ++i) mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < 4 * EG * EPI_TILES; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_2sm<C::TMEM_COLS>(tmem_slot);
@@ -873,16 +885,18 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   } else {
     // ===================== epilogue (warps 2..5, both CTAs) =====================
     const int quarter = warp & 3;
-    const int et = threadIdx.x - 64;
+    const int grp = (warp - 2) >> 2;               // epilogue group (see nthreads())
+    const int et = (threadIdx.x - 64) & 127;
+    s_ss += grp * 2 * BN;
     int cur_n0 = -1, ss_n0 = -1;
     if (p.stat_sum != nullptr) {
       for (int c = et; c < 2 * BN; c += 128) s_stat[c] = 0.f;
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
-    int it = 0;
+    int it = grp;
     uint8_t* my_stage = reinterpret_cast<uint8_t*>(stage_base) + (warp - 2) * STAGE_BYTES_W;
     EpiTmaState epi_st{my_stage, res_bar + (warp - 2) * EPI_TILES, 0u, false};
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+    for (int tile = cluster_id + grp * num_clusters; tile < num_tiles; tile += EG * num_clusters, it += EG) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       int m_idx, n_idx;
@@ -893,14 +907,14 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (cur_n0 >= 0) stat_flush<BN>(p, s_stat, cur_n0, et);
         cur_n0 = n0;
       }
-      if (n0 != ss_n0) { load_scale_shift<BN>(p, s_ss, n0, et); ss_n0 = n0; }
+      if (n0 != ss_n0) { load_scale_shift<BN>(p, s_ss, n0, et, grp); ss_n0 = n0; }
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_fence_after();
       if constexpr (DET_E > 0) {
         if (!(p.dbg & 8)) epilogue_tile_detect<BN, DET_E>(p, m0 + quarter * 32 + lane, t_row, lane, s_ss, reinterpret_cast<float*>(my_stage));
       } else if (p.epi_tma) {
-        const int ntile = tile + num_clusters;
+        const int ntile = tile + EG * num_clusters;
         int nm = 0, nn = 0;
         if (ntile < num_tiles) tile_coords(p, ntile, nm, nn);
         if (!(p.dbg & 8))
@@ -941,7 +955,9 @@ conv_igemm_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   constexpr int CSIZE = 2 * CM * CN;
   using C = Cfg2<BN, BK>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by POINTER ARITHMETIC on the __shared__ array: an integer round trip makes the pointer generic,
+  // and every staging-tile access then compiles to LD.E / ST.E + MEMBAR.ALL.CTA instead of LDS / STS (profiles/r02_b)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + C::STAGES * C::A_BYTES;
   float* stage_base = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);   // 4 x STAGE_BYTES_W, 1024-aligned
@@ -1151,6 +1167,29 @@ int make_tmap_2d(CUtensorMap* tm, const void* base, int dtype, long rows, long c
   return YB_OK;
 }
 
+// NHWC activation seen as {C, W, H, N}, TILED mode: box = box_c channels x box_w x box_h pixels of one image, traversal
+// stride `estride` along W and H (a box spanning 2 * count - 1 pixels at stride 2 loads `count` of them); pixels outside
+// the image come back zero-filled.  Used by the halo-tile conv (csrc/conv_halo.cu).
+int make_tmap_tiled4d(CUtensorMap* tm, const void* base, int dtype, int n, int h, int w, int c, long ld, int box_c,
+                      int box_w, int box_h, int estride) {
+  int rc = load_driver_entry_points();
+  if (rc) return rc;
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)w * ld * 2, (cuuint64_t)h * w * ld * 2};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
+  CUtensorMapSwizzle sw = box_c * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = g_encode_tiled(tm, tm_dtype(dtype), 4, const_cast<void*>(base), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(4d) failed (%d): n=%d h=%d w=%d c=%d ld=%ld box=%dx%dx%d stride %d", (int)r, n, h, w, c,
+              ld, box_c, box_w, box_h, estride);
+    return YB_ERR_CUDA;
+  }
+  return YB_OK;
+}
+
 // NHWC activation seen as {C, W, H, N}; im2col traversal for a ksize x ksize window with
 // symmetric padding `pad` and traversal stride `stride`; one request = 128 pixels x bk channels.
 int make_tmap_im2col_px(CUtensorMap* tm, const void* base, int dtype, int n, int h, int w, int c, long ld, int ksize,
@@ -1189,24 +1228,24 @@ int make_tmap_im2col_px(CUtensorMap* tm, const void* base, int dtype, int n, int
   return YB_OK;
 }
 
-template <typename T, int BN, int BK>
+template <typename T, int BN, int BK, int EG = 1>
 static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t st) {
-  using C = Cfg<BN, BK>;
+  using C = Cfg<BN, BK, EG>;
   static DeviceOnce once;
-  auto kern = conv_igemm_kernel<T, BN, BK>;
+  auto kern = conv_igemm_kernel<T, BN, BK, EG>;
   { const int rc = ensure_smem_attr(once, reinterpret_cast<const void*>(kern), C::SMEM_BYTES); if (rc) return rc; }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmA, tmB, p);
+  kern<<<grid, nthreads(EG), C::SMEM_BYTES, st>>>(tmA, tmB, p);
   YB_CUDA(cudaGetLastError());
   return YB_OK;
 }
 
-template <typename T, int BN, int BK, int DET_E = 0>
+template <typename T, int BN, int BK, int DET_E = 0, int EG = 1>
 static int launch_cfg2(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t st) {
-  using C = Cfg2<BN, BK>;
+  using C = Cfg2<BN, BK, EG>;
   static DeviceOnce once;
-  auto kern = conv_igemm_2cta_kernel<T, BN, BK, DET_E>;
+  auto kern = conv_igemm_2cta_kernel<T, BN, BK, DET_E, EG>;
   { const int rc = ensure_smem_attr(once, reinterpret_cast<const void*>(kern), C::SMEM_BYTES); if (rc) return rc; }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int max_clusters = num_sms() / 2;
@@ -1214,7 +1253,7 @@ static int launch_cfg2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(2 * clusters);
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(nthreads(EG));
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -1285,8 +1324,9 @@ int conv_launch(int dtype, int cout_pad, const CUtensorMap& tmA, const CUtensorM
   if (p.det.on) {
     // detection head with the decode fused in: pair kernel, one n-tile holding all 3 * E columns
     const int bn = conv_block_n2(cout_pad);
-#define YB_DISPATCH_DET(T)                                                                            \
-  if (bn == 256 && bk == 64 && p.det.E == 85) return launch_cfg2<T, 256, 64, 85>(tmA, tmB, p, st); \
+#define YB_DISPATCH_DET(T)                                                                                                  \
+  if (bn == 256 && bk == 64 && p.det.E == 85 && p.epi_groups == 2) return launch_cfg2<T, 256, 64, 85, 2>(tmA, tmB, p, st); \
+  if (bn == 256 && bk == 64 && p.det.E == 85) return launch_cfg2<T, 256, 64, 85>(tmA, tmB, p, st);                         \
   if (bn == 128 && bk == 64 && p.det.E == 25) return launch_cfg2<T, 128, 64, 25>(tmA, tmB, p, st);
     if (p.two_cta && dtype == YB_F16) { YB_DISPATCH_DET(__half) }
     else if (p.two_cta && dtype == YB_BF16) { YB_DISPATCH_DET(__nv_bfloat16) }
@@ -1297,6 +1337,7 @@ int conv_launch(int dtype, int cout_pad, const CUtensorMap& tmA, const CUtensorM
   if (p.two_cta) {
     const int bn = conv_block_n2(cout_pad);
 #define YB_DISPATCH2(T)                                                         \
+  if (bn == 256 && bk == 64 && p.epi_groups == 2) return launch_cfg2<T, 256, 64, 0, 2>(tmA, tmB, p, st); \
   if (bn == 256 && bk == 64) return launch_cfg2<T, 256, 64>(tmA, tmB, p, st); \
   if (bn == 256 && bk == 32) return launch_cfg2<T, 256, 32>(tmA, tmB, p, st); \
   if (bn == 128 && bk == 64) return launch_cfg2<T, 128, 64>(tmA, tmB, p, st); \
@@ -1309,6 +1350,9 @@ int conv_launch(int dtype, int cout_pad, const CUtensorMap& tmA, const CUtensorM
   } else {
     const int bn = conv_block_n(cout_pad);
 #define YB_DISPATCH(T)                                                         \
+  if (bn == 128 && bk == 64 && p.epi_groups == 2) return launch_cfg<T, 128, 64, 2>(tmA, tmB, p, st); \
+  if (bn == 64 && bk == 64 && p.epi_groups == 2) return launch_cfg<T, 64, 64, 2>(tmA, tmB, p, st);   \
+  if (bn == 64 && bk == 32 && p.epi_groups == 2) return launch_cfg<T, 64, 32, 2>(tmA, tmB, p, st);   \
   if (bn == 128 && bk == 64) return launch_cfg<T, 128, 64>(tmA, tmB, p, st); \
   if (bn == 128 && bk == 32) return launch_cfg<T, 128, 32>(tmA, tmB, p, st); \
   if (bn == 64 && bk == 64) return launch_cfg<T, 64, 64>(tmA, tmB, p, st);   \
@@ -1377,11 +1421,20 @@ static int conv_prepare_core(const yb_conv_desc* d, int win, int kh, int kw, int
   memset(&p->det, 0, sizeof(p->det));
   p->kps = 1;   // set below once the tile shape is known
   const int bn = two ? conv_block_n2(cout_pad) : conv_block_n(cout_pad);
+  // Two epilogue groups for the layers whose mainloop is shorter than their epilogue (1x1 convs; no BN
+  // statistics, no multicast): the kernels exist for 1-CTA 128x{128,64} / BK 64, 128x64 / BK 32 and the 256-wide pair.
+  {
+    const char* eg = opt("YB_CONV_EG");          // "1": always one group (A/B), "2": two groups wherever a kernel exists
+    const bool have = two ? (bn == 256 && bk == 64) : ((bn == 128 && bk == 64) || (bn == 64));
+    const bool want = (kh * kw == 1 || (eg[0] == '2'));   // (Cin <= 64 3x3 layers are TMA-row bound: the smaller ring costs them 15-25 %, r02_c)
+    p->epi_groups = (have && want && !stat_sum && mc_m * mc_n == 1 && eg[0] != '1') ? 2 : 1;
+  }
+  const int ring = ring_budget(p->epi_groups);
   {
     // resident weights (1-CTA kernel): one n-tile, and the [BN, K] tile leaves room for >= 3 A stages
     const long b_bytes = (long)kh * kw * d->cin * bn * 2;
     const char* br = opt("YB_CONV_BRES");
-    p->b_resident = (!two && cout_pad == bn && SMEM_BUDGET - b_bytes >= 3L * BLOCK_M * bk * 2 && (br && br[0] == '1')) ? 1 : 0;   // opt-in: measured no gain (profiles/r01_i)
+    p->b_resident = (!two && cout_pad == bn && ring - b_bytes >= 3L * BLOCK_M * bk * 2 && (br && br[0] == '1')) ? 1 : 0;   // opt-in: measured no gain (profiles/r01_i)
   }
   if (!two && !p->b_resident) {
     // k-blocks per barrier phase in the 1-CTA kernel: the largest of {4, 3, 2} that divides the k-block count and still
@@ -1390,7 +1443,7 @@ static int conv_prepare_core(const yb_conv_desc* d, int win, int kh, int kw, int
     const bool on = !(ke && ke[0] == '0');
     const int num_kb = kh * kw * (d->cin / bk);
     const long stage_bytes = (long)(BLOCK_M + bn) * bk * 2;
-    int stages = (int)(SMEM_BUDGET / stage_bytes);
+    int stages = (int)(ring / stage_bytes);
     if (stages > 8) stages = 8;
     if (on)
       for (int c = 4; c >= 2; --c)
@@ -1409,8 +1462,16 @@ static int conv_prepare_core(const yb_conv_desc* d, int win, int kh, int kw, int
   // 16-bit outputs leave through shared memory + TMA stores (YB_CONV_EPI=reg: the register-store epilogue of round 1);
   // the multicast kernel, the 2x-upsampling / parity-scatter stores and the fp32 heads keep the register path
   {
+    // epi_tma: 1 (default) TMA stores / TMA residual loads, 0 register stores (YB_CONV_EPI=reg).  A third variant (staging
+    // tile drained by coalesced st.global, residual prefetched through registers) measured equal on the plain layers
+    // and 1.5x slower on the residual ones (a one-chunk register prefetch cannot hide a DRAM miss): removed (r02_b).
+    // Convs that also produce BN batch statistics keep the register epilogue: its column sums go through the staging tile.
+    // A fourth variant (no staging at all: each lane stores its row's chunk as two 256-bit st.global.v8, residual by
+    // ld.global.v8 one chunk ahead) halved the epilogue's own time (2.9 k vs 4.6 k cycles per 128x128 tile) but not the
+    // layers': the 1x1 layers are then paced by the operand fill, and the residual layers lost 20 % because a register
+    // prefetch cannot hide a DRAM miss the way the TMA's 3-tile rotation does: removed (profiles/r02_c).
     const char* ep = opt("YB_CONV_EPI");
-    p->epi_tma = (!d->out_fp32 && !d->upsample2x && !scatter && mc_m * mc_n == 1 && !(ep[0] == 'r')) ? 1 : 0;
+    p->epi_tma = (!d->out_fp32 && !d->upsample2x && !scatter && mc_m * mc_n == 1 && !stat_sum && !(ep[0] == 'r')) ? 1 : 0;
     memset(&p->tmO, 0, sizeof(p->tmO));
     memset(&p->tmR, 0, sizeof(p->tmR));
     if (p->epi_tma) {
@@ -1470,7 +1531,7 @@ int conv_prepare_win(const yb_conv_desc* d, int kh, int kw, int scatter, const v
 extern "C" int yb_conv_cout_pad(int cout) { return (cout + 63) / 64 * 64; }
 
 // tools/conv_trace.py: convs PREPARED after this call stamp CTA 0's pipeline events (clock64) into `buf`
-// ([6 roles][64 tile iterations][32 slots] + 2 (kernel entry, set-up done) int64, caller-zeroed); NULL switches it off again.
+// ([10 warps][64 tile iterations][32 slots] + 2 (kernel entry, set-up done) int64, caller-zeroed); NULL switches it off again.
 extern "C" int yb_debug_set_conv_trace(long long* buf) { yb::g_conv_trace = buf; return YB_OK; }
 
 extern "C" int yb_conv2d_fwd(const yb_conv_desc* d, const void* x, const void* w_packed, const float* scale,

@@ -220,6 +220,15 @@ extern "C" int yb_net_bind(yb_net* net, void* activation_arena, size_t activatio
                           &L.tmB, &L.params, &cp);
     if (rc) return rc;
     L.prepared = true;
+    L.halo_ok = false;
+    if (L.info.has_bn && conv_halo_supported(&d)) {
+      L.halo_desc = d;
+      rc = conv_halo_prepare(&d, ten_ptr(net, L.in), net->par + L.w_packed, reinterpret_cast<const float*>(net->par + L.scale),
+                             reinterpret_cast<const float*>(net->par + L.shift),
+                             L.res.buf >= 0 ? ten_ptr(net, L.res) : nullptr, ten_ptr(net, L.out), &L.halo_maps, &L.halo_params);
+      if (rc) return rc;
+      L.halo_ok = true;
+    }
     if (!L.info.has_bn) {
       // fused-decode variant of the head (yb_net_detect); class counts without a kernel keep the unfused pipeline
       L.det_ok = conv_prepare_det(&d, net->class_num, ten_ptr(net, L.in), net->par + L.w_packed,
@@ -334,6 +343,15 @@ static int forward_layers_impl(yb_net* net, const float* images, float* fm1, flo
                                    reinterpret_cast<const float*>(net->par + L.scale),
                                    reinterpret_cast<const float*>(net->par + L.shift),
                                    L.res.buf >= 0 ? ten_ptr(net, L.res) : nullptr, ten_ptr(net, L.out), stream);
+      if (rc) return rc;
+      continue;
+    }
+    // halo-tile kernel: measured (profiles/r02_c, batch 64 @416) 302 vs 381 us on Conv_3 (32->64 @208^2) and 244 vs 382 us
+    // on Conv_1 (32->64 /2), but 227 vs 188 us on the 64->128 layers (their weights leave room for two halo stages only):
+    // default on for Cin = 32.  YB_HALO=0: never, YB_HALO=1: wherever supported.
+    const char* hopt = opt("YB_HALO");
+    if (L.halo_ok && hopt[0] != '0' && (hopt[0] == '1' || L.info.cin == 32)) {
+      int rc = conv_halo_launch(&L.halo_desc, L.halo_maps, L.halo_params, st);
       if (rc) return rc;
       continue;
     }

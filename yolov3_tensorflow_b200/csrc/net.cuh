@@ -31,6 +31,11 @@ struct Layer {
   CUtensorMap tmA, tmB;
   ConvParams params;
   bool prepared = false;
+  // Cin <= 64 3x3 layers: halo-tile kernel (csrc/conv_halo.cu), inference forward only
+  HaloMaps halo_maps;
+  HaloParams halo_params;
+  yb_conv_desc halo_desc;
+  bool halo_ok = false;
   // detection heads: the same conv with the decode + NMS candidate filter fused into its epilogue (yb_net_detect)
   CUtensorMap det_tmA, det_tmB;
   ConvParams det_params;

@@ -15,9 +15,13 @@ _WS_CACHE = {}
 
 
 def _workspace(n, B, Cn, mb, device):
+    """Scratch for one yb_nms call.  Cached per (device, stream): calls on one stream are ordered, so they may share
+    it; calls on different streams get different buffers.  A buffer that has to grow is replaced — the old tensor goes
+    back to torch's caching allocator, which keeps it alive until the stream's queued work has used it."""
     need = C.c_size_t()
     check(lib.yb_nms_workspace_bytes(n, B, Cn, mb, C.byref(need)), "yb_nms_workspace_bytes")
-    key = (str(device),)
+    with torch.cuda.device(device):
+        key = (str(device), torch.cuda.current_stream().cuda_stream)
     ws = _WS_CACHE.get(key)
     if ws is None or ws.numel() < need.value:
         ws = torch.empty(max(need.value, 256), dtype=torch.uint8, device=device)
@@ -46,8 +50,9 @@ def batched_nms_raw(boxes, scores, num_classes, max_boxes, score_thresh, nms_thr
     oi = torch.empty((n, max(cap, 1)), dtype=torch.int32, device=dev)
     cnt = torch.empty((n,), dtype=torch.int32, device=dev)
     ws = _workspace(n, B, num_classes, int(max_boxes), dev)
-    check(lib.yb_nms(ptr(boxes), ptr(scores), n, B, num_classes, int(max_boxes), float(score_thresh), float(nms_thresh),
-                     ptr(ws), ws.numel(), ptr(ob), ptr(os_), ptr(ol), ptr(oi), ptr(cnt), stream_handle()), "yb_nms")
+    with torch.cuda.device(dev):                       # the tensors' device, not whatever device happens to be current
+        check(lib.yb_nms(ptr(boxes), ptr(scores), n, B, num_classes, int(max_boxes), float(score_thresh), float(nms_thresh),
+                         ptr(ws), ws.numel(), ptr(ob), ptr(os_), ptr(ol), ptr(oi), ptr(cnt), stream_handle()), "yb_nms")
     return ob, os_, ol, oi, cnt
 
 
