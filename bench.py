@@ -256,6 +256,19 @@ def nms_stress(pkg, with_cpu):
     return out
 
 
+def synth_gt_lists(rng, n, size, class_num=CLASS_NUM, max_boxes=50):
+    """SURVEY.md §8d cfg 3/4 ground truth as LISTS (what a data loader hands over): per image U{1..max} boxes
+    [x0, y0, x1, y1, mix-up weight 1], w, h ~ logU[8, 400] clipped to the image, uniform centres and classes."""
+    bl, ll = [], []
+    for _ in range(n):
+        v = int(rng.integers(1, max_boxes + 1))
+        wh = np.exp(rng.uniform(np.log(8), np.log(400), (v, 2))).clip(max=size)
+        c = rng.uniform(0, size, (v, 2)).clip(wh / 2, size - wh / 2 - 1e-3)
+        bl.append(np.concatenate([c - wh / 2, c + wh / 2, np.ones((v, 1))], axis=1).astype(np.float32))
+        ll.append(rng.integers(0, class_num, v).astype(np.int64))
+    return bl, ll
+
+
 def synth_y_true(rng, n, size, anchors, class_num=CLASS_NUM, max_boxes=50):
     """SURVEY.md §8d cfg 3/4 targets: per image U{1..50} boxes, w,h ~ logU[8,400], best-anchor assignment
     (utils/data_utils.py:51-115 semantics, vectorised on the host) -> three y_true tensors on the GPU."""
@@ -297,7 +310,17 @@ def latency_b1(pkg, S, iters=30):
         if i >= 5:
             ts.append(a.elapsed_time(b))
     ts.sort()
+    tg = []
+    for i in range(iters + 5):                  # the same step replayed from a CUDA graph (model.detect_graphed)
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = model.detect_graphed(x, max_boxes=200, score_thresh=0.3, nms_thresh=0.45)
+        b.record(); torch.cuda.synchronize()
+        if i >= 5:
+            tg.append(a.elapsed_time(b))
+    tg.sort()
     return {"ms_median": ts[len(ts) // 2], "ms_min": ts[0], "images_per_s": 1e3 / ts[len(ts) // 2],
+            "cuda_graph_ms_median": tg[len(tg) // 2], "cuda_graph_ms_min": tg[0],
             "what": "batch 1, %dx%d, forward + decode + NMS (yb_net_detect), device-resident input, 77 launches" % (S, S)}
 
 
@@ -378,10 +401,16 @@ def main():
     h2d_done = [torch.cuda.Event() for _ in range(2)]
     buf_free = [torch.cuda.Event() for _ in range(2)]
     cap = CLASS_NUM * NMS_ARGS["max_boxes"]
-    h_counts = torch.empty((B,), dtype=torch.int32).pin_memory()
-    h_boxes = torch.empty((B, cap, 4), dtype=torch.float32).pin_memory()
-    h_scores = torch.empty((B, cap), dtype=torch.float32).pin_memory()
-    h_labels = torch.empty((B, cap), dtype=torch.int32).pin_memory()
+    # detections go back through a D2H stream into double-buffered pinned memory: step i's read-back overlaps step i+1's
+    # compute, like the H2D prefetch; the host waits for step i-1's results at the end of step i (and for the last one
+    # before the timed region closes), so every step's detections ARE on the host inside the timed region
+    d2h_stream = torch.cuda.Stream()
+    h_counts = [torch.empty((B,), dtype=torch.int32).pin_memory() for _ in range(2)]
+    h_boxes = [torch.empty((B, cap, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+    h_scores = [torch.empty((B, cap), dtype=torch.float32).pin_memory() for _ in range(2)]
+    h_labels = [torch.empty((B, cap), dtype=torch.int32).pin_memory() for _ in range(2)]
+    d2h_done = [torch.cuda.Event() for _ in range(2)]
+    out_keep = [None, None]
 
     def e2e_prefetch(i):
         with torch.cuda.stream(copy_stream):
@@ -395,12 +424,17 @@ def main():
         cur.wait_event(h2d_done[i % 2])
         _, ob, os_, ol, oi, cnt = model.detect_raw(x_bufs[i % 2], **NMS_ARGS)
         buf_free[i % 2].record(cur)
-        h_counts.copy_(cnt, non_blocking=True)                                 # D2H: K per image
-        h_boxes.copy_(ob, non_blocking=True)                                   # D2H: detections (fixed-size, contiguous)
-        h_scores.copy_(os_, non_blocking=True)
-        h_labels.copy_(ol, non_blocking=True)
-        torch.cuda.current_stream().synchronize()                              # results are on the host
-        return h_counts, cap
+        out_keep[i % 2] = (ob, os_, ol, cnt)                                   # keep the device tensors alive until copied
+        computed = torch.cuda.Event(); computed.record(cur)
+        with torch.cuda.stream(d2h_stream):
+            d2h_stream.wait_event(computed)
+            h_counts[i % 2].copy_(cnt, non_blocking=True)                      # D2H: K per image
+            h_boxes[i % 2].copy_(ob, non_blocking=True)                        # D2H: detections (fixed-size, contiguous)
+            h_scores[i % 2].copy_(os_, non_blocking=True)
+            h_labels[i % 2].copy_(ol, non_blocking=True)
+            d2h_done[i % 2].record(d2h_stream)
+        d2h_done[(i - 1) % 2].synchronize()                                    # the PREVIOUS step's results are on the host
+        return h_counts[i % 2], cap
 
     def barrier():
         if world > 1:
@@ -433,6 +467,8 @@ def main():
     # ---------------- timed: end to end (host -> host) ----------------
     for ev in buf_free:
         ev.record()
+    for ev in d2h_done:
+        ev.record()
     e2e_prefetch(0)
     for i in range(2):
         step_e2e(i)
@@ -443,6 +479,8 @@ def main():
     for i in range(2, 2 + args.steps):
         counts, kmax = step_e2e(i)
         d2h = counts.numel() * 4 + B * kmax * (16 + 4 + 4)
+    d2h_stream.synchronize()                                                   # the last step's results too
+    torch.cuda.current_stream().wait_stream(d2h_stream)
     t1.record()
     barrier()
     ms2 = torch.tensor([t0.elapsed_time(t1)], device="cuda")
@@ -501,6 +539,8 @@ def main():
         del model, x_dev
         torch.cuda.empty_cache()
 
+        bucket_mb = float(os.environ.get("YB_BUCKET_MB", "32"))     # gradient all-reduce bucket size (0: one blocking all-reduce)
+
         def bench_train(tb, ts, tsteps):
             tm = pkg.yolov3(CLASS_NUM, anchors, use_label_smooth=True, use_focal_loss=True, batch_norm_decay=0.99, dtype="bf16")
             tm.init_params(seed=3)
@@ -508,29 +548,82 @@ def main():
             xt = torch.from_numpy(rng.random((tb, ts, ts, 3), dtype=np.float32)).cuda()
             yts = synth_y_true(rng, tb, ts, anchors)
             for _ in range(3):
-                tm.train_step(xt, yts, 1e-4)
+                tm.train_step(xt, yts, 1e-4, bucket_mb=bucket_mb)
             barrier()
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a0.record()
             for _ in range(tsteps):
-                tl = tm.train_step(xt, yts, 1e-4)
+                tl = tm.train_step(xt, yts, 1e-4, bucket_mb=bucket_mb)
             a1.record()
             barrier()
             tms = torch.tensor([a0.elapsed_time(a1)], device="cuda")
             if world > 1:
                 dist.all_reduce(tms, op=dist.ReduceOp.MAX)
             t_step = float(tms) / tsteps * 1e-3
+            # end to end: pinned host images + ground-truth LISTS -> H2D (copy stream, double buffered) -> y_true built on
+            # the device (yb_process_box) -> train step -> D2H of the 5 losses, every step inside the timed region
+            from yolov3_tensorflow_b200.utils import data_utils as DU
+            bl, ll = synth_gt_lists(np.random.default_rng(30 + rank), tb, ts, CLASS_NUM, 50)
+            hb, hl, hc = DU.pack_gt(bl, ll, 50)
+            x_h = xt.cpu().pin_memory()
+            cs = torch.cuda.Stream()
+            xb = [torch.empty_like(xt) for _ in range(2)]
+            gb = [(torch.empty_like(hb, device="cuda"), torch.empty_like(hl, device="cuda"), torch.empty_like(hc, device="cuda")) for _ in range(2)]
+            yb_ = [[torch.empty_like(y) for y in yts] for _ in range(2)]
+            done = [torch.cuda.Event() for _ in range(2)]
+            free = [torch.cuda.Event() for _ in range(2)]
+            h_loss = torch.empty(5, dtype=torch.float32).pin_memory()
+
+            def prefetch(i):
+                with torch.cuda.stream(cs):
+                    cs.wait_event(free[i % 2])
+                    xb[i % 2].copy_(x_h, non_blocking=True)
+                    for d_, h_ in zip(gb[i % 2], (hb, hl, hc)):
+                        d_.copy_(h_, non_blocking=True)
+                    done[i % 2].record(cs)
+
+            def step_train_e2e(i):
+                prefetch(i + 1)
+                cur = torch.cuda.current_stream()
+                cur.wait_event(done[i % 2])
+                y3 = DU.process_box_batch(*gb[i % 2], [ts, ts], CLASS_NUM, anchors, out=yb_[i % 2])
+                ls = tm.train_step(xb[i % 2], y3, 1e-4, bucket_mb=bucket_mb)
+                free[i % 2].record(cur)
+                h_loss.copy_(torch.stack(ls), non_blocking=True)
+                cur.synchronize()
+
+            for ev in free:
+                ev.record()
+            prefetch(0)
+            for i in range(2):
+                step_train_e2e(i)
+            barrier()
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record()
+            for i in range(2, 2 + tsteps):
+                step_train_e2e(i)
+            b1.record()
+            barrier()
+            tme = torch.tensor([b0.elapsed_time(b1)], device="cuda")
+            if world > 1:
+                dist.all_reduce(tme, op=dist.ReduceOp.MAX)
+            e2e_step = float(tme) / tsteps * 1e-3
             gflop = 197.29 * (ts / 416.0) ** 2               # fwd + dgrad + wgrad per image
             tfl = tb * gflop * 1e9 / t_step / 1e12
             out = {"images_per_s": tb * world / t_step, "ms_per_step": t_step * 1e3, "batch_per_gpu": tb, "image": [ts, ts],
                    "dtype": "bf16", "loss_total": float(tl[0]), "steps": tsteps, "warmup": 3,
+                   "e2e": {"value": tb * world / e2e_step, "unit": "images/s", "ms_per_step": e2e_step * 1e3,
+                           "h2d_bytes_per_step": int(x_h.numel() * 4 + hb.numel() * 4 + hl.numel() * 4 + hc.numel() * 4),
+                           "d2h_bytes_per_step": 20,
+                           "what": "pinned host images + gt box lists -> H2D -> y_true on the device (yb_process_box) -> train step -> losses to the host"},
                    "roofline": {"bound": "tensor", "kernel": "whole training step (conv fwd + dgrad + wgrad FLOPs / step time)",
                                 "achieved": tfl, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": tfl / pk["tflops"],
                                 "algorithmic_flop_per_step": tb * gflop * 1e9, "peak_source": pk["src"]},
                    "tflops": tfl, "frac_of_peak": tfl / pk["tflops"],
                    "what": "forward(BN batch stats) + compute_loss(focal, label-smooth) + backward + "
-                           + ("NCCL all-reduce + " if world > 1 else "") + "L2/clip/momentum update, synthetic <=50 boxes/img"}
-            del tm, xt, yts
+                           + (("NCCL all-reduce in %g MB buckets overlapping the backward + " % bucket_mb if bucket_mb > 0 else "one blocking NCCL all-reduce + ") if world > 1 else "")
+                           + "L2/clip/momentum update, synthetic <=50 boxes/img"}
+            del tm, xt, yts, xb, gb, yb_
             torch.cuda.empty_cache()
             return out
 

@@ -328,11 +328,17 @@ int yb_net_forward_layers(yb_net* net, const float* images, float* fm1, float* f
  * (forward(is_training=False) inside the training graph: fine-tuning with frozen BN; statistics are constants of the
  * backward pass and are not updated) — per-image results then do not depend on the rest of the batch, which is what
  * makes an N-rank data-parallel step bit-comparable with a 1-rank step on the concatenated batch. */
-enum { YB_TRAIN_FORWARD_ONLY = 1, YB_TRAIN_BN_FROZEN = 2 };
+enum { YB_TRAIN_FORWARD_ONLY = 1, YB_TRAIN_BN_FROZEN = 2, YB_TRAIN_NO_BACKWARD = 4 };
 int yb_net_train_fwd_bwd(yb_net* net, const float* images, const float* y_true_1, const float* y_true_2,
                          const float* y_true_3, const float* anchors9x2, int use_label_smooth, int use_focal_loss,
                          float bn_decay, float loss_scale, float* fm1, float* fm2, float* fm3, double* loss4,
                          int flags, void* stream);
+/* Bucketed data parallelism: yb_net_train_fwd_bwd(..., flags | YB_TRAIN_NO_BACKWARD) stops after the
+ * loss; yb_net_train_backward then runs the backward of layers last_layer .. first_layer (descending, same flags), and
+ * yb_net_grad_range returns the contiguous slice of the flat gradient those layers own — the caller issues the
+ * all-reduce of a finished bucket (detection heads first) while the next bucket's backward is running. */
+int yb_net_train_backward(yb_net* net, const float* images, int first_layer, int last_layer, int flags, void* stream);
+int yb_net_grad_range(yb_net* net, int first_layer, int last_layer, float** ptr, size_t* count);
 /* the flat float32 gradient of all 222 trainable tensors (creation order: per conv w [OHWI], then gamma, beta
  * | bias; each padded to 4 floats) — the buffer a data-parallel wrapper all-reduces. */
 int yb_net_grad_buffer(yb_net* net, float** ptr, size_t* count);

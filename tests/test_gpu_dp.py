@@ -59,6 +59,13 @@ def _worker(rank, world, port, q):
         dist.all_gather(ws, t)
         gathered.append(ws)
     same = all(torch.equal(ws[0], ws[1]) for ws in gathered)
+    # ---- the same step with ONE blocking all-reduce after the whole backward: the bucketed, backward-overlapped
+    # ---- reduction must give the same update (two runs differ only by the order of the fp32 atomics inside wgrad)
+    m_blk = fresh()
+    m_blk.train_step(xs, ys, lr, freeze_bn=True, bucket_mb=0)
+    blk = _flat(m_blk)
+    nb = len(m_dp._last_plan._buckets)
+    bucket_err = max(float((a - b).double().norm() / b.double().norm().clamp(min=1e-30)) for a, b in zip(dp, blk))
     # ---- 1-rank step on the concatenated batch (no collective), same engine, same parameters
     m_1 = fresh()
     m_1.train_step(torch.from_numpy(x).cuda(), [torch.from_numpy(y).cuda() for y in y_true], lr, freeze_bn=True,
@@ -74,7 +81,7 @@ def _worker(rank, world, port, q):
     moved = all(float((b - w0).abs().max()) > 0 for b, w0 in zip(one, before))
     dist.barrier()
     dist.destroy_process_group()
-    q.put((rank, max(errs), same, moved))
+    q.put((rank, max(errs), same, moved, nb, bucket_err))
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
@@ -90,7 +97,9 @@ def test_dp_train_step_equals_single_rank_on_concatenated_batch():
         p.join(timeout=900)
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     res = sorted(q.get(timeout=5) for _ in range(2))
-    for rank, err, same, moved in res:
+    for rank, err, same, moved, nb, bucket_err in res:
+        print(f"rank {rank}: {nb} gradient buckets; bucketed vs blocking all-reduce, max relative L2 difference of the parameters: {bucket_err:.3g}")
+        assert nb >= 4 and bucket_err < 1e-6
         print(f"rank {rank}: max relative L2 error of the parameter update, 2-rank DP vs 1-rank on 4 images: {err:.3g}")
         assert moved, "the 1-rank reference step did not move the parameters"
         # fp32 atomic-accumulation order in wgrad / BN reductions is the only difference (1/N is a power of two)

@@ -780,3 +780,25 @@ def test_detect_fused_equals_unfused_pipeline(cn, n, h, w, thr):
     assert k == len(oi) and np.array_equal(fb[4][0, :k].cpu().numpy(), oi) and np.array_equal(fb[3][0, :k].cpu().numpy(), ol)
     dets = m.detect(x, mb, thr, 0.45)
     assert len(dets) == n and dets[0][0].shape == (k, 4)
+
+
+def test_detect_graphed_equals_eager():
+    """model.detect_graphed (the detection step captured in a CUDA graph) returns the same bits as detect_raw, for
+    successive different inputs, and survives a parameter change (re-capture)."""
+    params = O.make_params(80, seed=23, random_bn=True, det_scale=8.0, conf_bias=-2.0)
+    m = _model(80, "fp16")
+    m.set_params(params, "HWIO")
+    for seed in (1, 2, 3):
+        x = torch.from_numpy(gen_inputs(seed, 1, 96, 128)).cuda()
+        e = [t.clone() for t in m.detect_raw(x, 20, 0.3, 0.45)]
+        g = m.detect_graphed(x, 20, 0.3, 0.45)
+        k = int(e[5][0])
+        assert int(g[5][0]) == k and k > 0
+        assert torch.equal(g[0], e[0])
+        for a, b in zip(g[1:5], e[1:5]):
+            assert torch.equal(a[0, :k], b[0, :k])
+    m.set_params(O.make_params(80, seed=24, random_bn=True, det_scale=8.0, conf_bias=-2.0), "HWIO")
+    x = torch.from_numpy(gen_inputs(9, 1, 96, 128)).cuda()
+    e = [t.clone() for t in m.detect_raw(x, 20, 0.3, 0.45)]
+    g = m.detect_graphed(x, 20, 0.3, 0.45)
+    assert torch.equal(g[0], e[0]) and torch.equal(g[5], e[5])

@@ -62,3 +62,44 @@ def test_save_weights_writes_the_darknet_stream(tmp_path):
     for a, b in zip(params, back):
         for k in a:
             assert np.array_equal(a[k], b[k]), k
+
+
+# ------------------------------------------------------------------------- N1: LR schedules / optimizer selection
+def _lr_args(**kw):
+    import types
+    base = dict(lr_type="exponential", learning_rate_init=1e-3, lr_decay_freq=400, lr_decay_factor=0.96, lr_lower_bound=1e-6,
+                total_epoches=10, use_warm_up=True, warm_up_epoch=3, train_batch_num=100,
+                pw_boundaries=[300.0, 500.0], pw_values=[1e-3, 3e-4, 1e-4])
+    base.update(kw)
+    return types.SimpleNamespace(**base)
+
+
+def test_learning_rate_schedules_match_the_oracle_restatement():
+    """utils/misc_utils.py:129-148 + warm-up train.py:93-99: the host-side schedule functions against the oracle's
+    independent restatement (oracle.learning_rate) over all five lr types, with and without warm-up."""
+    from oracle import yolov3_oracle as O
+    from yolov3_tensorflow_b200.utils import misc_utils as M
+    steps = [0, 1, 150, 299, 300, 301, 399, 400, 401, 799, 800, 1200, 2799, 2800, 5000]
+    for kind in ("exponential", "cosine_decay", "cosine_decay_restart", "fixed", "piecewise"):
+        for warm in (True, False):
+            a = _lr_args(lr_type=kind, use_warm_up=warm)
+            for s in steps:
+                got, ref = M.learning_rate_at(a, s), O.learning_rate(a, s)
+                assert abs(got - ref) <= 1e-12 + 1e-9 * abs(ref), (kind, warm, s, got, ref)
+    assert M.learning_rate_at(_lr_args(), 150) == 1e-3 * 150 / 300                      # linear warm-up (train.py:95)
+    assert M.config_learning_rate(_lr_args(lr_type="exponential"), 800) == max(1e-3 * 0.96 ** 2, 1e-6)
+    assert M.config_learning_rate(_lr_args(lr_type="piecewise"), 300) == 1e-3 and M.config_learning_rate(_lr_args(lr_type="piecewise"), 300.5) == 3e-4
+    with pytest.raises(ValueError, match="Unsupported learning rate type"):
+        M.config_learning_rate(_lr_args(lr_type="poly"), 0)
+
+
+def test_config_optimizer_and_tf_variable_names():
+    from yolov3_tensorflow_b200.utils import misc_utils as M
+    for name in ("momentum", "rmsprop", "adam", "sgd"):
+        assert M.config_optimizer(name, 1e-3).name == name
+    with pytest.raises(ValueError, match="Unsupported optimizer type"):
+        M.config_optimizer("adagrad", 1e-3)                                                # utils/misc_utils.py:161
+    names = M.tf_variable_names(80)
+    assert len(names) == 72 * 5 + 3 * 2 == 366
+    assert names[0][2] == "yolov3/darknet53_body/Conv/weights:0" and names[-1][2] == "yolov3/yolov3_head/Conv_22/biases:0"
+    assert names[5][2] == "yolov3/darknet53_body/Conv_1/weights:0" and names[1][2] == "yolov3/darknet53_body/Conv/BatchNorm/gamma:0"

@@ -54,6 +54,17 @@ def _worker(rank, world, port, out):
     assert scale == 0.5
     ref = torch.tensor([float((g * a).sum()) for g, a in zip(g_full, f)], dtype=torch.float64)
     assert torch.allclose(flat * scale, ref, rtol=1e-9, atol=1e-12), (flat * scale, ref)
+    # ---- bucketed reduction: buckets listed heads-first, every element reduced exactly once ----
+    sizes = [5, 0, 7, 3, 9, 1]
+    buckets = parallel.gradient_buckets(sizes, 8)
+    assert buckets == [(4, 5), (2, 3), (0, 1)]
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    flat2 = torch.arange(float(sum(sizes)), dtype=torch.float64) * (rank + 1)
+    red = parallel.BucketedAllReduce()
+    for lo_l, hi_l in buckets:
+        red.reduce(flat2[offs[lo_l]: offs[hi_l + 1]])
+    assert red.wait() == 0.5
+    assert torch.equal(flat2, torch.arange(float(sum(sizes)), dtype=torch.float64) * 3.0)
     # ---- timing reduction ----
     assert parallel.max_over_ranks(10.0 + rank, "cpu") == 11.0
     dist.barrier()
@@ -82,3 +93,7 @@ def test_single_process_helpers_are_noops():
     assert parallel.allreduce_gradients(t) == 1.0 and torch.equal(t, torch.ones(4))
     assert parallel.max_over_ranks(3.0, "cpu") == 3.0
     assert parallel.shard_batch(8, 0, 1) == (0, 8)
+    assert parallel.gradient_buckets([4, 4, 4], 100) == [(0, 2)] and parallel.gradient_buckets([4, 4, 4], 1) == [(2, 2), (1, 1), (0, 0)]
+    red = parallel.BucketedAllReduce()
+    red.reduce(t)
+    assert red.wait() == 1.0 and torch.equal(t, torch.ones(4))

@@ -321,8 +321,22 @@ extern "C" int yb_net_train_fwd_bwd(yb_net* net, const float* images, const floa
                        (3 * (5 + net->class_num) + 31) / 32 * 32, stream);
     if (rc) return rc;
   }
-  // ------------------------------------------------ backward
-  for (int i = (int)net->layers.size() - 1; i >= 0; --i) {
+  if (flags & YB_TRAIN_NO_BACKWARD) return YB_OK;
+  return yb_net_train_backward(net, images, 0, (int)net->layers.size() - 1, flags, stream);
+}
+
+// Backward of layers last_layer .. first_layer (descending), after yb_net_train_fwd_bwd(..., YB_TRAIN_NO_BACKWARD):
+// lets a data-parallel caller all-reduce the finished head-side gradient buckets while the backbone is still running.
+extern "C" int yb_net_train_backward(yb_net* net, const float* images, int first_layer, int last_layer, int flags,
+                                     void* stream) {
+  YB_REQUIRE(net && net->training && net->act && net->par && images, "train_backward: not a bound training plan");
+  YB_REQUIRE(first_layer >= 0 && first_layer <= last_layer && last_layer < (int)net->layers.size(), "train_backward: bad layer range");
+  const bool bn_frozen = (flags & YB_TRAIN_BN_FROZEN) != 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n = net->n, dt = net->dtype;
+  const float* zeros = fpar(net, net->zeros_off);
+  int rc;
+  for (int i = last_layer; i >= first_layer; --i) {
     Layer& L = net->layers[i];
     const long rows = (long)n * L.info.out_h * L.info.out_w;
     if (L.info.has_bn) {
@@ -416,6 +430,17 @@ extern "C" int yb_net_grad_buffer(yb_net* net, float** ptr, size_t* count) {
   YB_REQUIRE(net && net->training && net->par && ptr && count, "grad_buffer: not a bound training plan");
   *ptr = reinterpret_cast<float*>(net->par + net->grad_off);
   *count = (size_t)net->grad_count;
+  return YB_OK;
+}
+
+// flat-gradient slice of layers [first_layer, last_layer] (contiguous: the buffer is laid out in creation order)
+extern "C" int yb_net_grad_range(yb_net* net, int first_layer, int last_layer, float** ptr, size_t* count) {
+  YB_REQUIRE(net && net->training && net->par && ptr && count, "grad_range: not a bound training plan");
+  YB_REQUIRE(first_layer >= 0 && first_layer <= last_layer && last_layer < (int)net->layers.size(), "grad_range: bad layer range");
+  const long lo = net->layers[first_layer].g_w;
+  const long hi = last_layer + 1 < (int)net->layers.size() ? net->layers[last_layer + 1].g_w : net->grad_count;
+  *ptr = reinterpret_cast<float*>(net->par + net->grad_off) + lo;
+  *count = (size_t)(hi - lo);
   return YB_OK;
 }
 

@@ -107,6 +107,12 @@ class _Plan:
         flat = self.act[off: off + nelem * 2].view(tdt)
         return flat.as_strided((self.n, h, w, c), (h * w * ld.value, w * ld.value, ld.value, 1))
 
+    def grad_range(self, first_layer, last_layer):
+        """Flat-gradient slice owned by layers [first_layer, last_layer] (a data-parallel bucket)."""
+        p, n = C.c_void_p(), C.c_size_t()
+        check(lib.yb_net_grad_range(self.handle, int(first_layer), int(last_layer), C.byref(p), C.byref(n)), "yb_net_grad_range")
+        return self._view(p.value, (n.value,))
+
     def grad_flat(self):
         p, n = C.c_void_p(), C.c_size_t()
         check(lib.yb_net_grad_buffer(self.handle, C.byref(p), C.byref(n)), "yb_net_grad_buffer")
@@ -221,6 +227,7 @@ class yolov3(object):
             out.append(q)
         self._pending = out
         self._pending_layout = _lib.YB_W_HWIO if layout == "HWIO" else _lib.YB_W_OIHW
+        self.__dict__.pop("_graphs", None)           # captured graphs bake nothing parameter-dependent, but re-capture anyway
 
     def init_params(self, seed=0):
         """Random init as the reference graph would: Glorot-uniform conv weights,
@@ -446,6 +453,33 @@ class yolov3(object):
                                        ptr(oi), ptr(cnt), int(phases), stream_handle()), "yb_net_detect")
         return boxes, ob, os_, ol, oi, cnt
 
+    def detect_graphed(self, inputs, max_boxes=200, score_thresh=0.3, nms_thresh=0.45):
+        """detect_raw() replayed from a CUDA graph: the 77 launches of a detection step are captured
+        once per (input shape, thresholds) and replayed with one cudaGraphLaunch — for the single-image path of
+        test_single_image.py:48-62, where launch overhead, not the kernels, is the latency.  The input is copied into the
+        graph's static buffer; the returned tensors are the graph's static outputs (overwritten by the next call)."""
+        x = _as_cuda_f32(inputs, self.device)
+        key = (tuple(x.shape), int(max_boxes), float(score_thresh), float(nms_thresh))
+        graphs = self.__dict__.setdefault("_graphs", {})
+        entry = graphs.get(key)
+        if entry is None or self._fold_dirty or self._pending is not None:
+            sx = x.clone()
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):                 # warm-up outside the capture: plan, kernel attributes, workspace
+                for _ in range(2):
+                    self.detect_raw(sx, max_boxes, score_thresh, nms_thresh)
+            cur.wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self.detect_raw(sx, max_boxes, score_thresh, nms_thresh)
+            entry = graphs[key] = (g, sx, out)
+        g, sx, out = entry
+        sx.copy_(x, non_blocking=True)
+        g.replay()
+        return out
+
     def detect(self, inputs, max_boxes=200, score_thresh=0.3, nms_thresh=0.45):
         """detect_raw() unpacked like the reference's per-image result: a list of (boxes [K,4], scores [K], labels [K])
         per image (classes ascending, descending score inside a class).  Reading the counts is the one host sync."""
@@ -547,21 +581,23 @@ class yolov3(object):
 
     def train_step(self, images, y_true, learning_rate, momentum=0.9, clip_norm=100.0, process_group=None,
                    return_feature_maps=False, data_parallel=True, optimizer="momentum", decay=0.9, beta1=0.9,
-                   beta2=0.999, epsilon=None, freeze_bn=False):
+                   beta2=0.999, epsilon=None, freeze_bn=False, bucket_mb=32.0):
         """One training step of the reference (train.py:105-115): forward(is_training=True) -> compute_loss ->
         gradients of (loss[0] + l2_loss) w.r.t. the trainable tensors (all 222 unless set_trainable() restricted them,
         train.py:81) -> per-tensor clip_by_norm(clip_norm) -> optimizer update; BN moving statistics updated with
         self.batch_norm_decay.
 
         images float32 [N,H,W,3]; y_true = (y_true_13, y_true_26, y_true_52) in process_box format.
-        learning_rate: this step's value (utils.misc_utils.config_learning_rate / LearningRateSchedule evaluate the
+        learning_rate: this step's value (utils.misc_utils.config_learning_rate / learning_rate_at evaluate the
         reference's schedules on the host).  optimizer: 'momentum' (default), 'sgd', 'rmsprop', 'adam' or the object
         returned by utils.misc_utils.config_optimizer (utils/misc_utils.py:151-161; TF1 update rules).
         freeze_bn: BN layers normalise with their moving statistics and keep them (the graph the reference builds with
         is_training=False, train.py:72): fine-tuning with frozen BN.
         Data parallel: when torch.distributed is initialised (or process_group is given) the flat gradient is
         all-reduced (NCCL over NVLink) and averaged over the ranks before the update; every loss term is a
-        mean over the local batch (model.py:276-302), so this equals one big batch of world*N images.
+        mean over the local batch (model.py:276-302), so this equals one big batch of world*N images.  The gradient
+        is reduced in buckets of ~bucket_mb MB, detection heads first, each all-reduce overlapping the backward of
+        the layers below it (bucket_mb <= 0: one blocking all-reduce after the whole backward).
         Returns [total, xy, wh, conf, class] as 0-dim float32 CUDA tensors of the LOCAL batch."""
         import torch.distributed as dist
         x = _as_cuda_f32(images, self.device)
@@ -599,15 +635,29 @@ class yolov3(object):
         fms = [None, None, None]
         if return_feature_maps:
             fms = [torch.empty((n, h // s, w // s, 3 * (5 + C_)), dtype=torch.float32, device=self.device) for s in (32, 16, 8)]
-        from .parallel import allreduce_gradients
+        from .parallel import allreduce_gradients, gradient_buckets, BucketedAllReduce
         use_dp = data_parallel and (process_group is not None or (dist.is_available() and dist.is_initialized()))
+        use_dp = use_dp and dist.get_world_size(process_group) > 1
+        flags = _lib.YB_TRAIN_BN_FROZEN if freeze_bn else 0
+        bucketed = use_dp and bucket_mb and bucket_mb > 0
         check(lib.yb_net_train_fwd_bwd(plan.handle, ptr(x), ptr(ys[0]), ptr(ys[1]), ptr(ys[2]),
                                        _lib.fptr(self.anchors.reshape(-1)), int(self.use_label_smooth),
                                        int(self.use_focal_loss), float(self.batch_norm_decay), float(self.loss_scale),
                                        ptr(fms[0]), ptr(fms[1]), ptr(fms[2]), ptr(plan.loss4),
-                                       _lib.YB_TRAIN_BN_FROZEN if freeze_bn else 0, st), "yb_net_train_fwd_bwd")
+                                       flags | (_lib.YB_TRAIN_NO_BACKWARD if bucketed else 0), st), "yb_net_train_fwd_bwd")
         grad_scale = 1.0 / float(self.loss_scale)
-        if use_dp:
+        if bucketed:
+            # backward bucket by bucket (heads first); each bucket's all-reduce overlaps the next bucket's backward
+            if not hasattr(plan, "_buckets") or plan._bucket_mb != bucket_mb:
+                sizes = [plan.grad_range(i, i).numel() for i in range(plan.num_layers)]
+                plan._buckets = gradient_buckets(sizes, int(bucket_mb * (1 << 20) / 4))
+                plan._bucket_mb = bucket_mb
+            red = BucketedAllReduce(process_group)
+            for lo, hi in plan._buckets:
+                check(lib.yb_net_train_backward(plan.handle, ptr(x), lo, hi, flags, st), "yb_net_train_backward")
+                red.reduce(plan.grad_range(lo, hi))
+            grad_scale *= red.wait()
+        elif use_dp:
             grad_scale *= allreduce_gradients(plan.grad_flat(), process_group)   # NCCL all-reduce (sum) -> 1/world
         opt = _lib.Optimizer(kind=kind, lr=float(learning_rate), grad_scale=grad_scale, momentum=float(momentum),
                              decay=float(decay), beta1=float(beta1), beta2=float(beta2), epsilon=float(epsilon),

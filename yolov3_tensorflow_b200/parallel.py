@@ -48,6 +48,42 @@ def allreduce_gradients(flat_grad, group=None):
     return 1.0 / world
 
 
+def gradient_buckets(layer_floats, bucket_floats):
+    """Split the layers (creation order, `layer_floats[i]` = floats layer i owns in the flat gradient) into contiguous
+    buckets of roughly `bucket_floats`, listed in BACKWARD order (detection heads first): [(first_layer, last_layer), ...].
+    The backward pass finishes a bucket's gradients from its last layer down to its first; its all-reduce can start then."""
+    out, hi, acc = [], len(layer_floats) - 1, 0
+    for i in range(len(layer_floats) - 1, -1, -1):
+        acc += int(layer_floats[i])
+        if acc >= bucket_floats or i == 0:
+            out.append((i, hi))
+            hi, acc = i - 1, 0
+    return out
+
+
+class BucketedAllReduce:
+    """Overlap of the gradient all-reduce with the backward pass: every finished bucket is
+    handed to NCCL with async_op=True — torch's NCCL stream waits for the work enqueued so far on the compute stream and
+    runs the collective while the compute stream carries on with the next bucket's backward; wait() joins them before
+    the optimizer update.  Over gloo (CPU tensors, tests) the same calls run synchronously."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.pending = []
+
+    def reduce(self, flat_slice):
+        if self.world > 1:
+            self.pending.append(dist.all_reduce(flat_slice, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def wait(self):
+        """Returns the factor that turns the summed gradient into the mean (folded into the optimizer kernel)."""
+        for w in self.pending:
+            w.wait()
+        self.pending = []
+        return 1.0 / self.world
+
+
 def max_over_ranks(value, device):
     """Device-side max of a per-rank scalar (multi-GPU timings are reported as the max over ranks)."""
     t = torch.tensor([float(value)], device=device)
