@@ -113,6 +113,13 @@ int yb_stem_conv_fwd_tc(const float* x, const float* w_ohwi, const float* scale,
 int yb_conv3x3_halo_supported(const yb_conv_desc* d);
 int yb_conv3x3_halo_fwd(const yb_conv_desc* d, const void* x, const void* w_packed, const float* scale,
                         const float* shift, const void* res, void* out, void* stream);
+/* darknet53_body/Conv (3->32, 3x3/1) fused into darknet53_body/Conv_1 (32->64, 3x3/2) (utils/layer_utils.py:35-36):
+ * the stem is computed on the fly as the producer of Conv_1's shared-memory halo planes, its 64 B/pixel output is never
+ * written.  image float32 [n, h, w, 3]; d describes Conv_1 (d->h, d->w = image size, cin 32, cout 64, stride 2);
+ * stem_w_ohwi float32 [32][27], stem_scale / stem_shift float32 [32] (folded BN); out [n, h/2, w/2, out_ld] 16-bit. */
+int yb_stem_conv1_fused_fwd(const yb_conv_desc* d, const float* image, const float* stem_w_ohwi, const float* stem_scale,
+                            const float* stem_shift, const void* w_packed, const float* scale, const float* shift, void* out,
+                            void* stream);
 
 /* ---------------------------------------------------------------------------------
  * Pre-processing either side of the hot path, on the device

@@ -333,3 +333,50 @@ def test_conv3x3_halo_rejects_unsupported():
     d2 = L.ConvDesc(n=1, h=20, w=20, cin=64, cout=128, ksize=3, stride=1, in_ld=64, out_ld=128, res_ld=0, dtype=0,
                     out_fp32=0, leaky=1, upsample2x=0)
     assert L.lib.yb_conv3x3_halo_supported(C.byref(d2)) == 0          # 20 % 8 != 0
+
+
+# ------------------------------------------------------------------------- stem fused into Conv_1 (csrc/conv_halo.cu, STEMW)
+@pytest.mark.parametrize("n,h,w,dtype", [(2, 64, 32, torch.float16), (3, 80, 48, torch.bfloat16), (1, 416, 416, torch.float16),
+                                         (2, 96, 160, torch.float16)])
+def test_stem_conv1_fused(n, h, w, dtype, conv_mode):
+    """yb_stem_conv1_fused_fwd (the stem computed on the fly as the producer of Conv_1's halo planes) against the two
+    separate launches (stem kernel, then Conv_1 on its 16-bit output) and against fp32 convs on the same rounded
+    operands: image borders (the stem's SAME padding AND Conv_1's pad-1), partial bottom tiles, both storage types."""
+    if conv_mode != "1cta":
+        pytest.skip("independent of the igemm kernel selection")
+    L = _lib()
+    lib, check, ptr, st = L.lib, L.check, L.ptr, L.stream_handle
+    g = torch.Generator(device="cpu").manual_seed(5 + h)
+    dev = "cuda"
+    code = L.YB_F16 if dtype == torch.float16 else L.YB_BF16
+    x = torch.rand((n, h, w, 3), generator=g).to(dev)
+    w0 = (torch.randn((32, 3, 3, 3), generator=g) / 5.0).to(dev)                       # OHWI fp32
+    s0 = (torch.rand(32, generator=g) + 0.5).to(dev); b0 = (torch.randn(32, generator=g) * 0.1).to(dev)
+    w1 = (torch.randn((64, 3, 3, 32), generator=g) / (3 * 32 ** 0.5)).to(dev)
+    s1 = (torch.rand(64, generator=g) + 0.5).to(dev); b1 = (torch.randn(64, generator=g) * 0.1).to(dev)
+    w1p = torch.zeros((64, 3, 3, 32), dtype=dtype, device=dev)
+    check(lib.yb_pack_conv_weights(ptr(w1), L.YB_W_OHWI, 64, 32, 3, 64, code, ptr(w1p), st()), "pack")
+    # ---- two launches
+    a0 = torch.empty((n, h, w, 32), dtype=dtype, device=dev)
+    check(lib.yb_stem_conv_fwd_tc(ptr(x), ptr(w0), ptr(s0), ptr(b0), n, h, w, code, 1, ptr(a0), st()), "stem")
+    d = L.ConvDesc(n=n, h=h, w=w, cin=32, cout=64, ksize=3, stride=2, in_ld=32, out_ld=64, res_ld=0, dtype=code, out_fp32=0,
+                   leaky=1, upsample2x=0)
+    two = torch.empty((n, h // 2, w // 2, 64), dtype=dtype, device=dev)
+    check(lib.yb_conv2d_fwd(C.byref(d), ptr(a0), ptr(w1p), ptr(s1), ptr(b1), None, ptr(two), None, None, st()), "conv1")
+    # ---- fused
+    one = torch.full((n, h // 2, w // 2, 64), -7.0, dtype=dtype, device=dev)
+    check(lib.yb_stem_conv1_fused_fwd(C.byref(d), ptr(x), ptr(w0), ptr(s0), ptr(b0), ptr(w1p), ptr(s1), ptr(b1), ptr(one), st()), "fused")
+    torch.cuda.synchronize()
+    # ---- fp32 reference on the rounded operands (image and stem weights rounded to the storage type, like both kernels)
+    xr = x.to(dtype).float().permute(0, 3, 1, 2)
+    y0 = F.conv2d(xr, w0.to(dtype).float().permute(0, 3, 1, 2), None, stride=1, padding=1) * s0.view(1, -1, 1, 1) + b0.view(1, -1, 1, 1)
+    y0 = torch.where(y0 > 0, y0, 0.1 * y0).to(dtype).float()
+    y1 = F.conv2d(y0, w1p.float().permute(0, 3, 1, 2), None, stride=2, padding=1) * s1.view(1, -1, 1, 1) + b1.view(1, -1, 1, 1)
+    ref = torch.where(y1 > 0, y1, 0.1 * y1).permute(0, 2, 3, 1)
+    eps = 2.0 ** -8 if dtype == torch.float16 else 2.0 ** -5      # two rounding stages (stem output, Conv_1 output)
+    for name, got in (("two launches", two), ("fused", one)):
+        err = (got.float() - ref).abs()
+        tol = eps * torch.clamp(ref.abs(), min=1.0)
+        assert not (err > tol).any(), f"{name}: {int((err > tol).sum())} bad, max err {float(err.max()):.4g}"
+    # the fused kernel sees bit-identical stem activations; only Conv_1's accumulation order may differ
+    assert float((one.float() - two.float()).abs().max()) <= eps * max(1.0, float(ref.abs().max()))

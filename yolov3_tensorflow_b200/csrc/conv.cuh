@@ -48,7 +48,7 @@ int conv_prepare_win(const yb_conv_desc* d, int kh, int kw, int scatter, const v
 int conv_prepare_det(const yb_conv_desc* d, int class_num, const void* x, const void* w_packed, const float* scale,
                      const float* shift, CUtensorMap* tmA, CUtensorMap* tmB, ConvParams* p, int* cout_pad_out);
 // halo-tile conv for the Cin <= 64 3x3 layers (csrc/conv_halo.cu)
-struct HaloMaps { CUtensorMap plane[4]; CUtensorMap w; };
+struct HaloMaps { CUtensorMap plane[4]; CUtensorMap w; CUtensorMap in3d; };
 struct HaloParams {
   int n, ho, wo;               // output geometry
   int tiles_x, tiles_y, num_tiles;
@@ -60,11 +60,22 @@ struct HaloParams {
   long res_ld;
   void* out;                   // [n, ho, wo, out_ld]
   long out_ld;
+  // fused stem (darknet53_body/Conv 3->32 computed on the fly as the producer of Conv_1's halo planes)
+  const float* stem_w;         // [32][27] float32 OHWI, NULL: plain halo conv
+  const float* stem_scale;     // [32]
+  const float* stem_shift;     // [32]
+  int in_h, in_w;              // image size (= the stem's output size)
 };
 bool conv_halo_supported(const yb_conv_desc* d);
 int conv_halo_prepare(const yb_conv_desc* d, const void* x, const void* w_packed, const float* scale, const float* shift,
                       const void* res, void* out, HaloMaps* maps, HaloParams* p);
 int conv_halo_launch(const yb_conv_desc* d, const HaloMaps& maps, const HaloParams& p, cudaStream_t st);
+// stem (3->32, 3x3/1, BN + leaky) fused into Conv_1 (32->64, 3x3/2): d describes Conv_1 (its input = the stem's output,
+// which is never written); image float32 [n, d->h, d->w, 3].
+int conv_stem_halo_prepare(const yb_conv_desc* d, const float* image, const float* stem_w, const float* stem_scale,
+                           const float* stem_shift, const void* w_packed, const float* scale, const float* shift, void* out,
+                           HaloMaps* maps, HaloParams* p);
+int conv_stem_halo_launch(const yb_conv_desc* d, const HaloMaps& maps, const HaloParams& p, cudaStream_t st);
 int conv_launch(int dtype, int cout_pad, const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p,
                 cudaStream_t st);
 

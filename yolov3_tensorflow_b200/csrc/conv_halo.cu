@@ -31,6 +31,7 @@ namespace yb {
 
 int make_tmap_2d(CUtensorMap* tm, const void* base, int dtype, long rows, long cols, long ld, int box_rows, int box_cols,
                  int weights);
+int make_tmap_image3d(CUtensorMap* tm, const float* base, int n, int h, int w, int box_f, int box_h);
 int make_tmap_tiled4d(CUtensorMap* tm, const void* base, int dtype, int n, int h, int w, int c, long ld, int box_c,
                       int box_w, int box_h, int estride);
 
@@ -67,6 +68,37 @@ struct HaloCfg {
   static constexpr int tap_ds(int s) { return STRIDE == 1 ? s : (s == 2 ? 1 : 0); }
 };
 
+// Fused stem (darknet53_body/Conv, 3 -> 32, 3x3/1, utils/layer_utils.py:35) as the PRODUCER of Conv_1's parity planes:
+// the 709 MB stem output of a batch-64 step is never written nor re-read.  Per 16x8-pixel tile of Conv_1 the stem is
+// needed on 33 x 17 pixels; their 35 x 19-pixel float32 input halo arrives by one 3D TMA load, STEMW producer warps
+// compute the stem on mma.sync (m16n8k16: A = the 27 -> 32 patch values gathered straight from the halo, B = the stem
+// weights held in registers), apply BN + leaky and store the 16-bit results into the swizzled plane tiles the
+// tcgen05 descriptors of Conv_1 read.  Stem pixels outside the image are Conv_1's zero padding (utils/layer_utils.py:15-16).
+struct StemCfg {
+  static constexpr int SH = 2 * HT_H + 1, SW = 2 * HT_W + 1;             // stem pixels per tile: 33 x 17
+  static constexpr int NPX = SH * SW;                                     // 561
+  static constexpr int NT16 = (NPX + 15) / 16;                            // 36 m16 tiles
+  static constexpr int IN_ROWS = SH + 2;                                  // 35 image rows
+  static constexpr int IN_ROWF = 60;                                      // floats per halo row: 19 px x 3 = 57, padded to 16 bytes
+  static constexpr int IN_BYTES = (IN_ROWS * IN_ROWF * 4 + 127) / 128 * 128;
+  static constexpr int NIN = 2;                                           // input halo stages
+};
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void mma16816_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, bool bf16) {
+  if (bf16)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -74,10 +106,11 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
-template <typename T, int CIN, int COUT, int STRIDE>
-__global__ void __launch_bounds__(HALO_THREADS, 1)
+template <typename T, int CIN, int COUT, int STRIDE, int STEMW = 0>
+__global__ void __launch_bounds__(HALO_THREADS + 32 * STEMW, 1)
 conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ HaloParams p) {
   using C = HaloCfg<CIN, COUT, STRIDE>;
+  static_assert(STEMW == 0 || (CIN == 32 && STRIDE == 2), "the fused stem feeds Conv_1 (32 -> 64, stride 2)");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic: stays in the shared space
   uint8_t* sB = smem;                                        // [9][COUT][CIN]   swizzled, resident
@@ -91,20 +124,29 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
   uint64_t* b_bar = bars + 20;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
   float* s_ss = reinterpret_cast<float*>(sE + C::EPI_BYTES + C::MISC_BYTES);   // [2][COUT] scale / shift
+  uint64_t* in_full = bars + 24;        // [NIN] float32 input halo landed (TMA -> stem producers)
+  uint64_t* in_empty = bars + 26;       // [NIN] stem producers -> TMA
+  uint8_t* sIn = reinterpret_cast<uint8_t*>(s_ss + 2 * COUT);                  // [NIN][35][60] float32 (STEMW > 0 only; 128-byte aligned)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
+    if (STEMW == 0) {                            // (with the fused stem the plane maps are unused and zeroed)
 #pragma unroll
-    for (int i = 0; i < C::NPLANE; ++i) tma_prefetch_desc(&maps.plane[i]);
+      for (int i = 0; i < C::NPLANE; ++i) tma_prefetch_desc(&maps.plane[i]);
+    }
     tma_prefetch_desc(&maps.w);
-    for (int i = 0; i < C::NST; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < C::NST; ++i) { mbar_init(&full_bar[i], STEMW > 0 ? STEMW : 1); mbar_init(&empty_bar[i], 1); }
+    if (STEMW > 0) {
+      tma_prefetch_desc(&maps.in3d);
+      for (int i = 0; i < StemCfg::NIN; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], STEMW); }
+    }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
     mbar_init(b_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
-  for (int c = threadIdx.x; c < COUT; c += HALO_THREADS) {
+  for (int c = threadIdx.x; c < COUT; c += HALO_THREADS + 32 * STEMW) {
     s_ss[c] = c < p.cout ? __ldg(p.scale + c) : 0.f;
     s_ss[COUT + c] = c < p.cout ? __ldg(p.shift + c) : 0.f;
   }
@@ -121,7 +163,22 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
       for (int t = 0; t < 9; ++t) tma_load_2d(sB + t * C::B_TAP_BYTES, &maps.w, b_bar, t * CIN, 0);
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      if (STEMW > 0) {
+        // float32 image halo of the tile: rows 2 h0 - 2 .. 2 h0 + 32, pixels 2 w0 - 2 .. 2 w0 + 16 (x 3 channels),
+        // zero-filled outside the image (= the stem's SAME padding)
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+          const int tx = tile % p.tiles_x;
+          const int ty = (tile / p.tiles_x) % p.tiles_y;
+          const int img = tile / (p.tiles_x * p.tiles_y);
+          mbar_wait(&in_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&in_full[stage], (uint32_t)(StemCfg::IN_ROWS * StemCfg::IN_ROWF * 4));
+          // (the innermost TMA coordinate must be 16-byte aligned — an unaligned start is an illegal instruction; the halo's
+          //  first float (2 tx 8 - 2) * 3 is always 2 mod 4, so the box starts 2 floats earlier: 2 + 57 <= 60 floats per row)
+          tma_load_3d(sIn + stage * StemCfg::IN_BYTES, &maps.in3d, &in_full[stage], (2 * tx * HT_W - 2) * 3 - 2, 2 * ty * HT_H - 2, img);
+          if (++stage == StemCfg::NIN) { stage = 0; phase ^= 1; }
+        }
+      }
+      for (int tile = blockIdx.x; STEMW == 0 && tile < p.num_tiles; tile += gridDim.x) {
         const int tx = tile % p.tiles_x;
         const int ty = (tile / p.tiles_x) % p.tiles_y;
         const int img = tile / (p.tiles_x * p.tiles_y);
@@ -179,13 +236,131 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
       }
     }
     __syncwarp();
+  } else if (STEMW > 0 && warp >= 6) {
+    // ===================== stem producers (warps 6 .. 6 + STEMW - 1) =====================
+    const int pw_id = warp - 6;
+    const bool bf16 = std::is_same<T, __nv_bfloat16>::value;
+    const int g = lane >> 2, q = lane & 3;         // mma fragment coordinates: row group, column quad
+    // B fragments: stem weights W[n][k] (k = (r*3+s)*3+c < 27), n8 tile nt, k-step ks: b0 = k 2q..2q+1, b1 = k + 8
+    uint32_t bfrag[4][2][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+          const int n = nt * 8 + g, k = ks * 16 + hb * 8 + 2 * q;
+          const float w0 = k < 27 ? __ldg(p.stem_w + n * 27 + k) : 0.f;
+          const float w1 = k + 1 < 27 ? __ldg(p.stem_w + n * 27 + k + 1) : 0.f;
+          bfrag[nt][ks][hb] = Pack2<T>::pack(w0, w1);
+        }
+    float sc[4][2], sh[4][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        sc[nt][j] = __ldg(p.stem_scale + nt * 8 + 2 * q + j);
+        sh[nt][j] = __ldg(p.stem_shift + nt * 8 + 2 * q + j);
+      }
+    // halo offsets of this thread's 8 patch elements: k -> row k / 9, float k % 9 of the 3 x 9 patch
+    int koff[2][2][2];
+    bool kok[2][2][2];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int hb = 0; hb < 2; ++hb)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int k = ks * 16 + hb * 8 + 2 * q + j;
+          kok[ks][hb][j] = k < 27;
+          koff[ks][hb][j] = k < 27 ? (k / 9) * StemCfg::IN_ROWF + (k % 9) : 0;
+        }
+    int in_stage = 0, stage = 0;
+    uint32_t in_phase = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int tx = tile % p.tiles_x;
+      const int ty = (tile / p.tiles_x) % p.tiles_y;
+      const int gy0 = 2 * ty * HT_H - 1, gx0 = 2 * tx * HT_W - 1;      // image coordinates of stem pixel (0, 0) of the tile
+      mbar_wait(&in_full[in_stage], in_phase);
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      const float* halo = reinterpret_cast<const float*>(sIn + in_stage * StemCfg::IN_BYTES) + 2;   // see the TMA coordinate
+      uint8_t* planes = sA + stage * C::STAGE_BYTES;
+      // The 561 stem pixels are walked PLANE BY PLANE in m16 tiles (10 + 9 + 9 + 8 = 36): a tile lies inside one plane, so
+      // the plane's constants are warp-uniform, consecutive fragment rows are consecutive 64-byte rows of the plane tile,
+      // and the pixel -> (row, col) split is one constant division (the first version split every pixel index by 17 and
+      // selected the plane per pixel: ~250 instructions per m16 tile, issue-bound at 6.5 k cycles per output tile).
+#pragma unroll 1
+      for (int t = pw_id; t < StemCfg::NT16; t += STEMW) {
+        const int pl = t < 10 ? 0 : (t < 19 ? 1 : (t < 28 ? 2 : 3));              // warp-uniform
+        const int t0 = pl == 0 ? 0 : (pl == 1 ? 10 : (pl == 2 ? 19 : 28));
+        const int pwid = (pl & 1) == 0 ? HT_W + 1 : HT_W;
+        const int npl = ((pl >> 1) == 0 ? HT_H + 1 : HT_H) * pwid;                // pixels of this plane
+        const int poff = pl == 0 ? C::poff(0) : (pl == 1 ? C::poff(1) : (pl == 2 ? C::poff(2) : C::poff(3)));
+        const int ya = pl >> 1, xb = pl & 1;                                       // stem row = 2 * plane row + ya, col likewise
+        uint32_t a[2][4];
+        int rho[2];
+        bool live[2], inside[2];
+#pragma unroll
+        for (int hr = 0; hr < 2; ++hr) {                       // fragment rows g and g + 8
+          rho[hr] = (t - t0) * 16 + g + 8 * hr;
+          live[hr] = rho[hr] < npl;
+          const int r_ = live[hr] ? rho[hr] : 0;
+          const int pr = (pl & 1) == 0 ? r_ / (HT_W + 1) : r_ >> 3;
+          const int pc = r_ - pr * pwid;
+          const int sy = 2 * pr + ya, sx = 2 * pc + xb;
+          inside[hr] = live[hr] && gy0 + sy >= 0 && gy0 + sy < p.in_h && gx0 + sx >= 0 && gx0 + sx < p.in_w;
+          const float* base = halo + sy * StemCfg::IN_ROWF + sx * 3;
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+            for (int hb = 0; hb < 2; ++hb) {
+              const float v0 = kok[ks][hb][0] ? base[koff[ks][hb][0]] : 0.f;
+              const float v1 = kok[ks][hb][1] ? base[koff[ks][hb][1]] : 0.f;
+              a[ks][hb * 2 + hr] = Pack2<T>::pack(v0, v1);       // a0: row g, k lo; a1: row g+8, k lo; a2: row g, k hi; a3: row g+8, k hi
+            }
+        }
+        float acc[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) mma16816_f16(acc[nt], a[ks], bfrag[nt][ks][0], bfrag[nt][ks][1], bf16);
+        }
+#pragma unroll
+        for (int hr = 0; hr < 2; ++hr) {
+          if (!live[hr]) continue;
+          uint8_t* row = planes + poff + rho[hr] * 64 + q * 4;
+          const int swz = (rho[hr] >> 1) & 3;
+          if (inside[hr]) {
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+              float v0 = fmaf(acc[nt][2 * hr], sc[nt][0], sh[nt][0]);
+              float v1 = fmaf(acc[nt][2 * hr + 1], sc[nt][1], sh[nt][1]);
+              v0 = fmaxf(v0, 0.1f * v0); v1 = fmaxf(v1, 0.1f * v1);      // leaky_relu(0.1), model.py:47
+              *reinterpret_cast<uint32_t*>(row + ((nt ^ swz) << 4)) = Pack2<T>::pack(v0, v1);
+            }
+          } else {                                                        // outside the image: Conv_1's zero padding
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) *reinterpret_cast<uint32_t*>(row + ((nt ^ swz) << 4)) = 0u;
+          }
+        }
+      }
+      fence_proxy_async();                       // generic-proxy plane writes -> visible to tcgen05.mma (async proxy)
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&full_bar[stage]);
+        mbar_arrive(&in_empty[in_stage]);
+      }
+      if (++in_stage == StemCfg::NIN) { in_stage = 0; in_phase ^= 1; }
+      if (++stage == C::NST) { stage = 0; phase ^= 1; }
+    }
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int quarter = warp & 3;                  // TMEM lanes [32 q, 32 q + 32): output rows 4q .. 4q+3 of the tile
     uint8_t* stage2 = sE + (warp - 2) * 4096;
     const int sw = (lane >> 1) & 3;
     const int cq = lane & 3, cr0 = lane >> 2;      // coalesced layout: staging row 8k + cr0 (tile row 4q + k, col cr0), piece cq
-    const bool has_res = p.res != nullptr;
+    const bool has_res = STEMW == 0 && p.res != nullptr;      // (Conv_1 has no shortcut: the residual code is compiled out of the fused kernel)
     constexpr int NCH = COUT / 32;
     uint32_t cnt = 0;
     int it = 0;
@@ -319,6 +494,51 @@ static int launch_halo(const HaloMaps& maps, const HaloParams& p, cudaStream_t s
   return YB_OK;
 }
 
+static constexpr int STEM_WARPS = 8;
+
+template <typename T>
+static int launch_stem_halo(const HaloMaps& maps, const HaloParams& p, cudaStream_t st) {
+  using C = HaloCfg<32, 64, 2>;
+  constexpr int SMEM = C::SMEM_BYTES + StemCfg::NIN * StemCfg::IN_BYTES;
+  static_assert(SMEM <= 227 * 1024, "fused stem + Conv_1 does not fit shared memory");
+  static DeviceOnce once;
+  auto kern = conv_halo_kernel<T, 32, 64, 2, STEM_WARPS>;
+  { const int rc = ensure_smem_attr(once, reinterpret_cast<const void*>(kern), SMEM); if (rc) return rc; }
+  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  kern<<<grid, HALO_THREADS + 32 * STEM_WARPS, SMEM, st>>>(maps, p);
+  YB_CUDA(cudaGetLastError());
+  return YB_OK;
+}
+
+int conv_stem_halo_prepare(const yb_conv_desc* d, const float* image, const float* stem_w, const float* stem_scale,
+                           const float* stem_shift, const void* w_packed, const float* scale, const float* shift, void* out,
+                           HaloMaps* maps, HaloParams* p) {
+  YB_REQUIRE(d->ksize == 3 && d->stride == 2 && d->cin == 32 && d->cout == 64 && !d->out_fp32 && !d->upsample2x,
+             "conv_stem_halo: Conv_1 is 3x3/2 32->64 (got k=%d s=%d %d->%d)", d->ksize, d->stride, d->cin, d->cout);
+  YB_REQUIRE(d->h % 2 == 0 && d->w % 16 == 0 && d->out_ld % 8 == 0 && d->out_ld >= 64, "conv_stem_halo: bad geometry (h=%d w=%d)", d->h, d->w);
+  YB_REQUIRE(image && stem_w && stem_scale && stem_shift && w_packed && scale && shift && out, "conv_stem_halo: null pointer");
+  YB_REQUIRE(((uintptr_t)image & 15) == 0 && ((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)out & 15) == 0, "conv_stem_halo: pointers must be 16-byte aligned");
+  memset(maps, 0, sizeof(*maps));
+  memset(p, 0, sizeof(*p));
+  p->n = d->n; p->ho = d->h / 2; p->wo = d->w / 2;
+  p->tiles_x = p->wo / HT_W; p->tiles_y = ceil_div(p->ho, HT_H);
+  p->num_tiles = p->tiles_x * p->tiles_y * d->n;
+  p->cout = d->cout; p->leaky = d->leaky; p->scale = scale; p->shift = shift;
+  p->res = nullptr; p->res_ld = 0; p->out = out; p->out_ld = d->out_ld;
+  p->stem_w = stem_w; p->stem_scale = stem_scale; p->stem_shift = stem_shift; p->in_h = d->h; p->in_w = d->w;
+  int rc = make_tmap_image3d(&maps->in3d, image, d->n, d->h, d->w, StemCfg::IN_ROWF, StemCfg::IN_ROWS);
+  if (rc) return rc;
+  const long K = 9L * d->cin;
+  return make_tmap_2d(&maps->w, w_packed, d->dtype, yb_conv_cout_pad(d->cout), K, K, d->cout, d->cin, 1);
+}
+
+int conv_stem_halo_launch(const yb_conv_desc* d, const HaloMaps& maps, const HaloParams& p, cudaStream_t st) {
+  if (d->dtype == YB_F16) return launch_stem_halo<__half>(maps, p, st);
+  if (d->dtype == YB_BF16) return launch_stem_halo<__nv_bfloat16>(maps, p, st);
+  set_error("conv_stem_halo: dtype must be f16 or bf16");
+  return YB_ERR_UNSUPPORTED;
+}
+
 bool conv_halo_supported(const yb_conv_desc* d) {
   if (d->ksize != 3 || (d->stride != 1 && d->stride != 2)) return false;
   if (!(d->cin == 32 || d->cin == 64) || !(d->cout == 64 || d->cout == 128)) return false;
@@ -338,6 +558,7 @@ int conv_halo_prepare(const yb_conv_desc* d, const void* x, const void* w_packed
              "conv_halo: pointers must be 16-byte aligned");
   if (res) YB_REQUIRE(d->res_ld >= d->cout && d->res_ld % 8 == 0, "conv_halo: res_ld %d invalid", d->res_ld);
   memset(maps, 0, sizeof(*maps));
+  memset(p, 0, sizeof(*p));
   p->n = d->n; p->ho = d->h / d->stride; p->wo = d->w / d->stride;
   p->tiles_x = p->wo / HT_W; p->tiles_y = ceil_div(p->ho, HT_H);
   p->num_tiles = p->tiles_x * p->tiles_y * d->n;
@@ -390,4 +611,17 @@ extern "C" int yb_conv3x3_halo_fwd(const yb_conv_desc* d, const void* x, const v
   int rc = conv_halo_prepare(d, x, w_packed, scale, shift, res, out, &maps, &p);
   if (rc) return rc;
   return conv_halo_launch(d, maps, p, static_cast<cudaStream_t>(stream));
+}
+
+// Stem + Conv_1 in one kernel (utils/layer_utils.py:35-36): image float32 [n, h, w, 3] -> Conv_1's output [n, h/2, w/2, out_ld].
+// d describes Conv_1 (h, w = image size = the stem's output size).  The stem's BN is folded into stem_scale / stem_shift.
+extern "C" int yb_stem_conv1_fused_fwd(const yb_conv_desc* d, const float* image, const float* stem_w_ohwi,
+                                       const float* stem_scale, const float* stem_shift, const void* w_packed,
+                                       const float* scale, const float* shift, void* out, void* stream) {
+  if (!d) { set_error("stem_conv1_fused: null descriptor"); return YB_ERR_INVALID_ARGUMENT; }
+  HaloMaps maps;
+  HaloParams p;
+  int rc = conv_stem_halo_prepare(d, image, stem_w_ohwi, stem_scale, stem_shift, w_packed, scale, shift, out, &maps, &p);
+  if (rc) return rc;
+  return conv_stem_halo_launch(d, maps, p, static_cast<cudaStream_t>(stream));
 }

@@ -1167,6 +1167,25 @@ int make_tmap_2d(CUtensorMap* tm, const void* base, int dtype, long rows, long c
   return YB_OK;
 }
 
+// float32 image [n, h, w, 3] seen as {W*3, H, N}: box = box_f floats x box_h rows of one image, no swizzle, zero fill
+// outside (the fused stem's input halo, csrc/conv_halo.cu).  w*3*4 bytes must be a multiple of 16 (w % 4 == 0).
+int make_tmap_image3d(CUtensorMap* tm, const float* base, int n, int h, int w, int box_f, int box_h) {
+  int rc = load_driver_entry_points();
+  if (rc) return rc;
+  cuuint64_t dims[3] = {(cuuint64_t)w * 3, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[2] = {(cuuint64_t)w * 3 * 4, (cuuint64_t)h * w * 3 * 4};
+  cuuint32_t box[3] = {(cuuint32_t)box_f, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(image) failed (%d): n=%d h=%d w=%d box=%dx%d", (int)r, n, h, w, box_f, box_h);
+    return YB_ERR_CUDA;
+  }
+  return YB_OK;
+}
+
 // NHWC activation seen as {C, W, H, N}, TILED mode: box = box_c channels x box_w x box_h pixels of one image, traversal
 // stride `estride` along W and H (a box spanning 2 * count - 1 pixels at stride 2 loads `count` of them); pixels outside
 // the image come back zero-filled.  Used by the halo-tile conv (csrc/conv_halo.cu).

@@ -312,7 +312,11 @@ static int forward_layers_impl(yb_net* net, const float* images, float* fm1, flo
     if (rc) return rc;
   }
   const bool thin = opt("YB_THIN")[0] != '0';   // A/B switch for the thin-layer kernels
-  if (first == 0) {
+  // stem fused into Conv_1 (csrc/conv_halo.cu): layer 0's output is never written.  YB_STEM_FUSE=0: two launches.
+  // (a layer range that stops at layer 0 then launches nothing: the stem no longer exists as a launch of its own)
+  const bool fuse_stem = opt("YB_STEM_FUSE")[0] != '0' && net->layers.size() > 1 && net->layers[1].halo_ok &&
+                         net->layers[1].info.cin == 32 && net->layers[1].info.stride == 2 && opt("YB_HALO")[0] != '0';
+  if (first == 0 && !fuse_stem) {
     Layer& L = net->layers[0];
     int rc;
     if (thin)
@@ -343,6 +347,20 @@ static int forward_layers_impl(yb_net* net, const float* images, float* fm1, flo
                                    reinterpret_cast<const float*>(net->par + L.scale),
                                    reinterpret_cast<const float*>(net->par + L.shift),
                                    L.res.buf >= 0 ? ten_ptr(net, L.res) : nullptr, ten_ptr(net, L.out), stream);
+      if (rc) return rc;
+      continue;
+    }
+    if (i == 1 && fuse_stem && first <= 1) {
+      Layer& L0 = net->layers[0];
+      HaloMaps hm;
+      HaloParams hp;
+      int rc = conv_stem_halo_prepare(&L.halo_desc, images, reinterpret_cast<const float*>(net->par + L0.w_master),
+                                      reinterpret_cast<const float*>(net->par + L0.scale),
+                                      reinterpret_cast<const float*>(net->par + L0.shift), net->par + L.w_packed,
+                                      reinterpret_cast<const float*>(net->par + L.scale),
+                                      reinterpret_cast<const float*>(net->par + L.shift), ten_ptr(net, L.out), &hm, &hp);
+      if (rc) return rc;
+      rc = conv_stem_halo_launch(&L.halo_desc, hm, hp, st);
       if (rc) return rc;
       continue;
     }
