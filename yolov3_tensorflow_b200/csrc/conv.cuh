@@ -65,6 +65,7 @@ struct HaloParams {
   const float* stem_scale;     // [32]
   const float* stem_shift;     // [32]
   int in_h, in_w;              // image size (= the stem's output size)
+  int direct;                  // 1: direct 256-bit register stores (no residual, 32-byte aligned dense rows)
 };
 bool conv_halo_supported(const yb_conv_desc* d);
 int conv_halo_prepare(const yb_conv_desc* d, const void* x, const void* w_packed, const float* scale, const float* shift,

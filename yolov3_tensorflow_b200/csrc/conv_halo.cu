@@ -90,6 +90,12 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uin
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// 256-bit global store (sm_100: STG.E.ENL2.256): one full 32-byte sector per lane
+__device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 __device__ __forceinline__ void mma16816_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, bool bf16) {
   if (bf16)
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -106,10 +112,15 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
-template <typename T, int CIN, int COUT, int STRIDE, int STEMW = 0>
-__global__ void __launch_bounds__(HALO_THREADS + 32 * STEMW, 1)
+// EPIG = 2: a second group of four epilogue warps drains the other accumulator stage (tiles alternate between the groups);
+// it uses the DIRECT epilogue only (no residual, dense 32-byte aligned rows: every lane stores its pixel's chunk as two
+// 256-bit st.global — with out_ld = 64 a lane owns a whole 128-byte line — so the groups need no staging tiles).
+template <typename T, int CIN, int COUT, int STRIDE, int STEMW = 0, int EPIG = 1>
+__global__ void __launch_bounds__(64 + 128 * EPIG + 32 * STEMW, 1)
 conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ HaloParams p) {
   using C = HaloCfg<CIN, COUT, STRIDE>;
+  constexpr int NTHREADS = 64 + 128 * EPIG + 32 * STEMW;
+  constexpr int PROD_WARP0 = 2 + 4 * EPIG;       // first stem-producer warp
   static_assert(STEMW == 0 || (CIN == 32 && STRIDE == 2), "the fused stem feeds Conv_1 (32 -> 64, stride 2)");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic: stays in the shared space
@@ -146,7 +157,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
-  for (int c = threadIdx.x; c < COUT; c += HALO_THREADS + 32 * STEMW) {
+  for (int c = threadIdx.x; c < COUT; c += NTHREADS) {
     s_ss[c] = c < p.cout ? __ldg(p.scale + c) : 0.f;
     s_ss[COUT + c] = c < p.cout ? __ldg(p.shift + c) : 0.f;
   }
@@ -236,9 +247,9 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
       }
     }
     __syncwarp();
-  } else if (STEMW > 0 && warp >= 6) {
-    // ===================== stem producers (warps 6 .. 6 + STEMW - 1) =====================
-    const int pw_id = warp - 6;
+  } else if (STEMW > 0 && warp >= PROD_WARP0) {
+    // ===================== stem producers (warps PROD_WARP0 .. PROD_WARP0 + STEMW - 1) =====================
+    const int pw_id = warp - PROD_WARP0;
     const bool bf16 = std::is_same<T, __nv_bfloat16>::value;
     const int g = lane >> 2, q = lane & 3;         // mma fragment coordinates: row group, column quad
     // B fragments: stem weights W[n][k] (k = (r*3+s)*3+c < 27), n8 tile nt, k-step ks: b0 = k 2q..2q+1, b1 = k + 8
@@ -264,7 +275,6 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
       }
     // halo offsets of this thread's 8 patch elements: k -> row k / 9, float k % 9 of the 3 x 9 patch
     int koff[2][2][2];
-    bool kok[2][2][2];
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
@@ -272,7 +282,6 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int k = ks * 16 + hb * 8 + 2 * q + j;
-          kok[ks][hb][j] = k < 27;
           koff[ks][hb][j] = k < 27 ? (k / 9) * StemCfg::IN_ROWF + (k % 9) : 0;
         }
     int in_stage = 0, stage = 0;
@@ -289,53 +298,58 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
       // the plane's constants are warp-uniform, consecutive fragment rows are consecutive 64-byte rows of the plane tile,
       // and the pixel -> (row, col) split is one constant division (the first version split every pixel index by 17 and
       // selected the plane per pixel: ~250 instructions per m16 tile, issue-bound at 6.5 k cycles per output tile).
-#pragma unroll 1
-      for (int t = pw_id; t < StemCfg::NT16; t += STEMW) {
+      struct M16 {                                 // one m16 tile of stem pixels in flight
+        uint32_t a[2][4];
+        float acc[4][4];
+        int rho[2], poff;
+        bool live[2], inside[2];
+      };
+      auto gather = [&](const int t, M16& m) {
         const int pl = t < 10 ? 0 : (t < 19 ? 1 : (t < 28 ? 2 : 3));              // warp-uniform
         const int t0 = pl == 0 ? 0 : (pl == 1 ? 10 : (pl == 2 ? 19 : 28));
         const int pwid = (pl & 1) == 0 ? HT_W + 1 : HT_W;
         const int npl = ((pl >> 1) == 0 ? HT_H + 1 : HT_H) * pwid;                // pixels of this plane
-        const int poff = pl == 0 ? C::poff(0) : (pl == 1 ? C::poff(1) : (pl == 2 ? C::poff(2) : C::poff(3)));
+        m.poff = pl == 0 ? C::poff(0) : (pl == 1 ? C::poff(1) : (pl == 2 ? C::poff(2) : C::poff(3)));
         const int ya = pl >> 1, xb = pl & 1;                                       // stem row = 2 * plane row + ya, col likewise
-        uint32_t a[2][4];
-        int rho[2];
-        bool live[2], inside[2];
 #pragma unroll
         for (int hr = 0; hr < 2; ++hr) {                       // fragment rows g and g + 8
-          rho[hr] = (t - t0) * 16 + g + 8 * hr;
-          live[hr] = rho[hr] < npl;
-          const int r_ = live[hr] ? rho[hr] : 0;
+          m.rho[hr] = (t - t0) * 16 + g + 8 * hr;
+          m.live[hr] = m.rho[hr] < npl;
+          const int r_ = m.live[hr] ? m.rho[hr] : 0;
           const int pr = (pl & 1) == 0 ? r_ / (HT_W + 1) : r_ >> 3;
           const int pc = r_ - pr * pwid;
           const int sy = 2 * pr + ya, sx = 2 * pc + xb;
-          inside[hr] = live[hr] && gy0 + sy >= 0 && gy0 + sy < p.in_h && gx0 + sx >= 0 && gx0 + sx < p.in_w;
+          m.inside[hr] = m.live[hr] && gy0 + sy >= 0 && gy0 + sy < p.in_h && gx0 + sx >= 0 && gx0 + sx < p.in_w;
           const float* base = halo + sy * StemCfg::IN_ROWF + sx * 3;
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
             for (int hb = 0; hb < 2; ++hb) {
-              const float v0 = kok[ks][hb][0] ? base[koff[ks][hb][0]] : 0.f;
-              const float v1 = kok[ks][hb][1] ? base[koff[ks][hb][1]] : 0.f;
-              a[ks][hb * 2 + hr] = Pack2<T>::pack(v0, v1);       // a0: row g, k lo; a1: row g+8, k lo; a2: row g, k hi; a3: row g+8, k hi
+              const float v0 = base[koff[ks][hb][0]];            // (k >= 27: offset 0, a finite value times a zero weight)
+              const float v1 = base[koff[ks][hb][1]];
+              m.a[ks][hb * 2 + hr] = Pack2<T>::pack(v0, v1);     // a0: row g, k lo; a1: row g+8, k lo; a2: row g, k hi; a3: row g+8, k hi
             }
         }
-        float acc[4][4];
+      };
+      auto multiply = [&](M16& m) {
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
-          acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+          m.acc[nt][0] = m.acc[nt][1] = m.acc[nt][2] = m.acc[nt][3] = 0.f;
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks) mma16816_f16(acc[nt], a[ks], bfrag[nt][ks][0], bfrag[nt][ks][1], bf16);
+          for (int ks = 0; ks < 2; ++ks) mma16816_f16(m.acc[nt], m.a[ks], bfrag[nt][ks][0], bfrag[nt][ks][1], bf16);
         }
+      };
+      auto store = [&](const M16& m) {
 #pragma unroll
         for (int hr = 0; hr < 2; ++hr) {
-          if (!live[hr]) continue;
-          uint8_t* row = planes + poff + rho[hr] * 64 + q * 4;
-          const int swz = (rho[hr] >> 1) & 3;
-          if (inside[hr]) {
+          if (!m.live[hr]) continue;
+          uint8_t* row = planes + m.poff + m.rho[hr] * 64 + q * 4;
+          const int swz = (m.rho[hr] >> 1) & 3;
+          if (m.inside[hr]) {
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
-              float v0 = fmaf(acc[nt][2 * hr], sc[nt][0], sh[nt][0]);
-              float v1 = fmaf(acc[nt][2 * hr + 1], sc[nt][1], sh[nt][1]);
+              float v0 = fmaf(m.acc[nt][2 * hr], sc[nt][0], sh[nt][0]);
+              float v1 = fmaf(m.acc[nt][2 * hr + 1], sc[nt][1], sh[nt][1]);
               v0 = fmaxf(v0, 0.1f * v0); v1 = fmaxf(v1, 0.1f * v1);      // leaky_relu(0.1), model.py:47
               *reinterpret_cast<uint32_t*>(row + ((nt ^ swz) << 4)) = Pack2<T>::pack(v0, v1);
             }
@@ -344,6 +358,17 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
             for (int nt = 0; nt < 4; ++nt) *reinterpret_cast<uint32_t*>(row + ((nt ^ swz) << 4)) = 0u;
           }
         }
+      };
+      // The 561 stem pixels are walked PLANE BY PLANE in m16 tiles (10 + 9 + 9 + 8 = 36): a tile lies inside one plane, so
+      // the plane's constants are warp-uniform and consecutive fragment rows are consecutive 64-byte rows of the plane tile.
+      // The producers are latency-bound, not issue-bound: 12 warps beat 8 (408 vs 465 us); keeping TWO tiles in flight per
+      // warp lost to the register pressure (498 / 538 us) and was dropped.
+#pragma unroll 1
+      for (int t = pw_id; t < StemCfg::NT16; t += STEMW) {
+        M16 m0;
+        gather(t, m0);
+        multiply(m0);
+        store(m0);
       }
       fence_proxy_async();                       // generic-proxy plane writes -> visible to tcgen05.mma (async proxy)
       __syncwarp();
@@ -357,13 +382,15 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int quarter = warp & 3;                  // TMEM lanes [32 q, 32 q + 32): output rows 4q .. 4q+3 of the tile
-    uint8_t* stage2 = sE + (warp - 2) * 4096;
+    const int grp = (warp - 2) >> 2;               // epilogue group: accumulator stage grp, tiles with iteration % EPIG == grp
+    uint8_t* stage2 = sE + ((warp - 2) & 3) * 4096;          // (staging is used by the non-direct path, EPIG = 1 only)
+    const bool direct = EPIG == 2 || p.direct != 0;
     const int sw = (lane >> 1) & 3;
     const int cq = lane & 3, cr0 = lane >> 2;      // coalesced layout: staging row 8k + cr0 (tile row 4q + k, col cr0), piece cq
     const bool has_res = STEMW == 0 && p.res != nullptr;      // (Conv_1 has no shortcut: the residual code is compiled out of the fused kernel)
     constexpr int NCH = COUT / 32;
     uint32_t cnt = 0;
-    int it = 0;
+    int it = grp;
     uint4 rnext[4];
     bool prefetched = false;
     auto pix_base = [&](int tile, long (&off)[4], bool (&ok)[4]) {
@@ -383,12 +410,12 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
         rnext[k] = ok[k] ? __ldg(reinterpret_cast<const uint4*>(static_cast<const T*>(p.res) + off[k] * p.res_ld + col0 + cq * 8))
                          : make_uint4(0u, 0u, 0u, 0u);
     };
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < p.num_tiles; tile += EPIG * gridDim.x, it += EPIG) {
       const int acc = it & 1;
       long off[4], noff[4];
       bool ok[4], nok[4];
       pix_base(tile, off, ok);
-      const int ntile = tile + gridDim.x;
+      const int ntile = tile + EPIG * gridDim.x;
       const bool has_next = ntile < p.num_tiles;
       if (has_res && has_next) pix_base(ntile, noff, nok);
       if (has_res && !prefetched) fetch_res(off, ok, 0);
@@ -464,10 +491,56 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ 
         }
         ++cnt;
       };
+      // direct path: this lane's pixel (tile row 4q + lane / 8, column lane % 8) and its 32 channels of a chunk = 64 bytes
+      long my_off = 0;
+      bool my_ok = false;
+      if (direct) {
+        const int tx = tile % p.tiles_x;
+        const int ty = (tile / p.tiles_x) % p.tiles_y;
+        const int img = tile / (p.tiles_x * p.tiles_y);
+        const int oh = ty * HT_H + 4 * quarter + (lane >> 3), ow = tx * HT_W + (lane & 7);
+        my_ok = oh < p.ho && ow < p.wo;
+        my_off = (((long)img * p.ho + oh) * p.wo + ow) * p.out_ld;
+      }
+      auto chunk_direct = [&](const uint32_t (&r)[32], const int ch) {
+        float v[32];
+        const float4* sc4 = reinterpret_cast<const float4*>(s_ss + ch * 32);
+        const float4* sh4 = reinterpret_cast<const float4*>(s_ss + COUT + ch * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 sc = sc4[j];
+          const float4 sh = sh4[j];
+          v[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), sc.x, sh.x);
+          v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), sc.y, sh.y);
+          v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), sc.z, sh.z);
+          v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), sc.w, sh.w);
+        }
+        if (p.leaky) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.1f * v[j]);
+        }
+        if (my_ok) {
+          uint32_t lo[8], hi[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            lo[j] = Pack2<T>::pack(v[2 * j], v[2 * j + 1]);
+            hi[j] = Pack2<T>::pack(v[16 + 2 * j], v[16 + 2 * j + 1]);
+          }
+          T* dst = static_cast<T*>(p.out) + my_off + ch * 32;
+          st_global_v8(dst, lo);
+          st_global_v8(dst + 16, hi);
+        }
+      };
       tmem_ld_wait();
-      chunk(r0, 0);
-      chunk(r1, 1);
-      if (NCH > 2) { chunk(r2, 2); chunk(r3, 3); }
+      if (direct) {
+        chunk_direct(r0, 0);
+        chunk_direct(r1, 1);
+        if (NCH > 2) { chunk_direct(r2, 2); chunk_direct(r3, 3); }
+      } else if (EPIG == 1) {
+        chunk(r0, 0);
+        chunk(r1, 1);
+        if (NCH > 2) { chunk(r2, 2); chunk(r3, 3); }
+      }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -494,18 +567,16 @@ static int launch_halo(const HaloMaps& maps, const HaloParams& p, cudaStream_t s
   return YB_OK;
 }
 
-static constexpr int STEM_WARPS = 8;
-
-template <typename T>
+template <typename T, int STEM_WARPS, int EPIG>
 static int launch_stem_halo(const HaloMaps& maps, const HaloParams& p, cudaStream_t st) {
   using C = HaloCfg<32, 64, 2>;
   constexpr int SMEM = C::SMEM_BYTES + StemCfg::NIN * StemCfg::IN_BYTES;
   static_assert(SMEM <= 227 * 1024, "fused stem + Conv_1 does not fit shared memory");
   static DeviceOnce once;
-  auto kern = conv_halo_kernel<T, 32, 64, 2, STEM_WARPS>;
+  auto kern = conv_halo_kernel<T, 32, 64, 2, STEM_WARPS, EPIG>;
   { const int rc = ensure_smem_attr(once, reinterpret_cast<const void*>(kern), SMEM); if (rc) return rc; }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  kern<<<grid, HALO_THREADS + 32 * STEM_WARPS, SMEM, st>>>(maps, p);
+  kern<<<grid, 64 + 128 * EPIG + 32 * STEM_WARPS, SMEM, st>>>(maps, p);
   YB_CUDA(cudaGetLastError());
   return YB_OK;
 }
@@ -526,6 +597,7 @@ int conv_stem_halo_prepare(const yb_conv_desc* d, const float* image, const floa
   p->cout = d->cout; p->leaky = d->leaky; p->scale = scale; p->shift = shift;
   p->res = nullptr; p->res_ld = 0; p->out = out; p->out_ld = d->out_ld;
   p->stem_w = stem_w; p->stem_scale = stem_scale; p->stem_shift = stem_shift; p->in_h = d->h; p->in_w = d->w;
+  p->direct = (d->out_ld % 16 == 0 && ((uintptr_t)out & 31) == 0 && opt("YB_HALO_DIRECT")[0] != '0') ? 1 : 0;
   int rc = make_tmap_image3d(&maps->in3d, image, d->n, d->h, d->w, StemCfg::IN_ROWF, StemCfg::IN_ROWS);
   if (rc) return rc;
   const long K = 9L * d->cin;
@@ -533,8 +605,16 @@ int conv_stem_halo_prepare(const yb_conv_desc* d, const float* image, const floa
 }
 
 int conv_stem_halo_launch(const yb_conv_desc* d, const HaloMaps& maps, const HaloParams& p, cudaStream_t st) {
-  if (d->dtype == YB_F16) return launch_stem_halo<__half>(maps, p, st);
-  if (d->dtype == YB_BF16) return launch_stem_halo<__nv_bfloat16>(maps, p, st);
+  // A/B switches: YB_STEM_WARPS = 8 | 12 producer warps, YB_STEM_EPIG = 1 | 2 epilogue groups
+  const bool w12 = opt("YB_STEM_WARPS")[0] != '8';      // default: twelve producer warps
+  const bool direct_ok = d->out_ld % 16 == 0 && ((uintptr_t)p.out & 31) == 0;
+  const bool eg2 = direct_ok && opt("YB_STEM_EPIG")[0] == '2';
+#define YB_STEM_LAUNCH(T)                                                        \
+  if (eg2) return w12 ? launch_stem_halo<T, 12, 2>(maps, p, st) : launch_stem_halo<T, 8, 2>(maps, p, st); \
+  return w12 ? launch_stem_halo<T, 12, 1>(maps, p, st) : launch_stem_halo<T, 8, 1>(maps, p, st);
+  if (d->dtype == YB_F16) { YB_STEM_LAUNCH(__half) }
+  if (d->dtype == YB_BF16) { YB_STEM_LAUNCH(__nv_bfloat16) }
+#undef YB_STEM_LAUNCH
   set_error("conv_stem_halo: dtype must be f16 or bf16");
   return YB_ERR_UNSUPPORTED;
 }
@@ -564,6 +644,8 @@ int conv_halo_prepare(const yb_conv_desc* d, const void* x, const void* w_packed
   p->num_tiles = p->tiles_x * p->tiles_y * d->n;
   p->cout = d->cout; p->leaky = d->leaky; p->scale = scale; p->shift = shift;
   p->res = res; p->res_ld = d->res_ld; p->out = out; p->out_ld = d->out_ld;
+  // direct 256-bit stores when there is no residual and the rows are 32-byte aligned
+  p->direct = (!res && d->out_ld % 16 == 0 && ((uintptr_t)out & 31) == 0 && opt("YB_HALO_DIRECT")[0] != '0') ? 1 : 0;
   int rc;
   if (d->stride == 1) {
     rc = make_tmap_tiled4d(&maps->plane[0], x, d->dtype, d->n, d->h, d->w, d->cin, d->in_ld, d->cin, HT_W + 2, HT_H + 2, 1);
