@@ -185,6 +185,13 @@ int yb_bn_finalize(const float* sum, const float* sqsum, long count, int c, cons
 int yb_bn_act_apply(const void* z, long z_ld, const float* scale, const float* shift, const void* res, long res_ld,
                     void* out, long out_ld, int n, int h, int w, int c, int dtype, int leaky, int upsample2x,
                     void* stream);
+/* yb_bn_finalize + yb_bn_act_apply in ONE launch (count = n*h*w; same arguments, bit-identical results): the training
+ * forward of a BN conv (slim.batch_norm(is_training=True) + leaky_relu, reference model.py:35-41). */
+int yb_bn_stats_act_apply(const void* z, long z_ld, const float* sum, const float* sqsum, const float* gamma,
+                          const float* beta, float eps, float decay, float* moving_mean, float* moving_var,
+                          float* scale, float* shift, float* save_mean, float* save_invstd, const void* res,
+                          long res_ld, void* out, long out_ld, int n, int h, int w, int c, int dtype, int leaky,
+                          int upsample2x, void* stream);
 /* dgamma/dbeta (fp32 [c], overwritten) from dA (gradient w.r.t. the layer output; upsample2x: summed over the
  * 4 copies) and the saved z.  workspace: NULL (atomic accumulation) or yb_bn_bwd_reduce_workspace_bytes() bytes,
  * zero-initialised once (two-stage deterministic reduction, no same-address atomics). */

@@ -447,6 +447,32 @@ def test_train_backward_self_consistency():
     assert not bad, bad[:8]
 
 
+def test_dgrad_weight_repack_multi_tensor_equals_per_layer():
+    """The one-launch repack of all 74 layers' dgrad weights (pack_dgrad_all) against the per-layer kernels, bit for bit
+    (plain flip + transpose layers and the four parity-class matrices of the stride-2 layers)."""
+    params, x, y_true = _train_case()
+    m = _pkg().yolov3(80, O.COCO_ANCHORS, batch_norm_decay=0.99, dtype="bf16")
+    m.set_params(params, "HWIO")
+    m.train_step(torch.from_numpy(x).cuda(), [torch.from_numpy(y).cuda() for y in y_true], 1e-3)
+    plan = m._last_plan
+    from yolov3_tensorflow_b200 import _lib
+    lib = _lib.lib
+    got = {}
+    for mode in ("0", None):
+        _lib.set_option("YB_PACK_MT", mode)
+        try:
+            for i in range(1, 75):
+                plan.dgrad_weights(i).fill_(7.0)
+            _lib.check(lib.yb_net_train_refresh_dgrad(plan.handle, _lib.stream_handle()), "refresh")
+            torch.cuda.synchronize()
+            got[mode] = [plan.dgrad_weights(i).clone() for i in range(1, 75)]
+        finally:
+            _lib.set_option("YB_PACK_MT", None)
+    for i, (a, b) in enumerate(zip(got["0"], got[None])):
+        assert torch.equal(a, b), (i + 1, int((a != b).sum()))
+    assert any(float(t.float().abs().max()) > 0 for t in got[None])
+
+
 # ------------------------------------------------------------------------- NMS band logic (many candidates per class)
 def test_nms_many_candidates_multiple_bands():
     # 20k candidates in one class, tiny boxes (little suppression) and max_boxes 3000: the selection must walk

@@ -134,8 +134,18 @@ def test_dgrad_stride2_parity_classes(cin, cout, with_res):
     assert torch.all(err <= 2.0 ** -6 * torch.clamp(ref.abs(), min=0.05)), float(err.max())
 
 
-@pytest.mark.parametrize("upsample,res,c", [(False, True, 64), (True, False, 128), (False, False, 32)])
-def test_bn_train_forward_backward(upsample, res, c):
+@pytest.fixture(params=["cpt4", "cpt8"])
+def bn_shape(request):
+    """Both builds of the BN streaming kernels (4 or 8 channels per thread; csrc/bn.cu)."""
+    L = _L()
+    L.set_option("YB_BN_CPT", "4" if request.param == "cpt4" else None)
+    yield request.param
+    L.set_option("YB_BN_CPT", None)
+
+
+@pytest.mark.parametrize("upsample,res,c", [(False, True, 64), (True, False, 128), (False, False, 32), (False, True, 1024),
+                                            (False, False, 2048), (False, False, 8)])
+def test_bn_train_forward_backward(upsample, res, c, bn_shape):
     L = _L()
     lib, ptr, st = L.lib, L.ptr, L.stream_handle
     g = torch.Generator().manual_seed(4)
@@ -159,6 +169,15 @@ def test_bn_train_forward_backward(upsample, res, c):
     up = 2 if upsample else 1
     out = torch.empty((n, h * up, w * up, c), dtype=dt, device="cuda")
     L.check(lib.yb_bn_act_apply(ptr(z), c, ptr(scale), ptr(shift), ptr(r), c, ptr(out), c, n, h, w, c, L.YB_BF16, 1, int(upsample), st()), "apply")
+    # the one-launch form (statistics -> scale/shift inside the apply kernel) is bit-identical to the two calls above
+    mm2 = torch.zeros(c).cuda(); mv2 = torch.ones(c).cuda()
+    sc2 = torch.empty(c).cuda(); sh2 = torch.empty(c).cuda(); sm2 = torch.empty(c).cuda(); si2 = torch.empty(c).cuda()
+    out2 = torch.empty_like(out)
+    L.check(lib.yb_bn_stats_act_apply(ptr(z), c, ptr(ssum), ptr(ssq), ptr(gamma), ptr(beta), 1e-5, 0.99, ptr(mm2), ptr(mv2), ptr(sc2),
+                                      ptr(sh2), ptr(sm2), ptr(si2), ptr(r), c, ptr(out2), c, n, h, w, c, L.YB_BF16, 1, int(upsample),
+                                      st()), "stats_act_apply")
+    for a_, b_ in ((mm2, mm), (mv2, mv), (sc2, scale), (sh2, shift), (sm2, smean), (si2, sinv), (out2, out)):
+        assert torch.equal(a_, b_)
     # reference through autograd
     zr = zf.clone().requires_grad_(True); gr = gamma.clone().requires_grad_(True); br = beta.clone().requires_grad_(True)
     y = (zr - mean) / torch.sqrt(var + 1e-5)

@@ -26,8 +26,11 @@ for r in csv.DictReader(lines):
     per[k][mname] = v
 launches = [per[k] for k in order if "at::" not in per[k]["name"] and "elementwise" not in per[k]["name"]]
 table = yolov3.conv_table(80)
-steps = max(1, len(launches) // 77)
-launches = launches[:77]
+# with the stem fused into Conv_1 (YB_STEM_FUSE, the default) launch 0 is conv_halo_kernel<.., STEMW > 0, ..> and covers layers 0 + 1
+m0 = re.search(r"conv_halo_kernel<[^,]+,\s*\d+,\s*\d+,\s*\d+,\s*(\d+)", launches[0]["name"])
+fused = bool(m0 and int(m0.group(1)) > 0)
+nl = 76 if fused else 77
+launches = launches[:nl]
 print(f"# per-layer table of one inference step (batch {B} @{S}, fp16), from {os.path.basename(path)}\n")
 print("ncu-serialised durations with cold caches (bench.py times the whole step warm).  TFLOP/s = 2*pixels*k*k*cin*cout / time; peaks: "
       f"{PEAK_TF} TFLOP/s (sustained bf16, measured), {PEAK_BW} GB/s (measured).\n")
@@ -63,12 +66,18 @@ def layer_hw():
             out.append(g)          # the upsampling 1x1 runs at the coarse resolution
     return out
 hw = layer_hw()
-for i, L in enumerate(launches):
+for li, L in enumerate(launches):
+    i = li + 1 if (fused and li > 0) else li
     name = re.sub(r"\(.*", "", L["name"]).replace("void ", "").replace("yb::", "")
     us = L.get("gpu__time_duration.sum", 0.0); by = L.get("dram__bytes_read.sum", 0.0) + L.get("dram__bytes_write.sum", 0.0)
     tp = L.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", 0.0)
     tot_us += us
-    if i < 75:
+    if fused and li == 0:
+        fl = sum(2.0 * B * hw[j] * hw[j] * table[j][2] ** 2 * table[j][0] * table[j][1] for j in (0, 1))
+        tf = fl / us / 1e6
+        conv_us += us; conv_bytes += by; conv_flop += fl
+        print(f"| 0+1 | 3x3/1 3->32 + 3x3/2 32->64 (fused) | {hw[1]}x{hw[1]} | `{name[:46]}` | {us:.1f} | {tf:.0f} | {tf / PEAK_TF:.2f} | {by / 1e6:.0f} | {by / us / 1e3:.0f} | {by / us / 1e3 / PEAK_BW:.2f} | {tp:.0f} |")
+    elif i < 75:
         cin, cout, k, s, bn = table[i]
         o = hw[i]
         fl = 2.0 * B * o * o * k * k * cin * cout
@@ -78,5 +87,5 @@ for i, L in enumerate(launches):
         print(f"| {i} | {k}x{k}/{s} {cin}->{cout} | {o}x{o} | `{name[:46]}` | {us:.1f} | {tf:.0f} | {tf / PEAK_TF:.2f} | {by / 1e6:.0f} | {by / us / 1e3:.0f} | {by / us / 1e3 / PEAK_BW:.2f} | {tp:.0f} |")
     else:
         print(f"| - | - | - | `{name[:46]}` | {us:.1f} | - | - | {by / 1e6:.0f} | {by / us / 1e3:.0f} | {by / us / 1e3 / PEAK_BW:.2f} | - |")
-print(f"\nsum {tot_us:.0f} us; tensor-core convs (layers 1..74): {conv_us:.0f} us, {conv_flop / conv_us / 1e6:.0f} TFLOP/s, DRAM {conv_bytes / 1e9:.2f} GB")
+print(f"\nsum {tot_us:.0f} us; convs ({'layers 0..74, stem fused into Conv_1' if fused else 'layers 1..74'}): {conv_us:.0f} us, {conv_flop / conv_us / 1e6:.0f} TFLOP/s, DRAM {conv_bytes / 1e9:.2f} GB")
 sys.stderr.write(json.dumps({"batch": B, "size": S, "dram_bytes_per_step": conv_bytes, "conv_us_ncu": conv_us, "source": os.path.basename(path)}) + "\n")

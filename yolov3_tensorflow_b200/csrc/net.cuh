@@ -80,6 +80,8 @@ struct yb_net {
   size_t opt_tensors_off = 0, opt_chunks_off = 0, opt_norm_off = 0; int num_opt_tensors = 0, num_opt_chunks = 0;
   std::vector<yb::OptTensor> opt_tensors;
   std::vector<yb::OptChunk> opt_chunks;
+  size_t pack_jobs_off = 0; int pack_tiles = 0;   // multi-tensor dgrad-weight repack (optim.cuh: PackJob)
+  std::vector<yb::PackJob> pack_jobs;
   bool fold_dirty = false;
   float bn_eps = 1e-5f;
 };

@@ -121,6 +121,7 @@ void train_layout(yb_net* net) {
   net->opt_chunks_off = o; o = al256(o + net->opt_chunks.size() * sizeof(OptChunk));
   net->opt_norm_off = o; o = al256(o + net->opt_tensors.size() * 4);
   net->opt_step_off = o; o = al256(o + 256);
+  net->pack_jobs_off = o; o = al256(o + net->layers.size() * sizeof(PackJob));
   net->param_bytes = o;
 }
 
@@ -236,6 +237,23 @@ int train_bind(yb_net* net, cudaStream_t st) {
                             cudaMemcpyHostToDevice, st));
     YB_CUDA(cudaMemcpyAsync(net->par + net->opt_chunks_off, net->opt_chunks.data(), net->opt_chunks.size() * sizeof(OptChunk),
                             cudaMemcpyHostToDevice, st));
+    // dgrad-weight repack table: every layer but the stem, one launch (pack_dgrad_all)
+    net->pack_jobs.clear();
+    int tile0 = 0;
+    for (auto& L : net->layers) {
+      if (L.info.index == 0) continue;
+      PackJob j; memset(&j, 0, sizeof(j));
+      j.w = fpar(net, L.w_master); j.dst = net->par + L.w_dgrad;
+      j.cout = L.info.cout; j.cin = L.info.cin; j.ks = L.info.ksize; j.kco = L.k_cout;
+      j.cin_pad = yb_conv_cout_pad(L.info.cin); j.s2 = L.dgrad_parity ? 1 : 0;
+      j.tiles_ci = (j.cin_pad + 31) / 32; j.tiles_co = (j.kco + 127) / 128;
+      j.tile0 = tile0;
+      tile0 += j.ks * j.ks * j.tiles_ci * j.tiles_co;
+      net->pack_jobs.push_back(j);
+    }
+    net->pack_tiles = tile0;
+    YB_CUDA(cudaMemcpyAsync(net->par + net->pack_jobs_off, net->pack_jobs.data(), net->pack_jobs.size() * sizeof(PackJob),
+                            cudaMemcpyHostToDevice, st));
   }
   return YB_OK;
 }
@@ -249,6 +267,18 @@ int train_refresh_dgrad_weights(yb_net* net, int layer, void* stream) {
                                     net->dtype, net->par + L.w_dgrad, stream);
   return yb_pack_dgrad_weights(fpar(net, L.w_master), L.info.cout, L.info.cin, L.info.ksize, L.k_cout,
                                yb_conv_cout_pad(L.info.cin), net->dtype, net->par + L.w_dgrad, stream);
+}
+
+// ... all layers: one multi-tensor launch (YB_PACK_MT=0: the per-layer kernels)
+static int refresh_all_dgrad_weights(yb_net* net, void* stream) {
+  if (opt("YB_PACK_MT")[0] != '0' && !net->pack_jobs.empty())
+    return pack_dgrad_all(reinterpret_cast<const PackJob*>(net->par + net->pack_jobs_off), (int)net->pack_jobs.size(),
+                          net->pack_tiles, net->dtype, static_cast<cudaStream_t>(stream));
+  for (size_t i = 1; i < net->layers.size(); ++i) {
+    int rc = train_refresh_dgrad_weights(net, (int)i, stream);
+    if (rc) return rc;
+  }
+  return YB_OK;
 }
 
 }  // namespace yb
@@ -278,6 +308,7 @@ extern "C" int yb_net_train_fwd_bwd(yb_net* net, const float* images, const floa
   }
   // ------------------------------------------------ forward (is_training=True)
   float* fm_ptr[3] = {nullptr, nullptr, nullptr};
+  const bool fuse_fin = opt("YB_BN_FIN")[0] != '0';
   for (size_t i = 0; i < net->layers.size(); ++i) {
     Layer& L = net->layers[i];
     const long rows = (long)n * L.info.out_h * L.info.out_w;
@@ -298,13 +329,24 @@ extern "C" int yb_net_train_fwd_bwd(yb_net* net, const float* images, const floa
       if (rc) return rc;
     }
     if (L.info.has_bn) {
+      const void* resp = L.res.buf >= 0 ? ten_ptr2(net, L.res) : nullptr;
+      const long res_ld = L.res.buf >= 0 ? net->bufs[L.res.buf].ld : 0;
+      if (fuse_fin) {     // statistics -> scale/shift inside the apply kernel (one launch per BN layer instead of two)
+        rc = yb_bn_stats_act_apply(net->act + L.z_off, L.info.cout, bn_frozen ? nullptr : fact(net, L.st_sum),
+                                   bn_frozen ? nullptr : fact(net, L.st_sqsum), fpar(net, L.gamma), fpar(net, L.beta),
+                                   net->bn_eps, bn_decay, fpar(net, L.mean), fpar(net, L.var), fact(net, L.st_scale),
+                                   fact(net, L.st_shift), fact(net, L.st_mean), fact(net, L.st_invstd), resp, res_ld,
+                                   ten_ptr2(net, L.out), net->bufs[L.out.buf].ld, n, L.info.out_h, L.info.out_w,
+                                   L.info.cout, dt, 1, L.upsample ? 1 : 0, stream);
+        if (rc) return rc;
+        continue;
+      }
       rc = yb_bn_finalize(bn_frozen ? nullptr : fact(net, L.st_sum), bn_frozen ? nullptr : fact(net, L.st_sqsum), rows,
                           L.info.cout, fpar(net, L.gamma), fpar(net, L.beta),
                           net->bn_eps, bn_decay, fpar(net, L.mean), fpar(net, L.var), fact(net, L.st_scale),
                           fact(net, L.st_shift), fact(net, L.st_mean), fact(net, L.st_invstd), stream);
       if (rc) return rc;
-      rc = yb_bn_act_apply(net->act + L.z_off, L.info.cout, fact(net, L.st_scale), fact(net, L.st_shift),
-                           L.res.buf >= 0 ? ten_ptr2(net, L.res) : nullptr, L.res.buf >= 0 ? net->bufs[L.res.buf].ld : 0,
+      rc = yb_bn_act_apply(net->act + L.z_off, L.info.cout, fact(net, L.st_scale), fact(net, L.st_shift), resp, res_ld,
                            ten_ptr2(net, L.out), net->bufs[L.out.buf].ld, n, L.info.out_h, L.info.out_w, L.info.cout, dt, 1,
                            L.upsample ? 1 : 0, stream);
       if (rc) return rc;
@@ -419,11 +461,7 @@ extern "C" int yb_net_set_trainable(yb_net* net, int layer, int trainable, void*
 
 extern "C" int yb_net_train_refresh_dgrad(yb_net* net, void* stream) {
   YB_REQUIRE(net && net->training && net->par, "train_refresh_dgrad: not a bound training plan");
-  for (size_t i = 1; i < net->layers.size(); ++i) {
-    int rc = train_refresh_dgrad_weights(net, (int)i, stream);
-    if (rc) return rc;
-  }
-  return YB_OK;
+  return refresh_all_dgrad_weights(net, stream);
 }
 
 extern "C" int yb_net_grad_buffer(yb_net* net, float** ptr, size_t* count) {
@@ -452,10 +490,8 @@ extern "C" int yb_net_train_update(yb_net* net, const yb_optimizer* opt, void* s
                     net->num_opt_chunks, fpar(net, net->opt_norm_off), reinterpret_cast<int*>(net->par + net->opt_step_off),
                     net->dtype, *opt, st);
   if (rc) return rc;
-  for (size_t i = 1; i < net->layers.size(); ++i) {
-    rc = train_refresh_dgrad_weights(net, (int)i, stream);
-    if (rc) return rc;
-  }
+  rc = refresh_all_dgrad_weights(net, stream);
+  if (rc) return rc;
   net->fold_dirty = true;
   return YB_OK;
 }
@@ -495,7 +531,9 @@ extern "C" int yb_net_train_buffer(yb_net* net, int layer, int which, void** ptr
             if (L.upsample) { h *= 2; w *= 2; } break;
     case 3: YB_REQUIRE(layer > 0, "train_buffer: layer 0 reads the image"); *ptr = ten_ptr2(net, L.in); *ld = net->bufs[L.in.buf].ld;
             h = L.info.in_h; w = L.info.in_w; break;
-    default: set_error("train_buffer: which must be 0..3"); return YB_ERR_INVALID_ARGUMENT;
+    case 4: YB_REQUIRE(layer > 0 && net->par, "train_buffer: the stem has no dgrad weights");   // [cin_pad * k * k][k_cout], 16-bit
+            *ptr = net->par + L.w_dgrad; *ld = L.k_cout; h = yb_conv_cout_pad(L.info.cin); w = L.info.ksize * L.info.ksize; break;
+    default: set_error("train_buffer: which must be 0..4"); return YB_ERR_INVALID_ARGUMENT;
   }
   if (rows_h) *rows_h = h;
   if (rows_w) *rows_w = w;

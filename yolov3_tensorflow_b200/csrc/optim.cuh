@@ -18,6 +18,18 @@ struct OptChunk {
   int tensor;
   long begin, end;
 };
+// One conv layer of the multi-tensor dgrad-weight repack (pack_dgrad_all): the flip + transpose W[co][r][s][ci] ->
+// Wd[ci][r'][s'][co] of every layer in ONE launch (a block = one 32(ci) x 128(co) tile of one tap, transposed through
+// shared memory so that both the fp32 reads and the 16-bit writes are coalesced).
+struct PackJob {
+  const float* w;   // fp32 master weights [cout][ks][ks][cin]
+  void* dst;        // 16-bit dgrad weights (layouts of yb_pack_dgrad_weights / yb_pack_dgrad_weights_s2)
+  int cout, cin, ks, kco, cin_pad, s2;
+  int tiles_ci, tiles_co;
+  int tile0;        // first block of this layer
+};
+int pack_dgrad_all(const PackJob* jobs, int num_jobs, int total_tiles, int dtype, cudaStream_t st);
+
 // ctrl[0]: a non-finite gradient was seen this step (the whole update is skipped), ctrl[1]: updates applied so far
 // (Adam's t - 1), ctrl[2]: steps skipped
 int opt_step(const OptTensor* tensors, const OptChunk* chunks, int num_tensors, int num_chunks, float* sqnorm, int* ctrl,

@@ -107,6 +107,14 @@ class _Plan:
         flat = self.act[off: off + nelem * 2].view(tdt)
         return flat.as_strided((self.n, h, w, c), (h * w * ld.value, w * ld.value, ld.value, 1))
 
+    def dgrad_weights(self, i):
+        """Layer i's 16-bit dgrad weights (flip + transpose of the masters, csrc/optim.cu), flat [cin_pad * k * k * k_cout]."""
+        p, ld, hh, ww = C.c_void_p(), C.c_int(), C.c_int(), C.c_int()
+        check(lib.yb_net_train_buffer(self.handle, i, 4, C.byref(p), C.byref(ld), C.byref(hh), C.byref(ww)), "yb_net_train_buffer")
+        off = p.value - self.par.data_ptr()
+        tdt = torch.float16 if self.act_dtype == torch.float16 else torch.bfloat16
+        return self.par[off: off + hh.value * ww.value * ld.value * 2].view(tdt)
+
     def grad_range(self, first_layer, last_layer):
         """Flat-gradient slice owned by layers [first_layer, last_layer] (a data-parallel bucket)."""
         p, n = C.c_void_p(), C.c_size_t()
