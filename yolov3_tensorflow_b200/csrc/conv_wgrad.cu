@@ -283,9 +283,24 @@ extern "C" int yb_conv2d_wgrad(const yb_conv_desc* d, const void* x, const void*
   const int tap_groups = taps / tp;
   const int co_tiles = ceil_div(d->cout, WG_BM);
   const long tiles = (long)tap_groups * p.n_chunks * co_tiles;
-  long splits = ((long)num_sms() * 2 + tiles - 1) / tiles;
-  if (splits > p.num_kb) splits = p.num_kb;
-  if (splits < 1) splits = 1;
+  // Pixel splits (split-K).  One CTA is resident per SM (192 KB of stages), so the grid runs in waves of num_sms CTAs,
+  // and every CTA ends with TP x BNW x 128 fp32 atomics that nothing overlaps: measured at ~40 pixel blocks' worth of
+  // main loop (profiles/r02_g: the 26x26 256->512 layer ran 13 splits x 24 tiles = 312 CTAs = 2.1 waves of 26 blocks,
+  // 84 us against 36 us of tensor work).  Pick the split count that minimises waves x (blocks per CTA + epilogue).
+  long splits = 1;
+  {
+    const long sms = num_sms();
+    const double epi = (double)opt_int("YB_WGRAD_EPI", 40);
+    double best = 1e30;
+    const long smax = p.num_kb < 4 * sms ? p.num_kb : 4 * sms;
+    for (long s = 1; s <= smax; ++s) {
+      const long kbs = ceil_div(p.num_kb, s);
+      const long s_eff = ceil_div(p.num_kb, kbs);
+      const long waves = ceil_div(tiles * s_eff, sms);
+      const double cost = (double)waves * ((double)kbs + epi);
+      if (cost < best - 1e-9) { best = cost; splits = s_eff; }
+    }
+  }
   p.kb_per_split = ceil_div(p.num_kb, splits);
   splits = ceil_div(p.num_kb, p.kb_per_split);
   CUtensorMap tmA, tmB;
