@@ -571,8 +571,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
     }
     mbar_init(bres_bar, 1);
-    // (dbg & 64, synccheck experiment: every epilogue warp initialises its own residual barriers instead)
-    if (!(p.dbg & 64)) for (int i = 0; i < 4 * EG * EPI_TILES; ++i) mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < 4 * EG * EPI_TILES; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
@@ -581,13 +580,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[10 * 64 * 32 + 1] = clock64();
-  if ((p.dbg & 64) && warp >= 2) {
-    if (lane == 0) {
-      for (int i = 0; i < EPI_TILES; ++i) mbar_init(&res_bar[(warp - 2) * EPI_TILES + i], 1);
-      fence_barrier_init();
-    }
-    __syncwarp();
-  }
 
   if (warp == 0) {
     // ===================== TMA producer =====================
