@@ -105,6 +105,11 @@ int yb_conv3x3_thin_fwd(const yb_conv_desc* d, const void* x, const void* w_pack
                         const float* shift, const void* res, void* out, void* stream);
 int yb_stem_conv_fwd_tc(const float* x, const float* w_ohwi, const float* scale, const float* shift, int n, int h,
                         int w, int dtype, int leaky, void* out, void* stream);
+/* ... and, for the training forward, also ACCUMULATING the per-channel sum / sum of squares of the stored outputs
+ * (fp32 [32] each, zeroed by the caller; both NULL = yb_stem_conv_fwd_tc): the batch statistics of
+ * slim.batch_norm(is_training=True) (reference model.py:35-41) without a second pass over the tensor. */
+int yb_stem_conv_fwd_tc_stats(const float* x, const float* w_ohwi, const float* scale, const float* shift, int n, int h,
+                              int w, int dtype, int leaky, void* out, float* stat_sum, float* stat_sqsum, void* stream);
 
 /* 3x3 convs with cin in {32, 64} and cout in {64, 128} (darknet53_body Conv_1/3/6/8, utils/layer_utils.py:36-44) from
  * a shared-memory HALO tile: one tiled TMA load per 16x8-pixel output tile (four parity planes for stride 2), the nine

@@ -302,6 +302,16 @@ def test_stem_conv_tensor_core(dtype, conv_mode):
     eps = 2.0 ** -9 if dtype == torch.float16 else 2.0 ** -6
     err = (out.float() - ref).abs()
     assert torch.all(err <= eps * torch.clamp(ref.abs(), min=1.0)), float(err.max())
+    # the training-forward form: same outputs, plus the batch statistics of the STORED values accumulated on top of what the
+    # buffers hold (h = 40, w = 56: partial tiles in both directions, their out-of-image pixels must not be counted)
+    out2 = torch.empty_like(out)
+    ssum = torch.full((32,), 1.0, device="cuda"); ssq = torch.full((32,), 2.0, device="cuda")
+    L.check(L.lib.yb_stem_conv_fwd_tc_stats(L.ptr(x), L.ptr(wt), L.ptr(sc), L.ptr(sh), n, h, w, code, 1, L.ptr(out2), L.ptr(ssum),
+                                            L.ptr(ssq), L.stream_handle()), "stem_tc_stats")
+    assert torch.equal(out2, out)
+    of = out.double()
+    torch.testing.assert_close(ssum.double() - 1.0, of.sum(dim=(0, 1, 2)), rtol=1e-4, atol=1e-2)
+    torch.testing.assert_close(ssq.double() - 2.0, (of * of).sum(dim=(0, 1, 2)), rtol=1e-4, atol=1e-2)
 
 
 # ------------------------------------------------------------------------- halo-tile tcgen05 conv (csrc/conv_halo.cu)

@@ -61,6 +61,7 @@ _SIGS = {
     "yb_conv3x3_halo_fwd": ([C.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp], i32),
     "yb_stem_conv1_fused_fwd": ([C.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp], i32),
     "yb_stem_conv_fwd_tc": ([vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp], i32),
+    "yb_stem_conv_fwd_tc_stats": ([vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp], i32),
     "yb_process_box": ([vp, vp, vp, i32, i32, i32, i32, i32, C.POINTER(f32), vp, vp, vp, vp], i32),
     "yb_letterbox_params": ([i32, i32, i32, i32, C.POINTER(C.c_double), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)], i32),
     "yb_letterbox_normalize": ([vp, i32, i32, C.c_long, i32, i32, vp, vp], i32),

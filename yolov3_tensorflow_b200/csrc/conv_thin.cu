@@ -30,6 +30,8 @@ struct ThinParams {
   int tiles_y, tiles_x, num_tiles;
   int leaky;
   int dbg;              // timing experiments (YB_STEM_DBG bitmask): 1 no halo load, 2 no im2col, 4 no MMA, 8 no stores
+  float* stat_sum;      // stem only, nullable: per-channel sum / sum of squares of the STORED (16-bit) outputs, accumulated
+  float* stat_sqsum;    //   (the BN batch statistics of the training forward: no separate pass over the 354 MB tensor)
 };
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
@@ -123,6 +125,7 @@ conv_thin_kernel(const ThinParams p) {
     }
   };
   if (STEM && (int)blockIdx.x < p.num_tiles && !(p.dbg & 1)) fetch_halo(blockIdx.x);
+  float st_s = 0.f, st_q = 0.f;   // stem statistics: thread = (warp: 32-pixel quarter of every tile, lane: channel)
 
   for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
     const int tx = tile % p.tiles_x;
@@ -249,6 +252,18 @@ conv_thin_kernel(const ThinParams p) {
       }
     }
     __syncthreads();
+    if (STEM && p.stat_sum != nullptr) {
+      // column sums over the staged tile (the values exactly as stored): a warp's lanes read one pixel's 32 channels
+#pragma unroll 4
+      for (int i = 0; i < 32; ++i) {
+        const int px = warp * 32 + i;
+        if (oy0 + px / TW < p.ho && ox0 + px % TW < p.wo) {
+          const float v = static_cast<float>(reinterpret_cast<const T*>(s_o + px * C::O_PITCH)[lane]);
+          st_s += v;
+          st_q = fmaf(v, v, st_q);
+        }
+      }
+    }
     // ---- coalesced copy-out: one 16-byte chunk per thread-iteration, full rows of COUT*2 bytes ----
     constexpr int OCH = COUT * 2 / 16;
     for (int i = tid; i < 128 * OCH; i += THIN_THREADS) {
@@ -261,6 +276,10 @@ conv_thin_kernel(const ThinParams p) {
     }
   }
   cp_async_wait_all();
+  if (STEM && p.stat_sum != nullptr) {          // 2 x 128 atomics per persistent CTA
+    atomicAdd(p.stat_sum + lane, st_s);
+    atomicAdd(p.stat_sqsum + lane, st_q);
+  }
 }
 
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* p) {
@@ -442,7 +461,7 @@ extern "C" int yb_conv3x3_thin_fwd(const yb_conv_desc* d, const void* x, const v
   p.ho = d->h / d->stride; p.wo = d->w / d->stride;
   p.tiles_y = ceil_div(p.ho, TH); p.tiles_x = ceil_div(p.wo, TW);
   p.num_tiles = p.tiles_x * p.tiles_y * d->n;
-  p.leaky = d->leaky; p.dbg = 0;
+  p.leaky = d->leaky; p.dbg = 0; p.stat_sum = nullptr; p.stat_sqsum = nullptr;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define YB_THIN(T)                                                                         \
   if (d->cout == 64 && d->stride == 1) return launch_thin<T, 64, 1, false>(p, st);        \
@@ -455,9 +474,13 @@ extern "C" int yb_conv3x3_thin_fwd(const yb_conv_desc* d, const void* x, const v
 }
 
 // Stem on the warp-level tensor path: float32 image [n,h,w,3] -> 16-bit [n,h,w,32]; w_ohwi float32 [32][27].
-extern "C" int yb_stem_conv_fwd_tc(const float* x, const float* w_ohwi, const float* scale, const float* shift, int n,
-                                   int h, int w, int dtype, int leaky, void* out, void* stream) {
+// stat_sum / stat_sqsum (both or neither; zeroed by the caller): the kernel also ACCUMULATES the per-channel sum and sum
+// of squares of the stored outputs — the batch statistics slim.batch_norm(is_training=True) needs (model.py:35-41).
+extern "C" int yb_stem_conv_fwd_tc_stats(const float* x, const float* w_ohwi, const float* scale, const float* shift,
+                                         int n, int h, int w, int dtype, int leaky, void* out, float* stat_sum,
+                                         float* stat_sqsum, void* stream) {
   YB_REQUIRE(x && w_ohwi && scale && shift && out && n > 0 && h > 0 && w > 0, "stem_tc: bad argument");
+  YB_REQUIRE((stat_sum == nullptr) == (stat_sqsum == nullptr), "stem_tc: stat_sum/stat_sqsum must both be given");
   ThinParams p;
   p.x = x; p.x_ld = 3; p.wt = w_ohwi; p.scale = scale; p.shift = shift; p.res = nullptr; p.res_ld = 0;
   p.out = out; p.out_ld = 32; p.n = n; p.h = h; p.w = w; p.ho = h; p.wo = w;
@@ -465,11 +488,16 @@ extern "C" int yb_stem_conv_fwd_tc(const float* x, const float* w_ohwi, const fl
   p.num_tiles = p.tiles_x * p.tiles_y * n;
   p.leaky = leaky;
   p.dbg = opt_int("YB_STEM_DBG", 0);
+  p.stat_sum = stat_sum; p.stat_sqsum = stat_sqsum;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == YB_F16) return launch_thin<__half, 32, 1, true>(p, st);
   if (dtype == YB_BF16) return launch_thin<__nv_bfloat16, 32, 1, true>(p, st);
   set_error("stem_tc: dtype must be f16 or bf16");
   return YB_ERR_UNSUPPORTED;
+}
+extern "C" int yb_stem_conv_fwd_tc(const float* x, const float* w_ohwi, const float* scale, const float* shift, int n,
+                                   int h, int w, int dtype, int leaky, void* out, void* stream) {
+  return yb_stem_conv_fwd_tc_stats(x, w_ohwi, scale, shift, n, h, w, dtype, leaky, out, nullptr, nullptr, stream);
 }
 
 // Stem weight gradient on the warp-level tensor path (float32 image split into 16-bit head + remainder).

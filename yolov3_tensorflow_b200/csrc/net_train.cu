@@ -309,15 +309,22 @@ extern "C" int yb_net_train_fwd_bwd(yb_net* net, const float* images, const floa
   // ------------------------------------------------ forward (is_training=True)
   float* fm_ptr[3] = {nullptr, nullptr, nullptr};
   const bool fuse_fin = opt("YB_BN_FIN")[0] != '0';
+  const bool stem_tc = opt("YB_STEM_TRAIN")[0] != 'c';
   for (size_t i = 0; i < net->layers.size(); ++i) {
     Layer& L = net->layers[i];
     const long rows = (long)n * L.info.out_h * L.info.out_w;
     if (i == 0) {
-      rc = yb_stem_conv_fwd(images, fpar(net, L.w_master), ones, zeros, n, net->h, net->w, L.info.cout, dt, 0,
-                            net->act + L.z_off, stream);
-      if (rc) return rc;
-      rc = yb_col_stats(net->act + L.z_off, L.info.cout, rows, L.info.cout, dt, fact(net, L.st_sum), fact(net, L.st_sqsum), stream);
-      if (rc) return rc;
+      if (stem_tc) {   // warp-level tensor path, batch statistics accumulated by the same kernel (the sums were zeroed above)
+        rc = yb_stem_conv_fwd_tc_stats(images, fpar(net, L.w_master), ones, zeros, n, net->h, net->w, dt, 0,
+                                       net->act + L.z_off, fact(net, L.st_sum), fact(net, L.st_sqsum), stream);
+        if (rc) return rc;
+      } else {         // YB_STEM_TRAIN=cuda: the fp32 CUDA-core stem + a column-statistics pass (the first version)
+        rc = yb_stem_conv_fwd(images, fpar(net, L.w_master), ones, zeros, n, net->h, net->w, L.info.cout, dt, 0,
+                              net->act + L.z_off, stream);
+        if (rc) return rc;
+        rc = yb_col_stats(net->act + L.z_off, L.info.cout, rows, L.info.cout, dt, fact(net, L.st_sum), fact(net, L.st_sqsum), stream);
+        if (rc) return rc;
+      }
     } else {
       ConvParams p = L.tparams;
       if (!L.info.has_bn) {
