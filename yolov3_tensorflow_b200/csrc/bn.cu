@@ -447,12 +447,6 @@ col_sum_kernel(const T* __restrict__ x, long ld, long rows, int c, long rows_per
   }
 }
 
-static int grid1d(long total) {
-  long g = (total + 255) / 256;
-  const long cap = (long)num_sms() * 16;
-  return (int)(g < cap ? g : cap);
-}
-
 }  // namespace yb
 
 using namespace yb;
