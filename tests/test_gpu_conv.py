@@ -308,8 +308,23 @@ def test_stem_conv_tensor_core(dtype, conv_mode):
     ssum = torch.full((32,), 1.0, device="cuda"); ssq = torch.full((32,), 2.0, device="cuda")
     L.check(L.lib.yb_stem_conv_fwd_tc_stats(L.ptr(x), L.ptr(wt), L.ptr(sc), L.ptr(sh), n, h, w, code, 1, L.ptr(out2), L.ptr(ssum),
                                             L.ptr(ssq), L.stream_handle()), "stem_tc_stats")
-    assert torch.equal(out2, out)
-    of = out.double()
+    # this form multiplies split-precision operands (x = hi + lo, w = hi + lo): it matches the float32 convolution of the
+    # UNROUNDED image and weights to the rounding of its 16-bit output (YB_STEM_SPLIT=0 gives the plain kernel's bits)
+    ref32 = F.conv2d(x.permute(0, 3, 1, 2), wt.permute(0, 3, 1, 2), None, padding=1)
+    ref32 = ref32 * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)
+    ref32 = torch.where(ref32 > 0, ref32, 0.1 * ref32).permute(0, 2, 3, 1)
+    ulp = 2.0 ** -11 if dtype == torch.float16 else 2.0 ** -8
+    err2 = (out2.float() - ref32).abs()
+    assert torch.all(err2 <= 1.02 * ulp * torch.clamp(ref32.abs(), min=1.0) + 1e-5), float(err2.max())
+    L.set_option("YB_STEM_SPLIT", "0")
+    try:
+        out3 = torch.empty_like(out); s3 = torch.zeros(32, device="cuda"); q3 = torch.zeros(32, device="cuda")
+        L.check(L.lib.yb_stem_conv_fwd_tc_stats(L.ptr(x), L.ptr(wt), L.ptr(sc), L.ptr(sh), n, h, w, code, 1, L.ptr(out3), L.ptr(s3),
+                                                L.ptr(q3), L.stream_handle()), "stem_tc_stats")
+        assert torch.equal(out3, out)
+    finally:
+        L.set_option("YB_STEM_SPLIT", None)
+    of = out2.double()
     torch.testing.assert_close(ssum.double() - 1.0, of.sum(dim=(0, 1, 2)), rtol=1e-4, atol=1e-2)
     torch.testing.assert_close(ssq.double() - 2.0, (of * of).sum(dim=(0, 1, 2)), rtol=1e-4, atol=1e-2)
 

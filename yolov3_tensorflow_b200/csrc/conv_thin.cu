@@ -58,17 +58,21 @@ __device__ __forceinline__ void mma16816<__nv_bfloat16>(float (&c)[4], const uin
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// CIN = 32 (layers) ; STEM: CIN = 3 float32 image, K padded 27 -> 32
-template <typename T, int COUT, int STRIDE, bool STEM>
+// CIN = 32 (layers) ; STEM: CIN = 3 float32 image, K padded 27 -> 32.
+// SPLIT (stem only; the training forward): split-precision operands, K = 96 = [x_hi | x_lo | x_hi] . [w_hi ; w_hi ; w_lo]
+// with v_hi = T(v), v_lo = T(v - v_hi): the products keep ~16 bits of the float32 image and weights (only lo x lo,
+// 2^-16 relative for bf16, is dropped), so the raw stem output feeding the batch statistics matches a float32
+// convolution like the reference's (model.py:35, utils/layer_utils.py:35) instead of one on operands rounded to 8 bits.
+template <typename T, int COUT, int STRIDE, bool STEM, bool SPLIT = false>
 struct ThinCfg {
   static constexpr int CIN = STEM ? 3 : 32;
-  static constexpr int K = STEM ? 32 : 9 * 32;                  // GEMM K
+  static constexpr int K = STEM ? (SPLIT ? 96 : 32) : 9 * 32;   // GEMM K
   static constexpr int HH = TH * STRIDE + 2, HW = TW * STRIDE + 2;   // halo tile
   static constexpr int PIX_PITCH = STEM ? 0 : (32 * 2 + 16);    // bytes per halo pixel (padded: conflict-free ldmatrix)
   static constexpr int HALO_BYTES = STEM ? HH * HW * 3 * 4 : HH * HW * PIX_PITCH;
   static constexpr int W_PITCH = K * 2 + 16;                    // bytes per weight row (one output channel)
   static constexpr int W_BYTES = COUT * W_PITCH;
-  static constexpr int A_PITCH = 32 * 2 + 16;                   // stem only: im2col'd [128][32] tile
+  static constexpr int A_PITCH = (STEM ? K : 32) * 2 + 16;      // stem only: im2col'd [128][K] tile
   static constexpr int A_BYTES = STEM ? 128 * A_PITCH : 0;
   static constexpr int O_PITCH = COUT * 2 + 16;                 // output staging [128 px][COUT]
   static constexpr int O_BYTES = 128 * O_PITCH;
@@ -77,10 +81,11 @@ struct ThinCfg {
   static constexpr int SMEM = ((HALO_OR_OUT + 127) / 128) * 128 + W_BYTES + A_BYTES + 128;
 };
 
-template <typename T, int COUT, int STRIDE, bool STEM>
+template <typename T, int COUT, int STRIDE, bool STEM, bool SPLIT = false>
 __global__ void __launch_bounds__(THIN_THREADS)
 conv_thin_kernel(const ThinParams p) {
-  using C = ThinCfg<T, COUT, STRIDE, STEM>;
+  using C = ThinCfg<T, COUT, STRIDE, STEM, SPLIT>;
+  static_assert(!SPLIT || STEM, "split-precision operands exist for the stem only");
   extern __shared__ __align__(128) uint8_t tsm[];
   uint8_t* s_halo = tsm;
   uint8_t* s_w = tsm + ((C::HALO_OR_OUT + 127) / 128) * 128;
@@ -93,7 +98,11 @@ conv_thin_kernel(const ThinParams p) {
     const float* wf = static_cast<const float*>(p.wt);          // [COUT][27]
     for (int i = tid; i < COUT * 32; i += THIN_THREADS) {
       const int co = i >> 5, k = i & 31;
-      reinterpret_cast<T*>(s_w + co * C::W_PITCH)[k] = static_cast<T>(k < 27 ? wf[co * 27 + k] : 0.f);
+      const float wv = k < 27 ? wf[co * 27 + k] : 0.f;
+      T* wrow = reinterpret_cast<T*>(s_w + co * C::W_PITCH);
+      const T hi = static_cast<T>(wv);
+      wrow[k] = hi;
+      if (SPLIT) { wrow[32 + k] = hi; wrow[64 + k] = static_cast<T>(wv - static_cast<float>(hi)); }
     }
   } else {
     const uint8_t* wg = static_cast<const uint8_t*>(p.wt);      // [cout_pad][288] 16-bit
@@ -170,13 +179,26 @@ conv_thin_kernel(const ThinParams p) {
           for (int c = 0; c < 3; ++c) pv[(r * 3 + s) * 3 + c] = hf[((py + r) * C::HW + (px + s)) * 3 + c];
 #pragma unroll
       for (int k = 27; k < 32; ++k) pv[k] = 0.f;
-      uint4* arow = reinterpret_cast<uint4*>(s_a + tid * C::A_PITCH);   // 80-byte pitch: 16-byte aligned rows
+      uint4* arow = reinterpret_cast<uint4*>(s_a + tid * C::A_PITCH);   // 16-byte aligned rows (pitch = 2 K + 16 bytes)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {                                     // four 128-bit stores instead of 32 16-bit ones
         uint4 u;
         u.x = Pack2<T>::pack(pv[8 * j + 0], pv[8 * j + 1]); u.y = Pack2<T>::pack(pv[8 * j + 2], pv[8 * j + 3]);
         u.z = Pack2<T>::pack(pv[8 * j + 4], pv[8 * j + 5]); u.w = Pack2<T>::pack(pv[8 * j + 6], pv[8 * j + 7]);
         arow[j] = u;
+        if (SPLIT) {                                                    // [x_hi | x_lo | x_hi]
+          arow[8 + j] = u;
+          float lo[8];
+          float2 f;
+          f = Pack2<T>::unpack(u.x); lo[0] = pv[8 * j + 0] - f.x; lo[1] = pv[8 * j + 1] - f.y;
+          f = Pack2<T>::unpack(u.y); lo[2] = pv[8 * j + 2] - f.x; lo[3] = pv[8 * j + 3] - f.y;
+          f = Pack2<T>::unpack(u.z); lo[4] = pv[8 * j + 4] - f.x; lo[5] = pv[8 * j + 5] - f.y;
+          f = Pack2<T>::unpack(u.w); lo[6] = pv[8 * j + 6] - f.x; lo[7] = pv[8 * j + 7] - f.y;
+          uint4 l;
+          l.x = Pack2<T>::pack(lo[0], lo[1]); l.y = Pack2<T>::pack(lo[2], lo[3]);
+          l.z = Pack2<T>::pack(lo[4], lo[5]); l.w = Pack2<T>::pack(lo[6], lo[7]);
+          arow[4 + j] = l;
+        }
       }
     }
     if (STEM) __syncthreads();
@@ -426,10 +448,10 @@ stem_wgrad_tc_kernel(const float* __restrict__ x, const T* __restrict__ dz, int 
   }
 }
 
-template <typename T, int COUT, int STRIDE, bool STEM>
+template <typename T, int COUT, int STRIDE, bool STEM, bool SPLIT = false>
 static int launch_thin(const ThinParams& p, cudaStream_t st) {
-  using C = ThinCfg<T, COUT, STRIDE, STEM>;
-  auto kern = conv_thin_kernel<T, COUT, STRIDE, STEM>;
+  using C = ThinCfg<T, COUT, STRIDE, STEM, SPLIT>;
+  auto kern = conv_thin_kernel<T, COUT, STRIDE, STEM, SPLIT>;
   static DeviceOnce once;
   { const int rc = ensure_smem_attr(once, reinterpret_cast<const void*>(kern), C::SMEM); if (rc) return rc; }
   int per_sm = 227 * 1024 / (C::SMEM + 1024);
@@ -490,8 +512,11 @@ extern "C" int yb_stem_conv_fwd_tc_stats(const float* x, const float* w_ohwi, co
   p.dbg = opt_int("YB_STEM_DBG", 0);
   p.stat_sum = stat_sum; p.stat_sqsum = stat_sqsum;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == YB_F16) return launch_thin<__half, 32, 1, true>(p, st);
-  if (dtype == YB_BF16) return launch_thin<__nv_bfloat16, 32, 1, true>(p, st);
+  // the statistics-producing form is the training forward: split-precision operands (YB_STEM_SPLIT=0: plain 16-bit)
+  const bool split = stat_sum != nullptr && opt("YB_STEM_SPLIT")[0] != '0';
+  if (dtype == YB_F16) return split ? launch_thin<__half, 32, 1, true, true>(p, st) : launch_thin<__half, 32, 1, true>(p, st);
+  if (dtype == YB_BF16)
+    return split ? launch_thin<__nv_bfloat16, 32, 1, true, true>(p, st) : launch_thin<__nv_bfloat16, 32, 1, true>(p, st);
   set_error("stem_tc: dtype must be f16 or bf16");
   return YB_ERR_UNSUPPORTED;
 }

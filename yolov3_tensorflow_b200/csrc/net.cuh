@@ -84,5 +84,13 @@ struct yb_net {
   std::vector<yb::PackJob> pack_jobs;
   bool fold_dirty = false;
   float bn_eps = 1e-5f;
+  // side stream of the backward pass: layer L's wgrad runs beside its dgrad (net_train.cu); created on first use
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t side_fork = nullptr, side_join = nullptr;
+  ~yb_net() {
+    if (side_fork) cudaEventDestroy(side_fork);
+    if (side_join) cudaEventDestroy(side_join);
+    if (side_stream) cudaStreamDestroy(side_stream);
+  }
 };
 

@@ -385,6 +385,19 @@ extern "C" int yb_net_train_backward(yb_net* net, const float* images, int first
   const int n = net->n, dt = net->dtype;
   const float* zeros = fpar(net, net->zeros_off);
   int rc;
+  // Layer L's weight gradient and input gradient both only read dz_L: the wgrad goes to a side stream and runs beside
+  // the dgrad (and the next layer's BN backward).  Both kernels own a whole SM per CTA, so the gain is in the tails:
+  // the SMs a finishing kernel frees — and the ~15 us every wgrad CTA spends flushing fp32 atomics at its end — are
+  // picked up by the other kernel's CTAs instead of idling until the launch boundary.  dz_L and the forward activations
+  // are never rewritten during the backward (one buffer per layer), the join below orders the side stream before
+  // whatever the caller enqueues next (all-reduce of this layer range, optimizer, next step's gradient memset).
+  const bool overlap = opt("YB_WGRAD_STREAM")[0] != '0';
+  bool forked = false;
+  if (overlap && net->side_stream == nullptr) {
+    YB_CUDA(cudaStreamCreateWithFlags(&net->side_stream, cudaStreamNonBlocking));
+    YB_CUDA(cudaEventCreateWithFlags(&net->side_fork, cudaEventDisableTiming));
+    YB_CUDA(cudaEventCreateWithFlags(&net->side_join, cudaEventDisableTiming));
+  }
   for (int i = last_layer; i >= first_layer; --i) {
     Layer& L = net->layers[i];
     const long rows = (long)n * L.info.out_h * L.info.out_w;
@@ -416,7 +429,14 @@ extern "C" int yb_net_train_backward(yb_net* net, const float* images, int first
     yb_conv_desc d; memset(&d, 0, sizeof(d));
     d.n = n; d.h = L.info.in_h; d.w = L.info.in_w; d.cin = L.info.cin; d.cout = L.info.cout;
     d.ksize = L.info.ksize; d.stride = L.info.stride; d.in_ld = net->bufs[L.in.buf].ld; d.dtype = dt;
-    rc = yb_conv2d_wgrad(&d, ten_ptr2(net, L.in), net->act + L.dz_off, L.dz_ld, L.dz_dilated, gradp(net, L.g_w), stream);
+    void* wstream = stream;
+    if (overlap) {
+      YB_CUDA(cudaEventRecord(net->side_fork, st));
+      YB_CUDA(cudaStreamWaitEvent(net->side_stream, net->side_fork, 0));
+      wstream = net->side_stream;
+      forked = true;
+    }
+    rc = yb_conv2d_wgrad(&d, ten_ptr2(net, L.in), net->act + L.dz_off, L.dz_ld, L.dz_dilated, gradp(net, L.g_w), wstream);
     if (rc) return rc;
     if (L.dgrad_parity) {
       for (int c = 0; c < 4; ++c) {
@@ -427,6 +447,10 @@ extern "C" int yb_net_train_backward(yb_net* net, const float* images, int first
       rc = conv_launch(dt, L.d_cout_pad, L.d_tmA, L.d_tmB, L.dparams, st);
       if (rc) return rc;
     }
+  }
+  if (forked) {
+    YB_CUDA(cudaEventRecord(net->side_join, net->side_stream));
+    YB_CUDA(cudaStreamWaitEvent(st, net->side_join, 0));
   }
   return YB_OK;
 }
