@@ -321,7 +321,7 @@ def latency_b1(pkg, S, iters=30):
     tg.sort()
     return {"ms_median": ts[len(ts) // 2], "ms_min": ts[0], "images_per_s": 1e3 / ts[len(ts) // 2],
             "cuda_graph_ms_median": tg[len(tg) // 2], "cuda_graph_ms_min": tg[0],
-            "what": "batch 1, %dx%d, forward + decode + NMS (yb_net_detect), device-resident input, 77 launches" % (S, S)}
+            "what": "batch 1, %dx%d, forward + decode + NMS (yb_net_detect), device-resident input, 76 launches" % (S, S)}
 
 
 def main():
