@@ -312,6 +312,14 @@ static int forward_layers_impl(yb_net* net, const float* images, float* fm1, flo
     if (rc) return rc;
   }
   const bool thin = opt("YB_THIN")[0] != '0';   // A/B switch for the thin-layer kernels
+  // detect path: heads 1 and 2 on a side stream (YB_HEAD_STREAM=0: everything on the caller's stream)
+  const bool head_overlap = det != nullptr && opt("YB_HEAD_STREAM")[0] != '0';
+  bool forked = false;
+  if (head_overlap && net->side_stream == nullptr) {
+    YB_CUDA(cudaStreamCreateWithFlags(&net->side_stream, cudaStreamNonBlocking));
+    YB_CUDA(cudaEventCreateWithFlags(&net->side_fork, cudaEventDisableTiming));
+    YB_CUDA(cudaEventCreateWithFlags(&net->side_join, cudaEventDisableTiming));
+  }
   // stem fused into Conv_1 (csrc/conv_halo.cu): layer 0's output is never written.  YB_STEM_FUSE=0: two launches.
   // (a layer range that stops at layer 0 then launches nothing: the stem no longer exists as a launch of its own)
   const bool fuse_stem = opt("YB_STEM_FUSE")[0] != '0' && net->layers.size() > 1 && net->layers[1].halo_ok &&
@@ -379,7 +387,17 @@ static int forward_layers_impl(yb_net* net, const float* images, float* fm1, flo
       if (det) {                                      // decode + candidate filter in the epilogue, no feature map
         ConvParams dp = L.det_params;
         dp.det = det[which];
-        int rc = conv_launch(net->dtype, L.det_cout_pad, L.det_tmA, L.det_tmB, dp, st);
+        // The first two heads are leaves of the graph (nothing but the NMS reads what they produce) and small (43 / 170
+        // tiles): they run on the plan's side stream beside the upsampling branch that continues on the caller's stream;
+        // the last head is on the critical path.  Every layer output has its own buffer, so the head's input stays intact.
+        cudaStream_t hs = st;
+        if (head_overlap && which < 2) {
+          YB_CUDA(cudaEventRecord(net->side_fork, st));
+          YB_CUDA(cudaStreamWaitEvent(net->side_stream, net->side_fork, 0));
+          hs = net->side_stream;
+          forked = true;
+        }
+        int rc = conv_launch(net->dtype, L.det_cout_pad, L.det_tmA, L.det_tmB, dp, hs);
         if (rc) return rc;
         continue;
       }
@@ -387,6 +405,10 @@ static int forward_layers_impl(yb_net* net, const float* images, float* fm1, flo
     }
     int rc = conv_launch(net->dtype, L.cout_pad, L.tmA, L.tmB, *p, st);
     if (rc) return rc;
+  }
+  if (forked) {
+    YB_CUDA(cudaEventRecord(net->side_join, net->side_stream));
+    YB_CUDA(cudaStreamWaitEvent(st, net->side_join, 0));
   }
   return YB_OK;
 }

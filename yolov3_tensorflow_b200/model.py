@@ -462,7 +462,7 @@ class yolov3(object):
         return boxes, ob, os_, ol, oi, cnt
 
     def detect_graphed(self, inputs, max_boxes=200, score_thresh=0.3, nms_thresh=0.45):
-        """detect_raw() replayed from a CUDA graph: the 77 launches of a detection step are captured
+        """detect_raw() replayed from a CUDA graph: the 76 launches of a detection step are captured
         once per (input shape, thresholds) and replayed with one cudaGraphLaunch — for the single-image path of
         test_single_image.py:48-62, where launch overhead, not the kernels, is the latency.  The input is copied into the
         graph's static buffer; the returned tensors are the graph's static outputs (overwritten by the next call)."""
