@@ -54,8 +54,8 @@ int ensure_smem_attr(DeviceOnce& once, const void* kernel, int bytes) {
 struct Opt { const char* key; char val[32]; };
 static Opt g_opts[] = {{"YB_CONV_MODE", ""}, {"YB_CONV_MC", ""}, {"YB_CONV_DBG", ""}, {"YB_CONV_BRES", ""},
                        {"YB_CONV_KPS", ""}, {"YB_CONV_EPI", ""}, {"YB_THIN", ""}, {"YB_STEM_DBG", ""},
-                       {"YB_STEM_WGRAD", ""}, {"YB_WGRAD_TP", ""}, {"YB_DGRAD_S2", ""}, {"YB_HEAD_FUSE", ""},
-                       {"YB_GRAPH", ""}, {"YB_BN_FUSE", ""}, {"YB_HALO", ""}, {"YB_CONV_EG", ""}, {"YB_STEM_FUSE", ""}, {"YB_STEM_WARPS", ""}, {"YB_STEM_EPIG", ""}, {"YB_HALO_DIRECT", ""},
+                       {"YB_STEM_WGRAD", ""}, {"YB_WGRAD_TP", ""}, {"YB_DGRAD_S2", ""},
+                       {"YB_HALO", ""}, {"YB_CONV_EG", ""}, {"YB_STEM_FUSE", ""}, {"YB_STEM_WARPS", ""}, {"YB_STEM_EPIG", ""}, {"YB_HALO_DIRECT", ""},
                        {"YB_BN_CPT", ""}, {"YB_BN_FIN", ""}, {"YB_PACK_MT", ""}, {"YB_WGRAD_EPI", ""}, {"YB_STEM_TRAIN", ""}, {"YB_WGRAD_STREAM", ""}, {"YB_STEM_SPLIT", ""}, {"YB_HEAD_STREAM", ""}};
 static std::once_flag g_opt_once;
 static void seed_opts() {
