@@ -181,6 +181,11 @@ int yb_pack_dgrad_weights_s2(const float* w_ohwi, int cout, int cin, int k_cout,
                              void* stream);
 int yb_conv2d_dgrad_s2(const yb_conv_desc* fwd, const void* dz, int dz_ld, int k_cout, const void* w_dgrad_s2,
                        const void* res, int res_ld, void* dx, int dx_ld, void* stream);
+/* Host-only: the split-K plan yb_conv2d_wgrad picks for a layer with `tiles` output tiles (tap groups x ci chunks x
+ * co tiles) over `num_pixel_blocks` 64-pixel blocks on `sms` SMs — the count that minimises
+ * waves x (blocks per CTA + epi_blocks); every block is covered exactly once. */
+int yb_wgrad_split_plan(long num_pixel_blocks, long tiles, int sms, int epi_blocks, long* splits,
+                        long* blocks_per_split);
 /* BN batch statistics -> scale/shift for bn_act_apply, saved mean/invstd for the backward, moving-stat update
  * (biased variance normalises, unbiased variance feeds the moving average; moving_* nullable). */
 int yb_bn_finalize(const float* sum, const float* sqsum, long count, int c, const float* gamma, const float* beta,

@@ -103,3 +103,30 @@ def test_config_optimizer_and_tf_variable_names():
     assert len(names) == 72 * 5 + 3 * 2 == 366
     assert names[0][2] == "yolov3/darknet53_body/Conv/weights:0" and names[-1][2] == "yolov3/yolov3_head/Conv_22/biases:0"
     assert names[5][2] == "yolov3/darknet53_body/Conv_1/weights:0" and names[1][2] == "yolov3/darknet53_body/Conv/BatchNorm/gamma:0"
+
+
+def test_wgrad_split_plan_one_wave_and_every_block_once():
+    """Host logic of yb_conv2d_wgrad (csrc/conv_wgrad.cu: wgrad_pick_splits): the split-K count minimises
+    waves x (pixel blocks per CTA + epilogue); every 64-pixel block is covered exactly once, no split is empty."""
+    import ctypes as C
+    from yolov3_tensorflow_b200 import _lib as L
+
+    def plan(num_kb, tiles, sms=148, epi=40):
+        s, k = C.c_long(), C.c_long()
+        L.check(L.lib.yb_wgrad_split_plan(num_kb, tiles, sms, epi, C.byref(s), C.byref(k)), "yb_wgrad_split_plan")
+        return s.value, k.value
+
+    # the training step's layers at batch 32 @416 (pixel blocks, tiles) -> (splits, blocks per split)
+    cases = {(21632, 1): (148, 147), (5408, 3): (49, 111), (1352, 6): (24, 57), (338, 24): (6, 57), (85, 96): (1, 85),
+             (85, 32): (4, 22), (1352, 2): (72, 19)}
+    for (num_kb, tiles), want in cases.items():
+        assert plan(num_kb, tiles) == want, (num_kb, tiles, plan(num_kb, tiles))
+    for num_kb, tiles in list(cases) + [(1, 1), (7, 400), (1000, 149), (64, 1)]:
+        s, k = plan(num_kb, tiles)
+        assert s >= 1 and (s - 1) * k < num_kb <= s * k
+        if tiles <= 148 and num_kb >= 148 // tiles:
+            assert tiles * s <= 148                 # one wave of one-CTA-per-SM blocks whenever the work allows it
+    # ignoring the epilogue cost (the first version's behaviour) splits further
+    assert plan(338, 24, epi=0)[0] > plan(338, 24)[0]
+    with pytest.raises(Exception):
+        plan(0, 1)

@@ -75,6 +75,7 @@ _SIGS = {
     "yb_conv2d_dgrad_s2": ([vp, vp, i32, i32, vp, vp, i32, vp, i32, vp], i32),
     "yb_bn_finalize": ([vp, vp, C.c_long, i32, vp, vp, f32, f32, vp, vp, vp, vp, vp, vp, vp], i32),
     "yb_bn_act_apply": ([vp, C.c_long, vp, vp, vp, C.c_long, vp, C.c_long, i32, i32, i32, i32, i32, i32, i32, vp], i32),
+    "yb_wgrad_split_plan": ([C.c_long, C.c_long, i32, i32, C.POINTER(C.c_long), C.POINTER(C.c_long)], i32),
     "yb_bn_stats_act_apply": ([vp, C.c_long, vp, vp, vp, vp, f32, f32, vp, vp, vp, vp, vp, vp, vp, C.c_long, vp, C.c_long,
                                i32, i32, i32, i32, i32, i32, i32, vp], i32),
     "yb_bn_bwd_reduce_workspace_bytes": ([C.POINTER(sz)], i32),

@@ -256,9 +256,38 @@ stem_wgrad_kernel(const float* __restrict__ x, const void* __restrict__ dz, int 
   for (int i = threadIdx.x; i < 32 * 27; i += 256) atomicAdd(dw + i, s_acc[i]);
 }
 
+// Pixel splits (split-K) of one wgrad launch.  One CTA is resident per SM (192 KB of stages), so the grid runs in waves
+// of `sms` CTAs, and every CTA ends with TP x BNW x 128 fp32 atomics that nothing overlaps: measured at ~40 pixel blocks'
+// worth of main loop (profiles/r02_g: the 26x26 256->512 layer ran 13 splits x 24 tiles = 312 CTAs = 2.1 waves of 26
+// blocks, 84 us against 36 us of tensor work).  Returns the split count that minimises waves x (blocks per CTA + epi).
+long wgrad_pick_splits(long num_kb, long tiles, long sms, long epi_blocks) {
+  long splits = 1;
+  double best = 1e30;
+  const long smax = num_kb < 4 * sms ? num_kb : 4 * sms;
+  for (long s = 1; s <= smax; ++s) {
+    const long kbs = (num_kb + s - 1) / s;
+    const long s_eff = (num_kb + kbs - 1) / kbs;
+    const long waves = (tiles * s_eff + sms - 1) / sms;
+    const double cost = (double)waves * ((double)kbs + (double)epi_blocks);
+    if (cost < best - 1e-9) { best = cost; splits = s_eff; }
+  }
+  return splits;
+}
+
 }  // namespace yb
 
 using namespace yb;
+
+// host-only view of the split selection (tests): tiles = tap groups x ci chunks x co tiles of the layer
+extern "C" int yb_wgrad_split_plan(long num_pixel_blocks, long tiles, int sms, int epi_blocks, long* splits,
+                                   long* blocks_per_split) {
+  YB_REQUIRE(num_pixel_blocks > 0 && tiles > 0 && sms > 0 && epi_blocks >= 0 && splits && blocks_per_split,
+             "wgrad_split_plan: bad argument");
+  const long s = wgrad_pick_splits(num_pixel_blocks, tiles, sms, epi_blocks);
+  *blocks_per_split = (num_pixel_blocks + s - 1) / s;
+  *splits = (num_pixel_blocks + *blocks_per_split - 1) / *blocks_per_split;
+  return YB_OK;
+}
 
 extern "C" int yb_conv2d_wgrad(const yb_conv_desc* d, const void* x, const void* dz, int dz_ld, int dz_dilated,
                                float* dw, void* stream) {
@@ -283,24 +312,7 @@ extern "C" int yb_conv2d_wgrad(const yb_conv_desc* d, const void* x, const void*
   const int tap_groups = taps / tp;
   const int co_tiles = ceil_div(d->cout, WG_BM);
   const long tiles = (long)tap_groups * p.n_chunks * co_tiles;
-  // Pixel splits (split-K).  One CTA is resident per SM (192 KB of stages), so the grid runs in waves of num_sms CTAs,
-  // and every CTA ends with TP x BNW x 128 fp32 atomics that nothing overlaps: measured at ~40 pixel blocks' worth of
-  // main loop (profiles/r02_g: the 26x26 256->512 layer ran 13 splits x 24 tiles = 312 CTAs = 2.1 waves of 26 blocks,
-  // 84 us against 36 us of tensor work).  Pick the split count that minimises waves x (blocks per CTA + epilogue).
-  long splits = 1;
-  {
-    const long sms = num_sms();
-    const double epi = (double)opt_int("YB_WGRAD_EPI", 40);
-    double best = 1e30;
-    const long smax = p.num_kb < 4 * sms ? p.num_kb : 4 * sms;
-    for (long s = 1; s <= smax; ++s) {
-      const long kbs = ceil_div(p.num_kb, s);
-      const long s_eff = ceil_div(p.num_kb, kbs);
-      const long waves = ceil_div(tiles * s_eff, sms);
-      const double cost = (double)waves * ((double)kbs + epi);
-      if (cost < best - 1e-9) { best = cost; splits = s_eff; }
-    }
-  }
+  long splits = wgrad_pick_splits(p.num_kb, tiles, num_sms(), opt_int("YB_WGRAD_EPI", 40));
   p.kb_per_split = ceil_div(p.num_kb, splits);
   splits = ceil_div(p.num_kb, p.kb_per_split);
   CUtensorMap tmA, tmB;
