@@ -39,14 +39,17 @@ FWD_GFLOP_416 = 65.864075264       # SURVEY.md Appendix A (2*MAC, 75 convs, per 
 STEM_GFLOP_416 = 2 * 416 * 416 * 32 * 27 / 1e9
 
 
-def make_bench_params(seed=2):
+def make_bench_params(seed=2, specs=None):
     """SURVEY.md §8d cfg 2 parameters (numpy, HWIO): Glorot-uniform, identity BN, head x8, conf bias -2.
-    Built from the ORACLE's layer walk so that the CPU arm never imports the product package (same table, same RNG
-    stream as yolov3.conv_table: tests/test_host_utils.py checks they agree)."""
-    from oracle import yolov3_oracle as O
+    `specs`: (cin, cout, k, stride, has_bn) per conv.  The CPU arm passes nothing and walks the ORACLE's layer list, so it
+    never imports the product package; the GPU arm passes the product's own yolov3.conv_table(), so it never imports
+    oracle/ (same table, same RNG stream: tests/test_bench_contract.py checks the two agree)."""
+    if specs is None:
+        from oracle import yolov3_oracle as O
+        specs = [(cin, cout, k, s, bn) for _scope, cin, cout, k, s, bn in O.conv_specs(CLASS_NUM)]
     rng = np.random.default_rng(seed)
     ps = []
-    for _scope, cin, cout, k, s, bn in O.conv_specs(CLASS_NUM):
+    for cin, cout, k, s, bn in specs:
         lim = np.sqrt(6.0 / (k * k * (cin + cout)))
         w = rng.uniform(-lim, lim, (k, k, cin, cout)).astype(np.float32)
         if bn:
@@ -379,7 +382,7 @@ def main():
     B, S = args.batch, args.size
     anchors = pkg.parse_anchors(os.path.join(ROOT, "yolov3_tensorflow_b200", "data", "yolo_anchors.txt"))
     model = pkg.yolov3(CLASS_NUM, anchors, dtype="fp16")
-    model.set_params(make_bench_params(), "HWIO")
+    model.set_params(make_bench_params(specs=pkg.yolov3.conv_table(CLASS_NUM)), "HWIO")
     x_host = torch.from_numpy(np.random.default_rng(2 + rank).random((B, S, S, 3), dtype=np.float32)).pin_memory()
     x_dev = x_host.cuda()
 

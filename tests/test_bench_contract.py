@@ -39,3 +39,7 @@ def test_bench_params_follow_the_products_conv_table():
     for p, (cin, cout, k, s, bn) in zip(ps, table):
         assert p["w"].shape == (k, k, cin, cout) and (("gamma" in p) == bool(bn))
     assert np.all(ps[58]["b"].reshape(3, -1)[:, 4] == -2.0)
+    # the GPU arm builds the same parameters from the product's table (it never imports oracle/): identical arrays
+    ps2 = bench.make_bench_params(specs=table)
+    for p, q in zip(ps, ps2):
+        assert p.keys() == q.keys() and all(np.array_equal(p[k], q[k]) for k in p)
